@@ -1,0 +1,353 @@
+"""Plan compiler, back end: parsed steps -> operations of the native library.
+
+Host logic only (numpy + ctypes struct filling); the arithmetic happens in libtnc_b200.so.
+What is decided here:
+
+  * the leaf table: where each leaf sits in the packed leaf blob and how its sliced bonds
+    are fixed per slice id (replaces `select(ind, bit).clone()`, artensor/simulation.py:110-113);
+  * hoisting: steps that depend on no sliced bond run once per execute call instead of once
+    per slice (the reference recomputes them for every slice, simulation.py:107-114);
+  * the physical mode order ("layout") of every intermediate, and which algorithm runs a step;
+  * arena offsets with liveness-based reuse (the reference lets torch allocate per einsum).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .plan import SchemeParser, Step, TensorInfo, SchemeError
+
+ALIGN = 1024
+
+
+class Arena:
+    """First-fit free-list allocator run at plan time; the high-water mark is the workspace."""
+
+    def __init__(self):
+        self.free: List[Tuple[int, int]] = []   # (offset, size), sorted, coalesced
+        self.top = 0
+        self.high = 0
+
+    def alloc(self, nbytes):
+        size = max(ALIGN, (nbytes + ALIGN - 1) // ALIGN * ALIGN)
+        for idx, (off, sz) in enumerate(self.free):
+            if sz >= size:
+                if sz == size:
+                    self.free.pop(idx)
+                else:
+                    self.free[idx] = (off + size, sz - size)
+                return off, size
+        # grow: extend a trailing free block if there is one
+        if self.free and self.free[-1][0] + self.free[-1][1] == self.top:
+            off, sz = self.free.pop()
+            self.top = off + size
+        else:
+            off = self.top
+            self.top += size
+        self.high = max(self.high, self.top)
+        return off, size
+
+    def release(self, off, size):
+        self.free.append((off, size))
+        self.free.sort()
+        merged = []
+        for o, s in self.free:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s)
+            else:
+                merged.append((o, s))
+        self.free = merged
+
+
+@dataclass
+class Buf:
+    """A tensor resident in the arena: `pos[mode]` is the bit position of each mode.
+    Buffers of slice-invariant data live in the ONCE region, everything else in the SLICE
+    region that starts where the ONCE region ends (bases are fixed after allocation)."""
+    region: int           # N.TNC_PHASE_ONCE or N.TNC_PHASE_SLICE
+    rel_offset: int
+    size: int
+    info: TensorInfo
+    pos: Dict[int, int]
+    is_leaf: bool
+    base: List[int] = None   # shared [once_base, slice_base], filled in at the end
+
+    @property
+    def dependent(self):
+        return self.region == N.TNC_PHASE_SLICE
+
+    def tensor(self):
+        return N.TncTensor(self.base[self.region] + self.rel_offset, self.info.rank, self.info.rows or 1)
+
+
+def logical_positions(info: TensorInfo):
+    r = info.rank
+    return {m: r - 1 - i for i, m in enumerate(info.modes)}
+
+
+@dataclass
+class PlanOptions:
+    tc_min_flops: float = float("inf")   # steps at or above this many flops use the tensor-core path
+    hoist: bool = True
+
+
+class ContractionPlan:
+    """A compiled scheme.  Immutable after construction; execute() is stream-ordered."""
+
+    def __init__(self, scheme, leaf_shapes: Dict[int, Tuple[int, ...]], sparse: bool, *,
+                 slicing_bonds=(), slicing_indices=None, dtype="c64", options: Optional[PlanOptions] = None,
+                 build_native=True):
+        self.options = options or PlanOptions()
+        self.sparse = sparse
+        self.dtype = {"c64": N.TNC_C64, "c32": N.TNC_C32}[dtype]
+        self.elem_bytes = 8 if self.dtype == N.TNC_C64 else 4
+        self.slicing_bonds = list(slicing_bonds)
+        self.n_sliced = len(self.slicing_bonds)
+        if self.n_sliced > 62:
+            raise SchemeError(f"{self.n_sliced} sliced bonds: slice ids do not fit 63 bits")
+        slicing_indices = slicing_indices or {}
+        # per leaf: {dim (un-sliced tensor dim): bond index x}
+        self.leaf_sliced: Dict[int, Dict[int, int]] = {}
+        for x, bond in enumerate(self.slicing_bonds):
+            for tid, dim in slicing_indices[bond]:
+                self.leaf_sliced.setdefault(int(tid), {})[int(dim)] = x
+        self.full_leaf_shapes = {int(k): tuple(int(e) for e in v) for k, v in leaf_shapes.items()}
+        sliced_shapes = {}
+        for tid, shp in self.full_leaf_shapes.items():
+            dims = self.leaf_sliced.get(tid, {})
+            for d in dims:
+                if d < 0 or d >= len(shp) or shp[d] != 2:
+                    raise SchemeError(f"leaf {tid}: sliced dim {d} invalid for shape {shp}")
+            sliced_shapes[tid] = tuple(e for d, e in enumerate(shp) if d not in dims)
+        parser = SchemeParser(sliced_shapes, sparse)
+        self.steps: List[Step] = parser.parse(scheme)
+        if not self.steps:
+            raise SchemeError("empty scheme")
+        self.leaf_info = parser.leaf_info
+        self.result_info = self.steps[-1].c
+        self.result_slot = self.steps[-1].i
+        self.out_shape = tuple(([self.result_info.rows] if self.result_info.rows is not None else []) +
+                               [2] * self.result_info.rank)
+        self._lib = None
+        self._handle = None
+        self._build = build_native
+        self._lower()
+
+    # ------------------------------------------------------------------ lowering
+    def _lower(self):
+        arenas = {N.TNC_PHASE_ONCE: Arena(), N.TNC_PHASE_SLICE: Arena()}
+        base = [0, 0]
+        # leaf blob layout (elements), in ascending tensor id order over the leaves the scheme uses
+        self.leaf_order = sorted(self.leaf_info)
+        self.leaf_src_offset = {}
+        off = 0
+        for tid in self.leaf_order:
+            self.leaf_src_offset[tid] = off
+            off += int(np.prod(self.full_leaf_shapes[tid], dtype=np.int64)) if self.full_leaf_shapes[tid] else 1
+        self.leaf_blob_elems = off
+
+        bufs: Dict[int, Buf] = {}
+        leaf_bufs = {N.TNC_PHASE_ONCE: [], N.TNC_PHASE_SLICE: []}
+        for tid in self.leaf_order:
+            info = self.leaf_info[tid]
+            region = N.TNC_PHASE_SLICE if (tid in self.leaf_sliced or not self.options.hoist) else N.TNC_PHASE_ONCE
+            o, sz = arenas[region].alloc(info.numel * self.elem_bytes)
+            buf = Buf(region, o, sz, info, logical_positions(info), True, base)
+            bufs[tid] = buf
+            leaf_bufs[region].append((tid, buf))
+
+        pending = []        # (phase, step, A, B, C, algo) in scheme order
+        self.step_phase, self.step_algo = [], []
+        for st in self.steps:
+            A, B = bufs[st.i], bufs[st.j]
+            phase = N.TNC_PHASE_SLICE if (A.dependent or B.dependent) else N.TNC_PHASE_ONCE
+            cpos = self._choose_layout(st, A, B)
+            o, sz = arenas[phase].alloc(st.c.numel * self.elem_bytes)
+            Cb = Buf(phase, o, sz, st.c, cpos, False, base)
+            algo = N.TNC_ALGO_TC if st.flops >= self.options.tc_min_flops else N.TNC_ALGO_SIMT
+            pending.append((phase, st, A, B, Cb, algo))
+            self.step_phase.append(phase)
+            self.step_algo.append(algo)
+            for old in (A, B):
+                # a buffer dies with its consumer unless it is a leaf (reloaded / kept) or a
+                # slice-invariant result consumed inside the slice loop (needed by every slice)
+                if not old.is_leaf and old.region == phase:
+                    arenas[phase].release(old.rel_offset, old.size)
+            bufs[st.i] = Cb
+            del bufs[st.j]
+        base[N.TNC_PHASE_ONCE] = 0
+        base[N.TNC_PHASE_SLICE] = arenas[N.TNC_PHASE_ONCE].high
+        self.workspace_bytes = max(arenas[N.TNC_PHASE_ONCE].high + arenas[N.TNC_PHASE_SLICE].high, ALIGN)
+
+        ops = {N.TNC_PHASE_ONCE: [], N.TNC_PHASE_SLICE: []}
+        for phase in ops:
+            if leaf_bufs[phase]:
+                ops[phase].append(("leaves", [self._leaf_record(tid, b) for tid, b in leaf_bufs[phase]]))
+        self.tables: List[np.ndarray] = []
+        for phase, st, A, B, Cb, algo in pending:
+            ops[phase].append(("einsum", self._einsum_record(st, A, B, Cb, algo)))
+        final = bufs[self.result_slot]
+        acc = N.TncAccum()
+        acc.src = final.tensor()
+        r = final.info.rank
+        out_pos = [0] * r
+        for i, m in enumerate(final.info.modes):
+            out_pos[final.pos[m]] = r - 1 - i
+        acc.out_pos = N.bits(out_pos)
+        # the accumulate runs per slice even when nothing is sliced (one "slice")
+        ops[N.TNC_PHASE_SLICE].append(("accum", acc))
+        self.ops = ops
+        if self._build:
+            self._build_native(ops)
+
+    def _leaf_record(self, tid, buf: Buf):
+        shp = self.full_leaf_shapes[tid]
+        info = buf.info
+        has_row = info.rows is not None
+        nbits = len(shp) - (1 if has_row else 0)
+        sliced = self.leaf_sliced.get(tid, {})
+        rec = N.TncLeaf()
+        rec.src_offset = self.leaf_src_offset[tid]
+        rec.dst = buf.tensor()
+        rec.src_rank = nbits
+        rec.n_sliced = len(sliced)
+        if len(sliced) > N.TNC_MAX_SLICED:
+            raise SchemeError(f"leaf {tid} carries {len(sliced)} sliced bonds (max {N.TNC_MAX_SLICED})")
+        sp, sb = [], []
+        keep_dims = []
+        for d in range(len(shp)):
+            if has_row and d == 0:
+                if d in sliced:
+                    raise SchemeError(f"leaf {tid}: the row mode cannot be sliced")
+                continue
+            bitdim = d - (1 if has_row else 0)
+            srcpos = nbits - 1 - bitdim
+            if d in sliced:
+                sp.append(srcpos)
+                sb.append(sliced[d])
+            else:
+                keep_dims.append(srcpos)
+        rec.sliced_pos = N.Sliced(*sp) if sp else N.Sliced()
+        rec.sliced_bond = N.Sliced(*sb) if sb else N.Sliced()
+        # kept dims in logical order are info.modes; destination position comes from buf.pos
+        keep_pos = [0] * info.rank
+        for mode, srcpos in zip(info.modes, keep_dims):
+            keep_pos[buf.pos[mode]] = srcpos
+        rec.keep_pos = N.bits(keep_pos)
+        return rec
+
+    def _choose_layout(self, st: Step, A: Buf, B: Buf):
+        """Physical mode order of the step's output.  v1: the reference's logical order."""
+        return logical_positions(st.c)
+
+    def _table(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.int32)
+        self.tables.append(arr)
+        return len(self.tables) - 1
+
+    def _rows_mode(self, r, nb):
+        if r is None:
+            return N.TNC_ROWS_NONE
+        if len(r) == nb and np.array_equal(r, np.arange(nb)):
+            return N.TNC_ROWS_IDENTITY
+        return self._table(r)
+
+    def _einsum_record(self, st: Step, A: Buf, B: Buf, Cb: Buf, algo):
+        e = N.TncEinsum()
+        e.a, e.b, e.c = A.tensor(), B.tensor(), Cb.tensor()
+        e.nb = st.nb
+        e.rows_a = self._rows_mode(st.ra, st.nb)
+        e.rows_b = self._rows_mode(st.rb, st.nb)
+        e.n_m, e.n_n, e.n_k, e.n_h = len(st.m_modes), len(st.n_modes), len(st.k_modes), len(st.h_modes)
+        e.m_a = N.bits(A.pos[m] for m in st.m_modes)
+        e.m_c = N.bits(Cb.pos[m] for m in st.m_modes)
+        e.n_b = N.bits(B.pos[m] for m in st.n_modes)
+        e.n_c = N.bits(Cb.pos[m] for m in st.n_modes)
+        e.k_a = N.bits(A.pos[m] for m in st.k_modes)
+        e.k_b = N.bits(B.pos[m] for m in st.k_modes_b)
+        e.h_a = N.bits(A.pos[m] for m in st.h_modes)
+        e.h_b = N.bits(B.pos[m] for m in st.h_modes_b)
+        e.h_c = N.bits(Cb.pos[m] for m in st.h_modes)
+        e.algo = algo
+        e.flags = 0
+        return e
+
+    def _build_native(self, ops):
+        lib = N.load()
+        handle = C.c_void_p()
+        N.check(lib.tnc_plan_create(self.dtype, self.n_sliced, C.byref(handle)))
+        self._lib, self._handle = lib, handle
+        try:
+            for t in self.tables:
+                tid = C.c_int32()
+                N.check(lib.tnc_plan_add_table(handle, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t), C.byref(tid)))
+            for phase in (N.TNC_PHASE_ONCE, N.TNC_PHASE_SLICE):
+                for kind, rec in ops[phase]:
+                    if kind == "leaves":
+                        arr = (N.TncLeaf * len(rec))(*rec)
+                        N.check(lib.tnc_plan_add_leaves(handle, phase, arr, len(rec)))
+                    elif kind == "einsum":
+                        N.check(lib.tnc_plan_add_einsum(handle, phase, C.byref(rec)))
+                    elif kind == "permute":
+                        N.check(lib.tnc_plan_add_permute(handle, phase, C.byref(rec)))
+                    elif kind == "accum":
+                        N.check(lib.tnc_plan_add_accum(handle, phase, C.byref(rec)))
+            N.check(lib.tnc_plan_finalize(handle, self.workspace_bytes))
+        except Exception:
+            lib.tnc_plan_destroy(handle)
+            self._handle = None
+            raise
+
+    def __del__(self):
+        if getattr(self, "_handle", None) is not None and self._lib is not None:
+            self._lib.tnc_plan_destroy(self._handle)
+            self._handle = None
+
+    # ------------------------------------------------------------------ host-side helpers
+    @property
+    def n_slices(self):
+        return 1 << self.n_sliced
+
+    def pack_leaves(self, leaves, out=None):
+        """Flatten the leaves the scheme uses into one contiguous complex array (the leaf blob).
+        `leaves` is a list or dict of torch tensors as the reference takes them
+        (simulation.py:92-99 list, :168-171 dict)."""
+        import torch
+        parts = []
+        for tid in self.leaf_order:
+            t = leaves[tid]
+            if tuple(t.shape) != self.full_leaf_shapes[tid]:
+                raise SchemeError(f"leaf {tid}: shape {tuple(t.shape)} differs from the planned {self.full_leaf_shapes[tid]}")
+            parts.append(t.reshape(-1))
+        blob = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
+        if out is not None:
+            out.copy_(blob)
+            return out
+        return blob
+
+    def execute(self, leaf_blob, out, slice_begin, slice_end, workspace, stream_ptr):
+        """Enqueue the contraction of slices [slice_begin, slice_end) on the given stream;
+        `out` (complex64, logical result order) is accumulated into."""
+        rc = self._lib.tnc_plan_execute(self._handle, leaf_blob.data_ptr(), int(slice_begin), int(slice_end),
+                                        out.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                        stream_ptr)
+        N.check(rc)
+
+    @property
+    def last_launches(self):
+        return int(self._lib.tnc_plan_last_launches(self._handle))
+
+    def work_summary(self):
+        """Executed vs reference-equivalent work per slice."""
+        tot_f = tot_b = dep_f = dep_b = 0
+        for st, ph in zip(self.steps, self.step_phase):
+            tot_f += st.flops
+            tot_b += st.bytes_c64
+            if ph == N.TNC_PHASE_SLICE:
+                dep_f += st.flops
+                dep_b += st.bytes_c64
+        return {"steps": len(self.steps), "ref_flops_per_slice": tot_f, "ref_bytes_per_slice": tot_b,
+                "exec_flops_per_slice": dep_f, "exec_bytes_per_slice": dep_b,
+                "hoisted_steps": sum(1 for p in self.step_phase if p == N.TNC_PHASE_ONCE)}

@@ -1,0 +1,194 @@
+// CUDA-core kernels of tnc_b200: the generic bit-einsum (any shape; used for the many tiny
+// steps of a scheme and as the always-available algorithm), leaf slicing, the bit-permutation
+// copy and the slice accumulator.  HBM-bound byte movers: coalesced, vectorised where the
+// permutation allows, grids sized in multiples of the SM count.
+#include <cuda_fp16.h>
+
+#include "tnc_internal.h"
+
+namespace tnc {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+inline int grid_for(int64_t work_items, int per_sm = 8) {
+    int64_t blocks = (work_items + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;          // grid-stride beyond: a multiple of the SM count
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T> struct Cplx;
+template <> struct Cplx<float2> {
+    static __device__ __forceinline__ float2 load(const float2* p) { return *p; }
+    static __device__ __forceinline__ void store(float2* p, float2 v) { *p = v; }
+};
+template <> struct Cplx<__half2> {
+    static __device__ __forceinline__ float2 load(const __half2* p) { return __half22float2(*p); }
+    static __device__ __forceinline__ void store(__half2* p, float2 v) { *p = __float22half2_rn(v); }
+};
+
+// ------------------------------------------------------------------ generic einsum
+// One thread per output element.  The output index is split into its bits; every bit that
+// also addresses A (m/h modes) or B (n/h modes) is moved to its position there.  The
+// contracted index walks two precomputed offset tables (deposit of k into A / B positions).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) simt_einsum_kernel(SimtEinsumParams p) {
+    const T* __restrict__ A = (const T*)p.a;
+    const T* __restrict__ B = (const T*)p.b;
+    T* __restrict__ C = (T*)p.c;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint32_t cmask = p.rank_c >= 32 ? 0xffffffffu : ((1u << p.rank_c) - 1u);
+    const uint32_t nk = 1u << p.kb;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += stride) {
+        const int64_t row = e >> p.rank_c;
+        const uint32_t cb = (uint32_t)e & cmask;
+        uint32_t oa = 0, ob = 0;
+        for (int q = 0; q < p.rank_c; ++q) {
+            const uint32_t bit = (cb >> q) & 1u;
+            const int pa = p.c2a[q], pb = p.c2b[q];
+            if (pa >= 0) oa |= bit << pa;
+            if (pb >= 0) ob |= bit << pb;
+        }
+        int64_t ra = 0, rb = 0;
+        if (p.rows_mode_a == TNC_ROWS_IDENTITY) ra = row;
+        else if (p.rows_mode_a >= 0) ra = p.rows_a[row];
+        if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = row;
+        else if (p.rows_mode_b >= 0) rb = p.rows_b[row];
+        const T* __restrict__ a = A + (ra << p.rank_a) + oa;
+        const T* __restrict__ b = B + (rb << p.rank_b) + ob;
+        float cr = 0.f, ci = 0.f;
+        for (uint32_t k = 0; k < nk; ++k) {
+            const float2 x = Cplx<T>::load(a + p.koff_a[k]);
+            const float2 y = Cplx<T>::load(b + p.koff_b[k]);
+            cr = fmaf(x.x, y.x, cr);
+            cr = fmaf(-x.y, y.y, cr);
+            ci = fmaf(x.x, y.y, ci);
+            ci = fmaf(x.y, y.x, ci);
+        }
+        Cplx<T>::store(C + e, make_float2(cr, ci));
+    }
+}
+
+// ------------------------------------------------------------------ leaf slicing
+// One block per leaf; leaves are tiny (rank <= ~6).  dst[r][e] = src[r][deposit(e) | fixed].
+template <typename T>
+__global__ void __launch_bounds__(128) leaf_gather_kernel(const LeafDev* __restrict__ leaves,
+                                                          const T* __restrict__ blob, char* arena,
+                                                          uint64_t slice_id) {
+    const LeafDev L = leaves[blockIdx.x];
+    T* dst = (T*)(arena + L.dst_offset);
+    uint32_t fixed = 0;
+    for (int s = 0; s < L.n_sliced; ++s)
+        fixed |= (uint32_t)((slice_id >> L.sliced_shift[s]) & 1ull) << L.sliced_pos[s];
+    const int64_t total = (int64_t)L.dst_rows << L.dst_rank;
+    const uint32_t mask = (1u << L.dst_rank) - 1u;
+    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+        const int64_t row = e >> L.dst_rank;
+        const uint32_t eb = (uint32_t)e & mask;
+        uint32_t so = fixed;
+        for (int q = 0; q < L.dst_rank; ++q) so |= ((eb >> q) & 1u) << L.keep_pos[q];
+        dst[e] = blob[L.src_offset + (row << L.src_rank) + so];
+    }
+}
+
+// ------------------------------------------------------------------ bit permutation (v1)
+// Thread per destination element, grid-stride; destination writes are fully coalesced, the
+// source side is coalesced for as many low positions as the permutation keeps in place.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) permute_kernel(PermuteParams p) {
+    const T* __restrict__ src = (const T*)p.src;
+    T* __restrict__ dst = (T*)p.dst;
+    const int64_t total = p.rows << p.rank;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t mask = (1ull << p.rank) - 1ull;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint64_t q = (uint64_t)e & mask;
+        uint64_t s = 0;
+        for (int i = 0; i < p.rank; ++i) s |= ((q >> i) & 1ull) << p.perm[i];
+        dst[e] = src[((e >> p.rank) << p.rank) + (int64_t)s];
+    }
+}
+
+// ------------------------------------------------------------------ accumulate
+template <typename T>
+__global__ void __launch_bounds__(kThreads) accum_kernel(AccumParams p) {
+    const T* __restrict__ src = (const T*)p.src;
+    float2* __restrict__ out = (float2*)p.out;
+    const int64_t total = p.rows << p.rank;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t mask = (1ull << p.rank) - 1ull;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint64_t q = (uint64_t)e & mask;
+        uint64_t d = 0;
+        for (int i = 0; i < p.rank; ++i) d |= ((q >> i) & 1ull) << p.out_pos[i];
+        const float2 v = Cplx<T>::load(src + e);
+        float2* o = out + ((e >> p.rank) << p.rank) + (int64_t)d;
+        float2 cur = *o;
+        cur.x += v.x;
+        cur.y += v.y;
+        *o = cur;
+    }
+}
+
+}  // namespace
+
+int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
+    if (p.total <= 0) return TNC_OK;
+    const int grid = grid_for(p.total);
+    if (dtype == TNC_C64) simt_einsum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
+    else simt_einsum_kernel<__half2><<<grid, kThreads, 0, s>>>(p);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+int launch_leaf_gather(const LeafDev* dev_leaves, int n, int max_elems, const void* blob,
+                       void* arena, uint64_t slice_id, int dtype, cudaStream_t s) {
+    (void)max_elems;
+    if (n <= 0) return TNC_OK;
+    if (dtype == TNC_C64)
+        leaf_gather_kernel<float2><<<n, 128, 0, s>>>(dev_leaves, (const float2*)blob, (char*)arena, slice_id);
+    else
+        leaf_gather_kernel<__half2><<<n, 128, 0, s>>>(dev_leaves, (const __half2*)blob, (char*)arena, slice_id);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+int launch_permute(const PermuteParams& p, int elem_bytes, cudaStream_t s) {
+    const int64_t total = p.rows << p.rank;
+    if (total <= 0) return TNC_OK;
+    const int grid = grid_for(total);
+    if (elem_bytes == 8) permute_kernel<float2><<<grid, kThreads, 0, s>>>(p);
+    else if (elem_bytes == 4) permute_kernel<float><<<grid, kThreads, 0, s>>>(p);
+    else {
+        set_error("permute: elem_bytes must be 4 or 8, got %d", elem_bytes);
+        return TNC_ERR_INVALID;
+    }
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+int launch_accum(const AccumParams& p, int dtype, cudaStream_t s) {
+    const int64_t total = p.rows << p.rank;
+    if (total <= 0) return TNC_OK;
+    const int grid = grid_for(total);
+    if (dtype == TNC_C64) accum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
+    else accum_kernel<__half2><<<grid, kThreads, 0, s>>>(p);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+}  // namespace tnc

@@ -1,0 +1,479 @@
+// Plan objects and the execute loop of tnc_b200 (C ABI in include/tnc_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <memory>
+
+#include "tnc_internal.h"
+#include "tc_gemm.h"
+
+namespace tnc {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return TNC_ERR_CUDA;
+}
+
+enum OpKind { OP_LEAVES = 0, OP_EINSUM = 1, OP_PERMUTE = 2, OP_ACCUM = 3 };
+
+struct Op {
+    int kind = 0;
+    tnc_einsum e{};
+    tnc_permute p{};
+    tnc_accum a{};
+    int leaf_begin = 0, leaf_count = 0;
+    int64_t koff_a = -1, koff_b = -1;     // byte offsets into the device blob
+    std::shared_ptr<TcGemmOp> tc;         // tensor-core lowering, when algo == TNC_ALGO_TC
+};
+
+}  // namespace tnc
+
+using namespace tnc;
+
+struct tnc_plan {
+    int dtype = TNC_C64;
+    int n_sliced = 0;
+    bool finalized = false;
+    std::vector<std::vector<int32_t>> tables;
+    std::vector<int64_t> table_off;        // byte offsets into the device blob
+    std::vector<Op> ops[2];
+    std::vector<LeafDev> leaves;
+    int64_t leaves_off = 0;
+    char* dev_blob = nullptr;
+    int64_t workspace_bytes = 0;
+    int64_t last_launches = 0;
+    int elem_bytes() const { return dtype == TNC_C64 ? 8 : 4; }
+};
+
+namespace {
+
+bool check_tensor(const tnc_plan* pl, const tnc_tensor& t, const char* what) {
+    if (t.rank < 0 || t.rank > TNC_MAX_BITS - 1 || t.rows < 1 || t.offset < 0 || (t.offset & 255)) {
+        set_error("%s: bad tensor (offset=%lld rank=%d rows=%d)", what, (long long)t.offset, t.rank, t.rows);
+        return false;
+    }
+    (void)pl;
+    return true;
+}
+
+bool check_positions(const int8_t* pos, int n, int rank, uint64_t& seen, const char* what) {
+    for (int i = 0; i < n; ++i) {
+        if (pos[i] < 0 || pos[i] >= rank || ((seen >> pos[i]) & 1ull)) {
+            set_error("%s: bit position %d invalid or repeated (rank %d)", what, (int)pos[i], rank);
+            return false;
+        }
+        seen |= 1ull << pos[i];
+    }
+    return true;
+}
+
+int64_t tensor_bytes(const tnc_plan* pl, const tnc_tensor& t) {
+    return ((int64_t)t.rows << t.rank) * pl->elem_bytes();
+}
+
+int phase_ok(int phase) { return phase == TNC_PHASE_ONCE || phase == TNC_PHASE_SLICE; }
+
+}  // namespace
+
+extern "C" {
+
+int tnc_abi_version(void) { return TNC_ABI_VERSION; }
+
+const char* tnc_last_error(void) { return g_error.c_str(); }
+
+int tnc_plan_create(int32_t dtype, int32_t n_sliced_bonds, tnc_plan** out) {
+    if (!out || (dtype != TNC_C64 && dtype != TNC_C32) || n_sliced_bonds < 0 || n_sliced_bonds > 63) {
+        set_error("plan_create: bad arguments (dtype=%d, sliced bonds=%d)", dtype, n_sliced_bonds);
+        return TNC_ERR_INVALID;
+    }
+    tnc_plan* p = new tnc_plan();
+    p->dtype = dtype;
+    p->n_sliced = n_sliced_bonds;
+    *out = p;
+    return TNC_OK;
+}
+
+void tnc_plan_destroy(tnc_plan* plan) {
+    if (!plan) return;
+    for (int ph = 0; ph < 2; ++ph)
+        for (auto& op : plan->ops[ph]) op.tc.reset();
+    if (plan->dev_blob) cudaFree(plan->dev_blob);
+    delete plan;
+}
+
+int tnc_plan_add_table(tnc_plan* plan, const int32_t* data, int64_t n, int32_t* table_id) {
+    if (!plan || plan->finalized || !data || n < 0 || !table_id) {
+        set_error("add_table: bad arguments or plan already finalized");
+        return plan && plan->finalized ? TNC_ERR_STATE : TNC_ERR_INVALID;
+    }
+    plan->tables.emplace_back(data, data + n);
+    *table_id = (int32_t)plan->tables.size() - 1;
+    return TNC_OK;
+}
+
+int tnc_plan_add_leaves(tnc_plan* plan, int32_t phase, const tnc_leaf* leaves, int32_t n) {
+    if (!plan || plan->finalized || !phase_ok(phase) || n < 0 || (n > 0 && !leaves)) {
+        set_error("add_leaves: bad arguments");
+        return TNC_ERR_INVALID;
+    }
+    Op op;
+    op.kind = OP_LEAVES;
+    op.leaf_begin = (int)plan->leaves.size();
+    op.leaf_count = n;
+    for (int i = 0; i < n; ++i) {
+        const tnc_leaf& L = leaves[i];
+        if (!check_tensor(plan, L.dst, "leaf")) return TNC_ERR_INVALID;
+        if (L.n_sliced < 0 || L.n_sliced > TNC_MAX_SLICED || L.src_rank != L.dst.rank + L.n_sliced ||
+            L.src_offset < 0) {
+            set_error("leaf %d: inconsistent ranks (src %d, dst %d, sliced %d)", i, L.src_rank, L.dst.rank, L.n_sliced);
+            return TNC_ERR_INVALID;
+        }
+        uint64_t seen = 0;
+        if (!check_positions(L.keep_pos, L.dst.rank, L.src_rank, seen, "leaf keep_pos")) return TNC_ERR_INVALID;
+        if (!check_positions(L.sliced_pos, L.n_sliced, L.src_rank, seen, "leaf sliced_pos")) return TNC_ERR_INVALID;
+        LeafDev d{};
+        d.src_offset = L.src_offset;
+        d.dst_offset = L.dst.offset;
+        d.dst_rank = L.dst.rank;
+        d.dst_rows = L.dst.rows;
+        d.src_rank = L.src_rank;
+        d.n_sliced = L.n_sliced;
+        for (int s = 0; s < L.n_sliced; ++s) {
+            if (L.sliced_bond[s] < 0 || L.sliced_bond[s] >= plan->n_sliced) {
+                set_error("leaf %d: sliced bond index %d out of range", i, (int)L.sliced_bond[s]);
+                return TNC_ERR_INVALID;
+            }
+            if (phase == TNC_PHASE_ONCE) {
+                set_error("leaf %d: a sliced leaf cannot be loaded in the ONCE phase", i);
+                return TNC_ERR_INVALID;
+            }
+            d.sliced_pos[s] = L.sliced_pos[s];
+            d.sliced_shift[s] = (int8_t)(plan->n_sliced - 1 - L.sliced_bond[s]);
+        }
+        memcpy(d.keep_pos, L.keep_pos, sizeof(d.keep_pos));
+        plan->leaves.push_back(d);
+    }
+    plan->ops[phase].push_back(op);
+    return TNC_OK;
+}
+
+int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* e) {
+    if (!plan || plan->finalized || !phase_ok(phase) || !e) {
+        set_error("add_einsum: bad arguments");
+        return TNC_ERR_INVALID;
+    }
+    if (!check_tensor(plan, e->a, "einsum A") || !check_tensor(plan, e->b, "einsum B") ||
+        !check_tensor(plan, e->c, "einsum C"))
+        return TNC_ERR_INVALID;
+    if (e->n_m < 0 || e->n_n < 0 || e->n_k < 0 || e->n_h < 0 || e->n_m + e->n_k + e->n_h != e->a.rank ||
+        e->n_n + e->n_k + e->n_h != e->b.rank || e->n_m + e->n_n + e->n_h != e->c.rank) {
+        set_error("einsum: mode counts (m=%d n=%d k=%d h=%d) do not match ranks (%d, %d, %d)", e->n_m, e->n_n,
+                  e->n_k, e->n_h, e->a.rank, e->b.rank, e->c.rank);
+        return TNC_ERR_INVALID;
+    }
+    if (e->n_k > 26) {
+        set_error("einsum: %d contracted bits exceed the supported 26", e->n_k);
+        return TNC_ERR_UNSUPPORTED;
+    }
+    uint64_t sa = 0, sb = 0, sc = 0;
+    if (!check_positions(e->m_a, e->n_m, e->a.rank, sa, "einsum m_a") ||
+        !check_positions(e->k_a, e->n_k, e->a.rank, sa, "einsum k_a") ||
+        !check_positions(e->h_a, e->n_h, e->a.rank, sa, "einsum h_a") ||
+        !check_positions(e->n_b, e->n_n, e->b.rank, sb, "einsum n_b") ||
+        !check_positions(e->k_b, e->n_k, e->b.rank, sb, "einsum k_b") ||
+        !check_positions(e->h_b, e->n_h, e->b.rank, sb, "einsum h_b") ||
+        !check_positions(e->m_c, e->n_m, e->c.rank, sc, "einsum m_c") ||
+        !check_positions(e->n_c, e->n_n, e->c.rank, sc, "einsum n_c") ||
+        !check_positions(e->h_c, e->n_h, e->c.rank, sc, "einsum h_c"))
+        return TNC_ERR_INVALID;
+    if (e->nb != e->c.rows) {
+        set_error("einsum: nb (%d) != c.rows (%d)", e->nb, e->c.rows);
+        return TNC_ERR_INVALID;
+    }
+    const int32_t modes[2] = {e->rows_a, e->rows_b};
+    const tnc_tensor* ops[2] = {&e->a, &e->b};
+    for (int s = 0; s < 2; ++s) {
+        const int32_t m = modes[s];
+        if (m == TNC_ROWS_NONE) continue;
+        if (m == TNC_ROWS_IDENTITY) {
+            if (ops[s]->rows < e->nb) {
+                set_error("einsum: identity rows but operand has %d rows < nb %d", ops[s]->rows, e->nb);
+                return TNC_ERR_INVALID;
+            }
+            continue;
+        }
+        if (m < 0 || m >= (int)plan->tables.size() || (int64_t)plan->tables[m].size() < e->nb) {
+            set_error("einsum: row table %d missing or shorter than nb=%d", m, e->nb);
+            return TNC_ERR_INVALID;
+        }
+        for (int i = 0; i < e->nb; ++i)
+            if (plan->tables[m][i] < 0 || plan->tables[m][i] >= ops[s]->rows) {
+                set_error("einsum: row table %d entry %d = %d out of range (rows %d)", m, i, plan->tables[m][i],
+                          ops[s]->rows);
+                return TNC_ERR_INVALID;
+            }
+    }
+    if (e->algo != TNC_ALGO_SIMT && e->algo != TNC_ALGO_TC) {
+        set_error("einsum: unknown algo %d", e->algo);
+        return TNC_ERR_INVALID;
+    }
+    Op op;
+    op.kind = OP_EINSUM;
+    op.e = *e;
+    plan->ops[phase].push_back(op);
+    return TNC_OK;
+}
+
+int tnc_plan_add_permute(tnc_plan* plan, int32_t phase, const tnc_permute* p) {
+    if (!plan || plan->finalized || !phase_ok(phase) || !p) {
+        set_error("add_permute: bad arguments");
+        return TNC_ERR_INVALID;
+    }
+    if (!check_tensor(plan, p->src, "permute src") || !check_tensor(plan, p->dst, "permute dst")) return TNC_ERR_INVALID;
+    if (p->src.rank != p->dst.rank || p->src.rows != p->dst.rows) {
+        set_error("permute: src and dst shapes differ");
+        return TNC_ERR_INVALID;
+    }
+    uint64_t seen = 0;
+    if (!check_positions(p->perm, p->src.rank, p->src.rank, seen, "permute perm")) return TNC_ERR_INVALID;
+    Op op;
+    op.kind = OP_PERMUTE;
+    op.p = *p;
+    plan->ops[phase].push_back(op);
+    return TNC_OK;
+}
+
+int tnc_plan_add_accum(tnc_plan* plan, int32_t phase, const tnc_accum* a) {
+    if (!plan || plan->finalized || !phase_ok(phase) || !a) {
+        set_error("add_accum: bad arguments");
+        return TNC_ERR_INVALID;
+    }
+    if (!check_tensor(plan, a->src, "accum src")) return TNC_ERR_INVALID;
+    uint64_t seen = 0;
+    if (!check_positions(a->out_pos, a->src.rank, a->src.rank, seen, "accum out_pos")) return TNC_ERR_INVALID;
+    Op op;
+    op.kind = OP_ACCUM;
+    op.a = *a;
+    plan->ops[phase].push_back(op);
+    return TNC_OK;
+}
+
+int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
+    if (!plan || plan->finalized || workspace_bytes < 0) {
+        set_error("finalize: bad arguments or already finalized");
+        return plan && plan->finalized ? TNC_ERR_STATE : TNC_ERR_INVALID;
+    }
+    // every tensor must fit the declared arena
+    auto fits = [&](const tnc_tensor& t) { return t.offset + tensor_bytes(plan, t) <= workspace_bytes; };
+    for (int ph = 0; ph < 2; ++ph)
+        for (auto& op : plan->ops[ph]) {
+            bool ok = true;
+            if (op.kind == OP_EINSUM) ok = fits(op.e.a) && fits(op.e.b) && fits(op.e.c);
+            if (op.kind == OP_PERMUTE) ok = fits(op.p.src) && fits(op.p.dst);
+            if (op.kind == OP_ACCUM) ok = fits(op.a.src);
+            if (!ok) {
+                set_error("finalize: an operation addresses memory beyond the declared %lld-byte arena",
+                          (long long)workspace_bytes);
+                return TNC_ERR_NOMEM;
+            }
+        }
+    for (auto& L : plan->leaves)
+        if (L.dst_offset + (((int64_t)L.dst_rows << L.dst_rank) * plan->elem_bytes()) > workspace_bytes) {
+            set_error("finalize: a leaf does not fit the declared arena");
+            return TNC_ERR_NOMEM;
+        }
+    // host image of the device blob: row tables, k-offset tables, leaf descriptors
+    std::vector<char> blob;
+    auto append = [&](const void* data, size_t bytes) {
+        size_t off = (blob.size() + 255) & ~(size_t)255;
+        blob.resize(off + bytes);
+        if (bytes) memcpy(blob.data() + off, data, bytes);
+        return (int64_t)off;
+    };
+    plan->table_off.clear();
+    for (auto& t : plan->tables) plan->table_off.push_back(append(t.data(), t.size() * sizeof(int32_t)));
+    for (int ph = 0; ph < 2; ++ph)
+        for (auto& op : plan->ops[ph]) {
+            if (op.kind != OP_EINSUM) continue;
+            const tnc_einsum& e = op.e;
+            const size_t nk = (size_t)1 << e.n_k;
+            std::vector<uint32_t> ka(nk), kb(nk);
+            for (size_t k = 0; k < nk; ++k) {
+                uint32_t oa = 0, ob = 0;
+                for (int i = 0; i < e.n_k; ++i) {
+                    const uint32_t bit = (uint32_t)(k >> i) & 1u;
+                    oa |= bit << e.k_a[i];
+                    ob |= bit << e.k_b[i];
+                }
+                ka[k] = oa;
+                kb[k] = ob;
+            }
+            op.koff_a = append(ka.data(), nk * sizeof(uint32_t));
+            op.koff_b = append(kb.data(), nk * sizeof(uint32_t));
+        }
+    plan->leaves_off = append(plan->leaves.data(), plan->leaves.size() * sizeof(LeafDev));
+    if (blob.empty()) blob.resize(256);
+    TNC_CUDA(cudaMalloc((void**)&plan->dev_blob, blob.size()));
+    TNC_CUDA(cudaMemcpy(plan->dev_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    // tensor-core lowering
+    for (int ph = 0; ph < 2; ++ph)
+        for (auto& op : plan->ops[ph]) {
+            if (op.kind != OP_EINSUM || op.e.algo != TNC_ALGO_TC) continue;
+            const int32_t* ra = op.e.rows_a >= 0 ? plan->tables[op.e.rows_a].data() : nullptr;
+            const int32_t* rb = op.e.rows_b >= 0 ? plan->tables[op.e.rows_b].data() : nullptr;
+            TcGemmOp* tc = nullptr;
+            int rc = tc_gemm_create(op.e, plan->dtype, ra, rb, &tc);
+            if (rc != TNC_OK) return rc;
+            op.tc.reset(tc, tc_gemm_destroy);
+        }
+    plan->workspace_bytes = workspace_bytes;
+    plan->finalized = true;
+    return TNC_OK;
+}
+
+int64_t tnc_plan_workspace_bytes(const tnc_plan* plan) { return plan ? plan->workspace_bytes : -1; }
+
+int64_t tnc_plan_num_ops(const tnc_plan* plan, int32_t phase) {
+    if (!plan || !phase_ok(phase)) return -1;
+    return (int64_t)plan->ops[phase].size();
+}
+
+int64_t tnc_plan_last_launches(const tnc_plan* plan) { return plan ? plan->last_launches : -1; }
+
+static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_id, void* accum_out, char* ws,
+                  cudaStream_t st) {
+    switch (op.kind) {
+        case OP_LEAVES: {
+            plan->last_launches += op.leaf_count > 0;
+            const LeafDev* dl = (const LeafDev*)(plan->dev_blob + plan->leaves_off) + op.leaf_begin;
+            return launch_leaf_gather(dl, op.leaf_count, 0, leaf_blob, ws, slice_id, plan->dtype, st);
+        }
+        case OP_EINSUM: {
+            const tnc_einsum& e = op.e;
+            if (op.tc) {
+                int launches = 0;
+                int rc = tc_gemm_run(op.tc.get(), ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, st, &launches);
+                plan->last_launches += launches;
+                return rc;
+            }
+            SimtEinsumParams p{};
+            p.a = ws + e.a.offset;
+            p.b = ws + e.b.offset;
+            p.c = ws + e.c.offset;
+            p.rows_mode_a = e.rows_a;
+            p.rows_mode_b = e.rows_b;
+            p.rows_a = e.rows_a >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_a]) : nullptr;
+            p.rows_b = e.rows_b >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_b]) : nullptr;
+            p.rank_a = e.a.rank;
+            p.rank_b = e.b.rank;
+            p.rank_c = e.c.rank;
+            p.kb = e.n_k;
+            p.total = (int64_t)e.nb << e.c.rank;
+            p.koff_a = (const uint32_t*)(plan->dev_blob + op.koff_a);
+            p.koff_b = (const uint32_t*)(plan->dev_blob + op.koff_b);
+            for (int q = 0; q < TNC_MAX_BITS; ++q) p.c2a[q] = p.c2b[q] = -1;
+            for (int i = 0; i < e.n_m; ++i) p.c2a[e.m_c[i]] = e.m_a[i];
+            for (int i = 0; i < e.n_n; ++i) p.c2b[e.n_c[i]] = e.n_b[i];
+            for (int i = 0; i < e.n_h; ++i) {
+                p.c2a[e.h_c[i]] = e.h_a[i];
+                p.c2b[e.h_c[i]] = e.h_b[i];
+            }
+            plan->last_launches += 1;
+            return launch_simt_einsum(p, plan->dtype, st);
+        }
+        case OP_PERMUTE: {
+            PermuteParams p{};
+            p.src = ws + op.p.src.offset;
+            p.dst = ws + op.p.dst.offset;
+            p.rank = op.p.src.rank;
+            p.rows = op.p.src.rows;
+            memcpy(p.perm, op.p.perm, sizeof(p.perm));
+            plan->last_launches += 1;
+            return launch_permute(p, plan->elem_bytes(), st);
+        }
+        case OP_ACCUM: {
+            AccumParams p{};
+            p.src = ws + op.a.src.offset;
+            p.out = accum_out;
+            p.rank = op.a.src.rank;
+            p.rows = op.a.src.rows;
+            memcpy(p.out_pos, op.a.out_pos, sizeof(p.out_pos));
+            plan->last_launches += 1;
+            return launch_accum(p, plan->dtype, st);
+        }
+    }
+    set_error("execute: unknown op kind %d", op.kind);
+    return TNC_ERR_INVALID;
+}
+
+int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin, uint64_t slice_end,
+                     void* accum_out, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!plan || !plan->finalized) {
+        set_error("execute: plan is not finalized");
+        return TNC_ERR_STATE;
+    }
+    if (!leaf_blob || !accum_out || (!workspace && plan->workspace_bytes > 0)) {
+        set_error("execute: null device pointer");
+        return TNC_ERR_INVALID;
+    }
+    if (workspace_bytes < plan->workspace_bytes) {
+        set_error("execute: workspace has %lld bytes, plan needs %lld", (long long)workspace_bytes,
+                  (long long)plan->workspace_bytes);
+        return TNC_ERR_NOMEM;
+    }
+    const uint64_t n_slices = plan->n_sliced >= 63 ? ~0ull : (1ull << plan->n_sliced);
+    if (slice_begin > slice_end || slice_end > n_slices) {
+        set_error("execute: slice range [%llu, %llu) outside [0, %llu)", (unsigned long long)slice_begin,
+                  (unsigned long long)slice_end, (unsigned long long)n_slices);
+        return TNC_ERR_INVALID;
+    }
+    if ((uintptr_t)workspace & 255) {
+        set_error("execute: workspace must be 256-byte aligned");
+        return TNC_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    plan->last_launches = 0;
+    if (slice_begin == slice_end) return TNC_OK;
+    for (auto& op : plan->ops[TNC_PHASE_ONCE]) {
+        int rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, st);
+        if (rc != TNC_OK) return rc;
+    }
+    for (uint64_t s = slice_begin; s < slice_end; ++s)
+        for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
+            int rc = run_op(plan, op, leaf_blob, s, accum_out, ws, st);
+            if (rc != TNC_OK) return rc;
+        }
+    return TNC_OK;
+}
+
+int tnc_permute_bits(const void* src, void* dst, int32_t rank, int64_t rows, const int8_t* perm,
+                     int32_t elem_bytes, void* stream) {
+    if (!src || !dst || !perm || rank < 0 || rank >= TNC_MAX_BITS || rows < 1) {
+        set_error("permute_bits: bad arguments");
+        return TNC_ERR_INVALID;
+    }
+    uint64_t seen = 0;
+    if (!check_positions(perm, rank, rank, seen, "permute_bits perm")) return TNC_ERR_INVALID;
+    PermuteParams p{};
+    p.src = src;
+    p.dst = dst;
+    p.rank = rank;
+    p.rows = rows;
+    memcpy(p.perm, perm, rank);
+    return launch_permute(p, elem_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

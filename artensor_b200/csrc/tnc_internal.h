@@ -1,0 +1,71 @@
+// Internal declarations shared by the tnc_b200 translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "tnc_b200.h"
+
+namespace tnc {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define TNC_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t _e = (call);                                    \
+        if (_e != cudaSuccess) return ::tnc::cuda_fail(_e, #call);  \
+    } while (0)
+
+// ---------------------------------------------------------------- generic (SIMT) einsum
+struct SimtEinsumParams {
+    const void* a;
+    const void* b;
+    void* c;
+    const int32_t* rows_a;   // table or nullptr
+    const int32_t* rows_b;
+    int32_t rows_mode_a;     // TNC_ROWS_NONE / TNC_ROWS_IDENTITY / >=0 (table)
+    int32_t rows_mode_b;
+    int32_t rank_a, rank_b, rank_c;
+    int32_t kb;
+    int64_t total;           // nb << rank_c
+    const uint32_t* koff_a;  // 2^kb entries
+    const uint32_t* koff_b;
+    int8_t c2a[TNC_MAX_BITS];  // for C position p: position in A, or -1
+    int8_t c2b[TNC_MAX_BITS];
+};
+int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s);
+
+// ---------------------------------------------------------------- leaves
+struct LeafDev {
+    int64_t src_offset;      // elements
+    int64_t dst_offset;      // bytes
+    int32_t dst_rank, dst_rows, src_rank, n_sliced;
+    int8_t sliced_pos[TNC_MAX_SLICED];
+    int8_t sliced_shift[TNC_MAX_SLICED];   // slice-id bit index (LSB-based)
+    int8_t keep_pos[TNC_MAX_BITS];
+};
+int launch_leaf_gather(const LeafDev* dev_leaves, int n, int max_elems, const void* blob,
+                       void* arena, uint64_t slice_id, int dtype, cudaStream_t s);
+
+// ---------------------------------------------------------------- permute / accumulate
+struct PermuteParams {
+    const void* src;
+    void* dst;
+    int32_t rank;
+    int64_t rows;
+    int8_t perm[TNC_MAX_BITS];   // perm[i]: source position feeding destination position i
+};
+int launch_permute(const PermuteParams& p, int elem_bytes, cudaStream_t s);
+
+struct AccumParams {
+    const void* src;
+    void* out;
+    int32_t rank;
+    int64_t rows;
+    int8_t out_pos[TNC_MAX_BITS];
+};
+int launch_accum(const AccumParams& p, int dtype, cudaStream_t s);
+
+}  // namespace tnc

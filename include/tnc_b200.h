@@ -1,0 +1,154 @@
+/* tnc_b200 -- C ABI of the B200-native tensor-network contraction executor.
+ *
+ * This library replaces what artensor's numerical executor dispatches to: the chain of
+ * `torch.einsum` calls in `tensor_contraction` (artensor/contraction.py:62-76) and
+ * `tensor_contraction_sparse` (artensor/contraction.py:132-205), and the slice loop of
+ * `TensorNetworkSimulation.contraction` (artensor/simulation.py:103-117; copy at :198-213).
+ * The reference is pure Python and has no FFI of its own; the binding a maintainer would
+ * add is the ctypes stub shown in INTEGRATION.md (it is `artensor_b200/_native.py`).
+ *
+ * Model: a *plan* is an immutable list of operations over one device workspace ("arena").
+ * The host-side plan compiler (artensor_b200/plan.py, backend.py) lowers a reference-format
+ * scheme into operations; the library runs them for a range of slice ids and accumulates
+ * the per-slice results into a caller-owned accumulator.
+ *
+ * Every tensor is "bits": `rows` blocks (the bitstring batch mode of sparse schemes,
+ * contraction.py:219-220; 1 if absent) of 2^rank elements; bit p of the in-block element
+ * index is "position p".  A mode order is an assignment of modes to positions.
+ *
+ * All pointers are plain device pointers; no torch types cross this boundary.
+ * All functions return 0 on success, a tnc_status otherwise; tnc_last_error() describes the
+ * last failure on the calling thread.  The reference's error convention for this path is
+ * print + sys.exit(1) (contraction.py:71-74, :192-195); here errors are returned.
+ */
+#ifndef TNC_B200_H
+#define TNC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNC_ABI_VERSION 1
+#define TNC_MAX_BITS 40          /* max bit modes per group / per tensor */
+#define TNC_MAX_SLICED 8         /* max sliced bonds on one leaf */
+
+typedef enum tnc_status {
+    TNC_OK = 0,
+    TNC_ERR_INVALID = 1,         /* malformed operation / argument */
+    TNC_ERR_CUDA = 2,            /* a CUDA call failed */
+    TNC_ERR_NOMEM = 3,           /* workspace too small */
+    TNC_ERR_UNSUPPORTED = 4,     /* valid but not implemented for these sizes */
+    TNC_ERR_STATE = 5            /* plan not finalized / already finalized */
+} tnc_status;
+
+typedef enum tnc_dtype {
+    TNC_C64 = 0,                 /* complex64 (interleaved fp32 pairs) */
+    TNC_C32 = 1                  /* complex-half (interleaved fp16 pairs) */
+} tnc_dtype;
+
+typedef enum tnc_phase {
+    TNC_PHASE_ONCE = 0,          /* slice-invariant: runs once per execute call */
+    TNC_PHASE_SLICE = 1          /* runs for every slice id */
+} tnc_phase;
+
+typedef enum tnc_algo {
+    TNC_ALGO_SIMT = 0,           /* generic CUDA-core kernel, any shape */
+    TNC_ALGO_TC = 1              /* tcgen05 tensor-core kernel (3xTF32 for c64) */
+} tnc_algo;
+
+/* Row table ids: a plan-owned int32 table (tnc_plan_add_table) or one of these. */
+#define TNC_ROWS_NONE (-1)       /* operand has no row mode: always block 0 */
+#define TNC_ROWS_IDENTITY (-2)   /* source row == output row */
+
+typedef struct tnc_plan tnc_plan;
+
+/* A tensor living in the arena. */
+typedef struct tnc_tensor {
+    int64_t offset;              /* byte offset into the workspace; multiple of 256 */
+    int32_t rank;                /* number of bit modes: a row block has 2^rank elements */
+    int32_t rows;                /* number of row blocks (>= 1) */
+} tnc_tensor;
+
+/* C[b][m,n,h] = sum_k A[ra[b]][m,k,h] * B[rb[b]][k,n,h]   (one step of a scheme;
+ * artensor/contraction.py:70 and :147-190 are the einsum call sites this replaces).
+ * Each mode is given by its bit position in the operands that carry it. */
+typedef struct tnc_einsum {
+    tnc_tensor a, b, c;
+    int32_t nb;                  /* output rows == c.rows */
+    int32_t rows_a;              /* row table id for A (nb entries) or TNC_ROWS_* */
+    int32_t rows_b;
+    int32_t n_m, n_n, n_k, n_h;
+    int8_t m_a[TNC_MAX_BITS], m_c[TNC_MAX_BITS];
+    int8_t n_b[TNC_MAX_BITS], n_c[TNC_MAX_BITS];
+    int8_t k_a[TNC_MAX_BITS], k_b[TNC_MAX_BITS];
+    int8_t h_a[TNC_MAX_BITS], h_b[TNC_MAX_BITS], h_c[TNC_MAX_BITS];
+    int32_t algo;                /* tnc_algo */
+    int32_t flags;               /* reserved, 0 */
+} tnc_einsum;
+
+/* dst[r][q] = src[r][p] where bit i of q equals bit perm[i] of p (a bit permutation of the
+ * in-block index; replaces the permute+reshape copies torch.einsum makes). */
+typedef struct tnc_permute {
+    tnc_tensor src, dst;
+    int8_t perm[TNC_MAX_BITS];   /* perm[i] = source position feeding destination position i */
+} tnc_permute;
+
+/* One leaf tensor copied from the caller's packed leaf blob into the arena, with its sliced
+ * bonds fixed by the slice id (artensor/simulation.py:108-113: select(ind, bit).clone()).
+ * Slice-id bit numbering follows np.binary_repr(s, S): bond x is bit (S-1-x). */
+typedef struct tnc_leaf {
+    int64_t src_offset;          /* element offset of the leaf inside the leaf blob */
+    tnc_tensor dst;              /* rank = un-sliced rank - n_sliced */
+    int32_t src_rank;            /* bit modes of the stored leaf (rows excluded) */
+    int32_t n_sliced;
+    int8_t sliced_pos[TNC_MAX_SLICED];   /* source bit position of each sliced mode */
+    int8_t sliced_bond[TNC_MAX_SLICED];  /* which slice-id bit (x, MSB-first index) drives it */
+    int8_t keep_pos[TNC_MAX_BITS];       /* source position of destination position i */
+} tnc_leaf;
+
+/* out[dst_index(e)] += src[e]: adds a per-slice result into the caller's accumulator
+ * (artensor/simulation.py:114 `collect_tensor += ...`); out_pos lets the accumulator use
+ * a different mode order (e.g. qubit order, simulation.py:115-116). */
+typedef struct tnc_accum {
+    tnc_tensor src;
+    int8_t out_pos[TNC_MAX_BITS];        /* accumulator position of source position i */
+} tnc_accum;
+
+/* ---- plan construction (host only, no CUDA calls until finalize) ---- */
+int tnc_abi_version(void);
+int tnc_plan_create(int32_t dtype, int32_t n_sliced_bonds, tnc_plan** out);
+int tnc_plan_add_table(tnc_plan* plan, const int32_t* data, int64_t n, int32_t* table_id);
+int tnc_plan_add_leaves(tnc_plan* plan, int32_t phase, const tnc_leaf* leaves, int32_t n);
+int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* op);
+int tnc_plan_add_permute(tnc_plan* plan, int32_t phase, const tnc_permute* op);
+int tnc_plan_add_accum(tnc_plan* plan, int32_t phase, const tnc_accum* op);
+/* Declares the arena size the operations were laid out for and uploads tables. */
+int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes);
+int64_t tnc_plan_workspace_bytes(const tnc_plan* plan);
+int64_t tnc_plan_num_ops(const tnc_plan* plan, int32_t phase);
+/* kernels launched by the last tnc_plan_execute on this plan */
+int64_t tnc_plan_last_launches(const tnc_plan* plan);
+void tnc_plan_destroy(tnc_plan* plan);
+
+/* ---- execution ----
+ * Runs ONCE-phase operations, then SLICE-phase operations for every slice id in
+ * [slice_begin, slice_end), on `stream` (a cudaStream_t passed as void*), without host
+ * synchronisation.  `leaf_blob`, `accum_out` and `workspace` are device pointers;
+ * `accum_out` is read-modify-written (the caller zeroes it, simulation.py:101-105). */
+int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin,
+                     uint64_t slice_end, void* accum_out, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
+/* Stand-alone bit permutation (same kernel the plan uses); elem_bytes is 8 (c64) or 4. */
+int tnc_permute_bits(const void* src, void* dst, int32_t rank, int64_t rows,
+                     const int8_t* perm, int32_t elem_bytes, void* stream);
+
+const char* tnc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNC_B200_H */

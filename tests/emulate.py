@@ -1,0 +1,98 @@
+"""TEST INFRASTRUCTURE: a numpy interpreter of the native operation records.
+
+Lets the CPU test-suite check the whole host side (scheme parser, hoisting, layouts, arena
+offsets, leaf table, row tables) against the oracle without a GPU: it executes exactly the
+records `ContractionPlan` would hand to libtnc_b200.so, with the semantics documented in
+include/tnc_b200.h.  Never used by the product path.
+"""
+import numpy as np
+
+from artensor_b200 import _native as N
+
+
+def _view(arena, t):
+    n = t.rows << t.rank
+    return arena[t.offset // 8: t.offset // 8 + n]
+
+
+def _deposit(idx, positions):
+    out = np.zeros_like(idx)
+    for i, p in enumerate(positions):
+        out |= ((idx >> i) & 1) << int(p)
+    return out
+
+
+def run_plan(plan, leaf_blob, slice_ids):
+    """Execute plan.ops on a host arena; returns the accumulator (logical result order)."""
+    assert plan.dtype == N.TNC_C64
+    arena = np.zeros(plan.workspace_bytes // 8, dtype=np.complex64)
+    out = np.zeros(int(np.prod(plan.out_shape)) if plan.out_shape else 1, dtype=np.complex64)
+    S = plan.n_sliced
+
+    def run(kind, rec, sid):
+        if kind == "leaves":
+            for L in rec:
+                dst = _view(arena, L.dst)
+                e = np.arange(L.dst.rows << L.dst.rank, dtype=np.int64)
+                row, eb = e >> L.dst.rank, e & ((1 << L.dst.rank) - 1)
+                so = _deposit(eb, [L.keep_pos[i] for i in range(L.dst.rank)])
+                for s in range(L.n_sliced):
+                    bit = (sid >> (S - 1 - L.sliced_bond[s])) & 1
+                    so |= bit << int(L.sliced_pos[s])
+                dst[:] = leaf_blob[L.src_offset + (row << L.src_rank) + so]
+        elif kind == "einsum":
+            E = rec
+            A, B, Cv = _view(arena, E.a), _view(arena, E.b), _view(arena, E.c)
+            e = np.arange(E.nb << E.c.rank, dtype=np.int64)
+            row, cb = e >> E.c.rank, e & ((1 << E.c.rank) - 1)
+            oa = np.zeros_like(e)
+            ob = np.zeros_like(e)
+            for i in range(E.n_m):
+                oa |= ((cb >> int(E.m_c[i])) & 1) << int(E.m_a[i])
+            for i in range(E.n_n):
+                ob |= ((cb >> int(E.n_c[i])) & 1) << int(E.n_b[i])
+            for i in range(E.n_h):
+                bit = (cb >> int(E.h_c[i])) & 1
+                oa |= bit << int(E.h_a[i])
+                ob |= bit << int(E.h_b[i])
+
+            def rows(mode):
+                if mode == N.TNC_ROWS_NONE:
+                    return np.zeros_like(row)
+                if mode == N.TNC_ROWS_IDENTITY:
+                    return row
+                return plan.tables[mode].astype(np.int64)[row]
+            oa += rows(E.rows_a) << E.a.rank
+            ob += rows(E.rows_b) << E.b.rank
+            k = np.arange(1 << E.n_k, dtype=np.int64)
+            ka = _deposit(k, [E.k_a[i] for i in range(E.n_k)])
+            kb = _deposit(k, [E.k_b[i] for i in range(E.n_k)])
+            acc = np.zeros(len(e), dtype=np.complex64)
+            step = max(1, (1 << 22) // len(k))
+            for lo in range(0, len(e), step):
+                hi = min(len(e), lo + step)
+                acc[lo:hi] = (A[oa[lo:hi, None] + ka[None, :]] * B[ob[lo:hi, None] + kb[None, :]]).sum(axis=1)
+            Cv[:] = acc
+        elif kind == "permute":
+            P = rec
+            src, dst = _view(arena, P.src), _view(arena, P.dst)
+            e = np.arange(P.src.rows << P.src.rank, dtype=np.int64)
+            q = e & ((1 << P.src.rank) - 1)
+            s = _deposit(q, [P.perm[i] for i in range(P.src.rank)])
+            dst[:] = src[((e >> P.src.rank) << P.src.rank) + s]
+        elif kind == "accum":
+            A = rec
+            src = _view(arena, A.src)
+            e = np.arange(A.src.rows << A.src.rank, dtype=np.int64)
+            q = e & ((1 << A.src.rank) - 1)
+            d = _deposit(q, [A.out_pos[i] for i in range(A.src.rank)])
+            out[((e >> A.src.rank) << A.src.rank) + d] += src
+        else:
+            raise ValueError(kind)
+
+    for kind, rec in plan.ops[N.TNC_PHASE_ONCE]:
+        run(kind, rec, 0)
+    for sid in slice_ids:
+        for kind, rec in plan.ops[N.TNC_PHASE_SLICE]:
+            run(kind, rec, int(sid))
+    return out.reshape(plan.out_shape)

@@ -1,0 +1,177 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden
+outputs.  complex64 bar (BASELINE.json north_star): <= 1e-5 relative error per amplitude.
+
+"Per amplitude" is applied as: every amplitude whose magnitude is at least 1% of the rms is
+within 1e-5 relative error, and every amplitude (however small) is within 1e-5 * rms absolute
+-- two complex64 evaluations of a tiny amplitude that is the sum of cancelling terms cannot
+agree better than fp32 epsilon relative to the terms, whichever executor produced them.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def assert_amplitudes_close(got, want, rtol=RTOL):
+    got, want = np.asarray(got).reshape(-1), np.asarray(want).reshape(-1)
+    assert got.shape == want.shape
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    err = np.abs(got - want)
+    big = np.abs(want) >= 1e-2 * rms
+    assert err.max() <= rtol * rms * 1.0 + 0, f"max abs err {err.max():.3e} > {rtol} * rms {rms:.3e}"
+    if big.any():
+        rel = (err[big] / np.abs(want[big])).max()
+        assert rel <= rtol, f"max relative error {rel:.3e} > {rtol}"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from artensor_b200 import _native
+    _native.load()      # the CUDA extension must be present: no fallback
+    return torch.device("cuda:0")
+
+
+def sim_from(name):
+    from artensor_b200 import TensorNetworkSimulation
+    case, exp = load_golden(name)
+    return case, exp, TensorNetworkSimulation.from_case(case)
+
+
+SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_full_slice_sum_matches_reference(dev, name):
+    case, exp, sim = sim_from(name)
+    got = sim.contraction(device=dev)
+    want = exp["per_slice_c128"].sum(axis=0).reshape(exp["shape"])
+    if case.permute_dims is not None:
+        want = np.transpose(want, case.permute_dims)
+    assert tuple(got.shape) == want.shape
+    assert_amplitudes_close(got.cpu().numpy(), want)
+    # and against the reference's own complex64 run
+    want64 = exp["per_slice_c64"].astype(np.complex128).sum(axis=0).reshape(exp["shape"])
+    if case.permute_dims is not None:
+        want64 = np.transpose(want64, case.permute_dims)
+    assert_amplitudes_close(got.cpu().numpy(), want64)
+
+
+@pytest.mark.parametrize("name", ["n12_sparse64_sc9", "n12_sparse100_sc8"])
+def test_individual_slices_and_ranges(dev, name):
+    case, exp, sim = sim_from(name)
+    for s in (0, 1, case.n_slices - 1):
+        got = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()
+        assert_amplitudes_close(got, exp["per_slice_c64"][s])
+    got = sim.contraction(device=dev, slice_range=(3, 11)).cpu().numpy()
+    assert_amplitudes_close(got, exp["per_slice_c128"][3:11].sum(axis=0))
+    # empty range: nothing runs, accumulator stays zero
+    assert sim.contraction(device=dev, slice_range=(4, 4)).abs().max().item() == 0.0
+
+
+def test_hoisting_does_not_change_results(dev):
+    from artensor_b200 import PlanOptions
+    case, exp, sim = sim_from("n12_sparse256c_sc10")
+    a = sim.contraction(device=dev).cpu().numpy()
+    sim.plan_options = PlanOptions(hoist=False)
+    b = sim.contraction(device=dev).cpu().numpy()
+    assert_amplitudes_close(a, b)
+    assert_amplitudes_close(b, exp["per_slice_c128"].sum(axis=0))
+
+
+def test_bare_executors_match_oracle(dev):
+    """tensor_contraction / tensor_contraction_sparse with the reference's container semantics."""
+    from artensor_b200 import tensor_contraction, tensor_contraction_sparse
+    from oracle import tn_oracle as O
+    case, exp = load_golden("n12_full")
+    tensors = {k: v.to(dev) for k, v in case.leaves.items()}
+    out = tensor_contraction(tensors, case.scheme)
+    assert tuple(out.shape) == tuple(exp["shape"])
+    assert tensors[case.scheme[-1][0][0]] is out
+    assert_amplitudes_close(out.cpu().numpy(), exp["per_slice_c64"][0])
+    case, exp = load_golden("n12_sparse5")
+    tensors = [case.leaves[k].to(dev) for k in range(len(case.leaves))]
+    out = tensor_contraction_sparse(tensors, case.scheme)
+    assert_amplitudes_close(out.cpu().numpy(), exp["per_slice_c64"][0])
+    assert tensors[case.scheme[0][0][1]] == []
+    want = O.tensor_contraction_sparse({k: v.numpy() for k, v in case.leaves.items()}, case.scheme)
+    assert_amplitudes_close(out.cpu().numpy(), want)
+    tensors = [case.leaves[k].to(dev) for k in range(len(case.leaves))]
+    factor, t = tensor_contraction_sparse(tensors, case.scheme, scientific_notation=True)
+    assert abs(t.abs().max().item() - 1.0) < 1e-6
+    assert_amplitudes_close((t * 10.0 ** factor).cpu().numpy(), exp["per_slice_c64"][0])
+
+
+def test_known_answers_n12(dev):
+    """tests/test_circuits.py:25-42 of the reference (table accurate to ~3e-5)."""
+    from test_oracle import KAT_N12
+    case, _, sim = sim_from("n12_sparse5")
+    got = sim.contraction(device=dev).cpu().numpy()
+    for b, amp in zip(case.bitstrings_sorted, got):
+        assert abs(amp - KAT_N12[b]) / abs(KAT_N12[b]) < 5e-5
+    case, _, sim = sim_from("n12_full")
+    amps = sim.contraction(device=dev).reshape(-1).cpu().numpy()
+    for b, amp in KAT_N12.items():
+        assert abs(amps[int(b, 2)] - amp) / abs(amp) < 5e-5
+    # state norm: sum |amp|^2 == 1 up to the gate tensors' unitarity (1e-5)
+    assert abs(np.sum(np.abs(amps.astype(np.complex128)) ** 2) - 1.0) < 1e-4
+
+
+def test_n30_sliced_chunked_vs_reference_and_google(dev):
+    case, exp, sim = sim_from("n30_sparse64_sc26")
+    for s in range(case.n_slices):
+        got = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()
+        assert_amplitudes_close(got, exp["per_slice_c64"][s])
+    total = sim.contraction(device=dev).cpu().numpy()
+    google = dict(zip(case.extra["bitstrings_in"], case.extra["google_amplitudes"]))
+    want = np.array([google[b] for b in case.bitstrings_sorted])
+    rel = np.abs(total - want) / np.abs(want)
+    assert np.median(rel) < 2e-4 and rel.max() < 2e-3     # Google's file: ~1e-4 golden
+
+
+def test_n53_m12_slices_vs_reference(dev):
+    case, exp, sim = sim_from("n53_m12_sparse1024")
+    for k, s in enumerate(exp["slice_ids"]):
+        got = sim.contraction(device=dev, slice_range=(int(s), int(s) + 1)).cpu().numpy()
+        assert_amplitudes_close(got, exp["per_slice_c64"][k])
+
+
+def test_permute_bits_kernel(dev):
+    import ctypes as C
+    from artensor_b200 import _native as N
+    lib = N.load()
+    rng = np.random.RandomState(1)
+    for rank, rows in [(1, 1), (5, 3), (12, 1), (16, 2), (20, 1)]:
+        for trial in range(3):
+            perm = rng.permutation(rank)
+            src = torch.randn(rows, 1 << rank, dtype=torch.complex64, device=dev)
+            dst = torch.empty_like(src)
+            arr = (C.c_int8 * rank)(*[int(p) for p in perm])
+            N.check(lib.tnc_permute_bits(src.data_ptr(), dst.data_ptr(), rank, rows, arr, 8,
+                                         torch.cuda.current_stream().cuda_stream))
+            q = np.arange(1 << rank)
+            s = np.zeros_like(q)
+            for i in range(rank):
+                s |= ((q >> i) & 1) << int(perm[i])
+            assert torch.equal(dst.cpu(), src.cpu()[:, torch.from_numpy(s)])      # bit-exact copy
+
+
+def test_native_errors_are_raised_not_fatal(dev):
+    from artensor_b200 import _native as N
+    case, _, sim = sim_from("n12_sparse64_sc9")
+    plan = sim.plan()
+    blob = plan.pack_leaves({k: v.to(dev) for k, v in case.leaves.items()})
+    out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
+    small = torch.empty(1024, dtype=torch.uint8, device=dev)
+    with pytest.raises(N.NativeError, match="NOMEM"):
+        plan.execute(blob, out, 0, 1, small, torch.cuda.current_stream().cuda_stream)
+    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
+    with pytest.raises(N.NativeError, match="slice range"):
+        plan.execute(blob, out, 0, case.n_slices + 1, ws, torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,86 @@
+"""Pins the numpy oracle (oracle/tn_oracle.py) against outputs of the REAL reference
+(fixtures written by tools/gen_cases.py, which imports /root/reference), against the
+reference's own known-answer table and against Google's amplitude file."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import tn_oracle as O
+
+SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10"]
+
+# tests/test_circuits.py:25-31 of the reference
+KAT_N12 = {
+    "100001000001": 0.0198028199 + 1j * 0.0106442748,
+    "000101111011": 0.00497586094 + 1j * -0.0245072283,
+    "011000101100": -0.00853562169 + 1j * -0.00701293815,
+    "111001100001": -0.0100137182 + 1j * 0.0147468708,
+    "001110110000": 0.00681955926 + 1j * 0.0106616206,
+}
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_reference_per_slice(name):
+    case, exp = load_golden(name)
+    sidx = case.slicing_indices()
+    ids = exp["slice_ids"]
+    pick = ids if len(ids) <= 16 else ids[:: max(1, len(ids) // 16)]
+    for s in pick:
+        k = int(np.where(ids == s)[0][0])
+        r = O.contract_slices(case.leaves, case.scheme, case.pattern, case.slicing_bonds, sidx, [s]).reshape(-1)
+        # two complex64 evaluations with different summation orders: agree to a few ulp of the scale
+        assert _rel(r, exp["per_slice_c64"][k]) < 5e-6
+        assert _rel(r, exp["per_slice_c128"][k]) < 5e-6
+
+
+def test_oracle_known_answers_n12_sparse():
+    """The reference's own KAT (effective tolerance ~3e-5: the table comes from another
+    simulator and the gate tensors are unitary only to 1e-7)."""
+    case, _ = load_golden("n12_sparse5")
+    r = O.contract_slices(case.leaves, case.scheme, case.pattern, case.slicing_bonds, case.slicing_indices(), [0])
+    for b, amp in zip(case.bitstrings_sorted, r.reshape(-1)):
+        assert abs(amp - KAT_N12[b]) / abs(KAT_N12[b]) < 5e-5
+
+
+def test_oracle_known_answers_n12_full():
+    case, _ = load_golden("n12_full")
+    r = O.contract_slices(case.leaves, case.scheme, case.pattern, case.slicing_bonds, case.slicing_indices(), [0])
+    amps = np.transpose(r, case.permute_dims).reshape(-1)
+    for b, amp in KAT_N12.items():
+        assert abs(amps[int(b, 2)] - amp) / abs(amp) < 5e-5
+
+
+def test_oracle_sliced_sum_is_slice_invariant_total():
+    """Sum over all slices of a sliced scheme == amplitudes of the same bitstrings taken from
+    the un-sliced full-amplitude contraction (different tree, different slicing)."""
+    case, exp = load_golden("n12_sparse64_sc9")
+    total = exp["per_slice_c128"].sum(axis=0)
+    full, fexp = load_golden("n12_full")
+    amps = np.transpose(fexp["per_slice_c128"][0].reshape(fexp["shape"]), full.permute_dims).reshape(-1)
+    want = np.array([amps[int(b, 2)] for b in case.bitstrings_sorted])
+    assert _rel(total, want) < 1e-5
+
+
+def test_oracle_scientific_notation():
+    case, exp = load_golden("n12_sparse5")
+    leaves = {k: v.numpy() for k, v in case.leaves.items()}
+    factor, t = O.tensor_contraction_sparse(dict(leaves), case.scheme, scientific_notation=True)
+    assert _rel((t * 10.0 ** factor).reshape(-1), exp["per_slice_c64"][0]) < 5e-6
+
+
+@pytest.mark.slow
+def test_oracle_n30_sliced_matches_reference_and_google():
+    """n30 m14, 64 bitstrings, sliced with chunked batched steps: slice 0 vs the reference,
+    and the reference's 4-slice total vs Google's amplitudes (~1e-4)."""
+    case, exp = load_golden("n30_sparse64_sc26")
+    r = O.contract_slices(case.leaves, case.scheme, case.pattern, case.slicing_bonds, case.slicing_indices(), [0])
+    assert _rel(r.reshape(-1), exp["per_slice_c64"][0]) < 5e-6
+    google = dict(zip(case.extra["bitstrings_in"], case.extra["google_amplitudes"]))
+    total = exp["per_slice_c64"].sum(axis=0)
+    want = np.array([google[b] for b in case.bitstrings_sorted])
+    rel = np.abs(total - want) / np.abs(want)
+    assert np.median(rel) < 2e-4 and rel.max() < 2e-3

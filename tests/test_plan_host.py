@@ -1,0 +1,167 @@
+"""Host logic of the plan compiler, checked on CPU: the operation records ContractionPlan
+emits are executed by a numpy interpreter (tests/emulate.py) and compared with the oracle
+and with the reference's golden outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from artensor_b200 import SchemeError, partition_slices
+from artensor_b200 import _native as N
+from artensor_b200.backend import Arena, ContractionPlan, PlanOptions
+from artensor_b200.plan import SchemeParser, parse_eq
+from oracle import tn_oracle as O
+import emulate
+
+SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10"]
+
+
+def make_plan(case, **kw):
+    return ContractionPlan(case.scheme, {k: tuple(v.shape) for k, v in case.leaves.items()}, case.pattern == "sparse",
+                           slicing_bonds=case.slicing_bonds, slicing_indices=case.slicing_indices(),
+                           build_native=False, **kw)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_lowered_plan_matches_reference(name):
+    case, exp = load_golden(name)
+    plan = make_plan(case)
+    blob = plan.pack_leaves(case.leaves).numpy()
+    ids = exp["slice_ids"]
+    pick = list(ids[:3]) + [int(ids[-1])]
+    for s in dict.fromkeys(int(x) for x in pick):
+        k = int(np.where(ids == s)[0][0])
+        got = emulate.run_plan(plan, blob, [s]).reshape(-1)
+        want = exp["per_slice_c64"][k]
+        assert np.abs(got - want).max() / np.abs(want).max() < 5e-6
+
+
+@pytest.mark.parametrize("name", ["n12_sparse64_sc9", "n12_sparse256c_sc10"])
+def test_slice_sum_and_hoisting(name):
+    """Summing a slice range inside one execute == summing per-slice oracle results; hoisted
+    (slice-invariant) steps give the same numbers as recomputing them per slice."""
+    case, exp = load_golden(name)
+    ids = list(range(5, 13))
+    want = O.contract_slices(case.leaves, case.scheme, case.pattern, case.slicing_bonds, case.slicing_indices(), ids)
+    for hoist in (True, False):
+        plan = make_plan(case, options=PlanOptions(hoist=hoist))
+        if not hoist:
+            assert plan.work_summary()["hoisted_steps"] == 0
+        got = emulate.run_plan(plan, plan.pack_leaves(case.leaves).numpy(), ids)
+        assert np.abs(got - want).max() / np.abs(want).max() < 5e-6
+
+
+def test_work_summary_counts():
+    case, _ = load_golden("n12_sparse64_sc9")
+    w = make_plan(case).work_summary()
+    assert w["steps"] == 68 and 0 < w["hoisted_steps"] < 68
+    assert w["exec_flops_per_slice"] < w["ref_flops_per_slice"]
+
+
+def test_multi_sliced_leaf_uses_corrected_dims():
+    """A leaf with two sliced bonds: all four settings must match numpy indexing on the
+    un-sliced tensor (the packaged reference loop is off by one here)."""
+    rng = np.random.RandomState(0)
+    t0 = torch.from_numpy((rng.randn(2, 2, 2, 2) + 1j * rng.randn(2, 2, 2, 2)).astype(np.complex64))
+    t1 = torch.from_numpy((rng.randn(2, 2) + 1j * rng.randn(2, 2)).astype(np.complex64))
+    scheme = [((0, 1), "ab,bc->ac")]      # after slicing dims 1 and 3 of t0 it is rank 2
+    sl = {"x": [(0, 1)], "y": [(0, 3)]}
+    plan = ContractionPlan(scheme, {0: (2, 2, 2, 2), 1: (2, 2)}, False, slicing_bonds=["x", "y"],
+                           slicing_indices=sl, build_native=False)
+    blob = plan.pack_leaves({0: t0, 1: t1}).numpy()
+    for s in range(4):
+        bx, by = (s >> 1) & 1, s & 1
+        want = t0.numpy()[:, bx, :, by] @ t1.numpy()
+        got = emulate.run_plan(plan, blob, [s])
+        assert np.allclose(got, want, atol=1e-6)
+
+
+def test_parser_rejects_bad_schemes():
+    with pytest.raises(SchemeError):
+        parse_eq("ab,bc,cd->ad")
+    with pytest.raises(SchemeError):
+        parse_eq("aab,bc->ac")
+    p = SchemeParser({0: (2, 2), 1: (2, 2)}, sparse=False)
+    with pytest.raises(SchemeError, match="summed inside one operand"):
+        p.parse([((0, 1), "ab,bc->c")])
+    p = SchemeParser({0: (2, 3), 1: (2, 2)}, sparse=False)
+    with pytest.raises(SchemeError, match="extent 2"):
+        p.parse([((0, 1), "ab,bc->ac")])
+    p = SchemeParser({0: (2, 2), 1: (2, 2)}, sparse=False)
+    with pytest.raises(SchemeError, match="not among the leaves"):
+        p.parse([((0, 5), "ab,bc->ac")])
+    p = SchemeParser({0: (2, 2), 1: (2, 2), 2: (2, 2)}, sparse=False)
+    with pytest.raises(SchemeError, match="already consumed"):
+        p.parse([((0, 1), "ab,bc->ac"), ((2, 1), "ab,bc->ac")])
+
+
+def test_parser_detects_invalid_chunking():
+    """B2: index lists that do not cover the announced row count are refused up front."""
+    a = torch.zeros(4, 2, dtype=torch.complex64)
+    b = torch.zeros(4, 2, dtype=torch.complex64)
+    good = [((0, 1), "ab,ab->a", [[torch.tensor([0, 1])], [torch.tensor([2, 3])]], None, (2,))]
+    SchemeParser({0: (4, 2), 1: (4, 2)}, True).parse(good)
+    bad = [((0, 1), "ab,ab->a", [[torch.tensor([0, 1])], [torch.tensor([2, 3])]], None, (3,))]
+    with pytest.raises(SchemeError, match="invalid chunking"):
+        SchemeParser({0: (4, 2), 1: (4, 2)}, True).parse(bad)
+
+
+def test_arena_reuses_and_coalesces():
+    a = Arena()
+    o1, s1 = a.alloc(1000)
+    o2, s2 = a.alloc(5000)
+    o3, s3 = a.alloc(100)
+    assert (o1, o2, o3) == (0, 1024, 1024 + 5120)
+    a.release(o1, s1)
+    a.release(o2, s2)
+    o4, s4 = a.alloc(6000)        # fits the coalesced hole
+    assert o4 == 0 and a.high == 1024 + 5120 + 1024
+    a.release(o3, s3)
+    o5, _ = a.alloc(10)
+    assert o5 in (6144, 7168)
+
+
+def test_partition_slices_covers_range_exactly():
+    for n, w in [(8, 2), (7, 3), (1, 8), (0, 4), (1 << 23, 8)]:
+        parts = [partition_slices(3, 3 + n, r, w) for r in range(w)]
+        assert parts[0][0] == 3 and parts[-1][1] == 3 + n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+def _dist_worker(rank, world, port, name, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case, _ = load_golden(name)
+    plan = make_plan(case)
+    lo, hi = partition_slices(0, case.n_slices, rank, world)
+    part = emulate.run_plan(plan, plan.pack_leaves(case.leaves).numpy(), range(lo, hi))
+    t = torch.from_numpy(np.ascontiguousarray(part))
+    dist.all_reduce(torch.view_as_real(t), op=dist.ReduceOp.SUM)   # same call the product makes over NCCL
+    if rank == 0:
+        out_q.put(t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_slice_partition_gloo():
+    """world_size-2 gloo run of the multi-GPU recipe: block-partition the slice range, contract
+    locally, one sum all-reduce of the partial amplitudes."""
+    import torch.multiprocessing as mp
+    name = "n12_sparse256c_sc10"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    case, exp = load_golden(name)
+    want = exp["per_slice_c128"].sum(axis=0)
+    assert np.abs(got.reshape(-1) - want).max() / np.abs(want).max() < 5e-6

@@ -149,6 +149,15 @@ CONFIGS = {
 }
 
 
+def google_extra(name, bitstrings):
+    """Google's amplitudes for the requested bitstrings (n30 cases only): golden vectors."""
+    if not name.startswith("n30_sparse"):
+        return {}
+    strings, amps = google_amplitudes(10000)
+    table = dict(zip(strings, amps))
+    return {"google_amplitudes": [complex(table[b]) for b in bitstrings]}
+
+
 def validate_scheme(scheme, pattern):
     """B2: every chunked step must cover exactly next_shape[0] rows, no empty chunk."""
     if pattern != "sparse":
@@ -180,6 +189,7 @@ def build(name):
             bitstrings_sorted=getattr(sim, "bitstrings_sorted", None),
             n_qubits=len(sim.final_qubits),
             extra={"prepare": {k: v for k, v in prep.items()}, "bitstrings_in": bitstrings,
+                   **google_extra(name, bitstrings),
                    "ref_slicing_indices": {b: [(int(t), int(d)) for t, d in v] for b, v in sim.slicing_indices.items()}},
         )
     case = load_case(case_path)
