@@ -9,7 +9,8 @@ import os
 
 TNC_MAX_BITS = 40
 TNC_MAX_SLICED = 8
-TNC_ABI_VERSION = 1
+TNC_ABI_VERSION = 2
+TNC_PROFILE_SLOTS = 4
 
 TNC_C64, TNC_C32 = 0, 1
 TNC_PHASE_ONCE, TNC_PHASE_SLICE = 0, 1
@@ -37,6 +38,7 @@ class TncEinsum(C.Structure):
         ("m_a", Bits), ("m_c", Bits), ("n_b", Bits), ("n_c", Bits), ("k_a", Bits), ("k_b", Bits),
         ("h_a", Bits), ("h_b", Bits), ("h_c", Bits),
         ("algo", C.c_int32), ("flags", C.c_int32),
+        ("scratch_offset", C.c_int64), ("scratch_bytes", C.c_int64),
     ]
 
 
@@ -58,6 +60,7 @@ class TncAccum(C.Structure):
 # name -> (restype, argtypes): every symbol include/tnc_b200.h declares
 SYMBOLS = {
     "tnc_abi_version": (C.c_int, []),
+    "tnc_einsum_tc_scratch_bytes": (C.c_int64, [C.c_int32, C.POINTER(TncEinsum)]),
     "tnc_plan_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "tnc_plan_add_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int32)]),
     "tnc_plan_add_leaves": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(TncLeaf), C.c_int32]),
@@ -71,6 +74,8 @@ SYMBOLS = {
     "tnc_plan_destroy": (None, [C.c_void_p]),
     "tnc_plan_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p]),
+    "tnc_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tnc_permute_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int8), C.c_int32,
                                    C.c_void_p]),
     "tnc_last_error": (C.c_char_p, []),

@@ -89,8 +89,22 @@ def logical_positions(info: TensorInfo):
 
 @dataclass
 class PlanOptions:
-    tc_min_flops: float = float("inf")   # steps at or above this many flops use the tensor-core path
+    tc_min_flops: float = 1e8    # steps at or above this many flops run on the tcgen05 path
     hoist: bool = True
+
+
+def tc_scratch_bytes(st: Step):
+    """Mirror of tnc_einsum_tc_scratch_bytes(): hi/lo panels of A' and of the expanded B'."""
+    al = lambda x: (x + 1023) // 1024 * 1024
+    nb_a = st.nb if st.ra is not None else 1
+    nb_b = st.nb if st.rb is not None else 1
+    a_panel = al((nb_a << (len(st.m_modes) + len(st.k_modes))) * 8)
+    b_panel = al((nb_b << (len(st.n_modes) + len(st.k_modes))) * 16)
+    return 2 * a_panel + 2 * b_panel
+
+
+def tc_eligible(st: Step):
+    return len(st.k_modes) >= 1 and len(st.n_modes) >= 1 and len(st.h_modes) == 0
 
 
 class ContractionPlan:
@@ -163,11 +177,19 @@ class ContractionPlan:
         for st in self.steps:
             A, B = bufs[st.i], bufs[st.j]
             phase = N.TNC_PHASE_SLICE if (A.dependent or B.dependent) else N.TNC_PHASE_ONCE
-            cpos = self._choose_layout(st, A, B)
+            algo = N.TNC_ALGO_SIMT
+            if st.flops >= self.options.tc_min_flops and tc_eligible(st) and self.dtype == N.TNC_C64:
+                algo = N.TNC_ALGO_TC
+            cpos = self._choose_layout(st, A, B, algo)
             o, sz = arenas[phase].alloc(st.c.numel * self.elem_bytes)
             Cb = Buf(phase, o, sz, st.c, cpos, False, base)
-            algo = N.TNC_ALGO_TC if st.flops >= self.options.tc_min_flops else N.TNC_ALGO_SIMT
-            pending.append((phase, st, A, B, Cb, algo))
+            scratch = None
+            if algo == N.TNC_ALGO_TC:
+                # packed operand panels live only while the step runs
+                so, ssz = arenas[phase].alloc(tc_scratch_bytes(st))
+                arenas[phase].release(so, ssz)
+                scratch = (so, ssz)
+            pending.append((phase, st, A, B, Cb, algo, scratch))
             self.step_phase.append(phase)
             self.step_algo.append(algo)
             for old in (A, B):
@@ -186,8 +208,14 @@ class ContractionPlan:
             if leaf_bufs[phase]:
                 ops[phase].append(("leaves", [self._leaf_record(tid, b) for tid, b in leaf_bufs[phase]]))
         self.tables: List[np.ndarray] = []
-        for phase, st, A, B, Cb, algo in pending:
-            ops[phase].append(("einsum", self._einsum_record(st, A, B, Cb, algo)))
+        op_steps = {ph: [None] * len(ops[ph]) for ph in ops}     # Step behind each op (None: not an einsum)
+        for phase, st, A, B, Cb, algo, scratch in pending:
+            rec = self._einsum_record(st, A, B, Cb, algo)
+            if scratch is not None:
+                rec.scratch_offset = base[phase] + scratch[0]
+                rec.scratch_bytes = scratch[1]
+            ops[phase].append(("einsum", rec))
+            op_steps[phase].append(st)
         final = bufs[self.result_slot]
         acc = N.TncAccum()
         acc.src = final.tensor()
@@ -198,7 +226,9 @@ class ContractionPlan:
         acc.out_pos = N.bits(out_pos)
         # the accumulate runs per slice even when nothing is sliced (one "slice")
         ops[N.TNC_PHASE_SLICE].append(("accum", acc))
+        op_steps[N.TNC_PHASE_SLICE].append(None)
         self.ops = ops
+        self.op_steps = op_steps
         if self._build:
             self._build_native(ops)
 
@@ -238,9 +268,21 @@ class ContractionPlan:
         rec.keep_pos = N.bits(keep_pos)
         return rec
 
-    def _choose_layout(self, st: Step, A: Buf, B: Buf):
-        """Physical mode order of the step's output.  v1: the reference's logical order."""
-        return logical_positions(st.c)
+    def _choose_layout(self, st: Step, A: Buf, B: Buf, algo):
+        """Physical mode order of the step's output.  The generic kernel writes the reference's
+        logical order.  The tensor-core GEMM writes C[rows][m][n] with the right-only modes in
+        the low positions; inside each group the modes keep the order they have in their
+        operand, which keeps the pack kernels' reads in long contiguous runs."""
+        if algo != N.TNC_ALGO_TC:
+            return logical_positions(st.c)
+        pos = {}
+        for i, m in enumerate(sorted(st.n_modes, key=lambda m: B.pos[m])):
+            pos[m] = i
+        nn = len(st.n_modes)
+        for i, m in enumerate(sorted(st.m_modes, key=lambda m: A.pos[m])):
+            pos[m] = nn + i
+        return pos
+
 
     def _table(self, arr):
         arr = np.ascontiguousarray(arr, dtype=np.int32)
@@ -265,8 +307,9 @@ class ContractionPlan:
         e.m_c = N.bits(Cb.pos[m] for m in st.m_modes)
         e.n_b = N.bits(B.pos[m] for m in st.n_modes)
         e.n_c = N.bits(Cb.pos[m] for m in st.n_modes)
-        e.k_a = N.bits(A.pos[m] for m in st.k_modes)
-        e.k_b = N.bits(B.pos[m] for m in st.k_modes_b)
+        korder = sorted(range(len(st.k_modes)), key=lambda i: A.pos[st.k_modes[i]])
+        e.k_a = N.bits(A.pos[st.k_modes[i]] for i in korder)
+        e.k_b = N.bits(B.pos[st.k_modes_b[i]] for i in korder)
         e.h_a = N.bits(A.pos[m] for m in st.h_modes)
         e.h_b = N.bits(B.pos[m] for m in st.h_modes_b)
         e.h_c = N.bits(Cb.pos[m] for m in st.h_modes)
@@ -310,10 +353,12 @@ class ContractionPlan:
     def n_slices(self):
         return 1 << self.n_sliced
 
-    def pack_leaves(self, leaves, out=None):
-        """Flatten the leaves the scheme uses into one contiguous complex array (the leaf blob).
+    def pack_leaves(self, leaves, device=None):
+        """Flatten the leaves the scheme uses into one contiguous complex64 array (the leaf blob).
         `leaves` is a list or dict of torch tensors as the reference takes them
-        (simulation.py:92-99 list, :168-171 dict)."""
+        (simulation.py:92-99 list, :168-171 dict).  Host leaves are gathered into one pinned
+        staging buffer and cross to `device` in a single copy; the reference moves every leaf
+        with its own `.to(device)` (simulation.py:93-99)."""
         import torch
         parts = []
         for tid in self.leaf_order:
@@ -321,11 +366,18 @@ class ContractionPlan:
             if tuple(t.shape) != self.full_leaf_shapes[tid]:
                 raise SchemeError(f"leaf {tid}: shape {tuple(t.shape)} differs from the planned {self.full_leaf_shapes[tid]}")
             parts.append(t.reshape(-1))
-        blob = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
-        if out is not None:
-            out.copy_(blob)
-            return out
-        return blob
+        on_host = all(p.device.type == "cpu" for p in parts)
+        if device is None or not on_host:
+            blob = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
+            blob = blob.to(torch.complex64)
+            return blob if device is None else blob.to(device)
+        stage = getattr(self, "_stage", None)
+        if stage is None or stage.numel() != self.leaf_blob_elems:
+            pin = torch.device(device).type == "cuda" and torch.cuda.is_available()
+            stage = torch.empty(self.leaf_blob_elems, dtype=torch.complex64, pin_memory=pin)
+            self._stage = stage
+        torch.cat(parts, out=stage) if parts[0].dtype == torch.complex64 else stage.copy_(torch.cat(parts))
+        return stage.to(device, non_blocking=True)
 
     def execute(self, leaf_blob, out, slice_begin, slice_end, workspace, stream_ptr):
         """Enqueue the contraction of slices [slice_begin, slice_end) on the given stream;
@@ -334,6 +386,16 @@ class ContractionPlan:
                                         out.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
                                         stream_ptr)
         N.check(rc)
+
+    def profile(self, leaf_blob, out, slice_id, workspace, stream_ptr):
+        """Per-operation device times (ms) of the ONCE phase and of one slice: two lists aligned
+        with self.ops[phase] (measurement aid for bench.py; synchronises)."""
+        n0, n1 = len(self.ops[N.TNC_PHASE_ONCE]), len(self.ops[N.TNC_PHASE_SLICE])
+        a0, a1 = (C.c_float * max(n0, 1))(), (C.c_float * max(n1, 1))()
+        N.check(self._lib.tnc_plan_profile(self._handle, leaf_blob.data_ptr(), int(slice_id), out.data_ptr(),
+                                           workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                           stream_ptr, a0, a1))
+        return list(a0)[:n0], list(a1)[:n1]
 
     @property
     def last_launches(self):

@@ -109,7 +109,7 @@ def _run(tensors, scheme, sparse):
         raise RuntimeError(f"artensor_b200: unsupported dtype {dt}; supported: {list(_DTYPES)}")
     plan = get_plan(scheme, tensors, sparse, dtype=_DTYPES[dt])
     with torch.cuda.device(dev):
-        blob = plan.pack_leaves(tensors)
+        blob = plan.pack_leaves(tensors, device=dev)
         out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
         ws = get_workspace(dev, plan.workspace_bytes)
         plan.execute(blob, out, 0, 1, ws, torch.cuda.current_stream(dev).cuda_stream)

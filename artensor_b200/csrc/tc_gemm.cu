@@ -1,15 +1,662 @@
-// Tensor-core (tcgen05) lowering of one einsum step -- placeholder until the kernel lands.
+// Tensor-core lowering of one scheme step (artensor/contraction.py:70, :147-190 call sites):
+//
+//   C[b][m, n] = sum_k A[ra[b]][m, k] * B[rb[b]][k, n]            (complex64)
+//
+// is executed as ONE real GEMM on the 5th-generation tensor cores.  complex64 storage is
+// interleaved, so a K-major complex panel A[M][K] *is* the real matrix A'[M][2K]; with
+//   B'[2n  ][2k] =  Br(k,n)   B'[2n  ][2k+1] = -Bi(k,n)
+//   B'[2n+1][2k] =  Bi(k,n)   B'[2n+1][2k+1] =  Br(k,n)
+// the product A' * B'^T is C in interleaved complex form (the "4M" formulation, no extra flops).
+// fp32 accuracy comes from the 3xTF32 split: x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and
+//   A'B' ~= lo*hi + hi*lo + hi*hi      (fp32 accumulation in tensor memory).
+//
+// Kernels in this file
+//   pack_kernel          bit-permutation of an operand into its K-major panel(s), tiled through
+//                        shared memory with an XOR swizzle (coalesced reads AND writes, no bank
+//                        conflicts); also does the hi/lo split and the B' expansion.  HBM bound.
+//   gemm3xtf32_kernel    warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B
+//                        swizzle), warp 1 = tcgen05.mma issuer (kind::tf32, accumulator in TMEM),
+//                        warps 2-5 = epilogue (tcgen05.ld -> registers -> global).  Tensor bound.
+#include <cuda.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "tc_gemm.h"
 
 namespace tnc {
 
-struct TcGemmOp {};
+namespace {
 
-int tc_gemm_create(const tnc_einsum&, int, const int32_t*, const int32_t*, TcGemmOp**) {
-    set_error("einsum: TNC_ALGO_TC is not available in this build");
-    return TNC_ERR_UNSUPPORTED;
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
-int tc_gemm_run(TcGemmOp*, const void*, const void*, void*, cudaStream_t, int*) { return TNC_ERR_UNSUPPORTED; }
+
+// =====================================================================================
+// pack kernel
+// =====================================================================================
+constexpr int kPackThreads = 256;
+constexpr int kPackMaxTileBits = 10;
+
+struct PackParams {
+    const float2* src;
+    float2* dst_hi;
+    float2* dst_lo;
+    const int32_t* rows;
+    int32_t rows_mode;
+    int32_t rank, tbits, mode, inner_bits, nb, n_outer, n_xor;
+    int64_t n_tiles;
+    int8_t tile_src_pos[kPackMaxTileBits];   // source position of tile bit j in SOURCE order (ascending)
+    int8_t tile_u2v[kPackMaxTileBits];       // destination-order tile bit that source-order bit j is
+    int8_t tile_dst_pos[kPackMaxTileBits];   // destination position of tile bit j in DESTINATION order
+    int8_t xor_from[kPackMaxTileBits], xor_to[kPackMaxTileBits];
+    int8_t outer_dst_pos[TNC_MAX_BITS], outer_src_pos[TNC_MAX_BITS];
+};
+
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackParams p) {
+    extern __shared__ __align__(16) unsigned char pack_smem[];
+    const int tile = 1 << p.tbits;
+    float2* data = (float2*)pack_smem;
+    uint32_t* src_off = (uint32_t*)(data + tile);
+    uint32_t* dst_off = src_off + tile;
+    uint16_t* slot_u = (uint16_t*)(dst_off + tile);   // swizzled smem slot of source-order element u
+    uint16_t* slot_v = slot_u + tile;                 // swizzled smem slot of destination-order element v
+    for (int x = threadIdx.x; x < tile; x += kPackThreads) {
+        uint32_t so = 0, dofs = 0, v = 0;
+        for (int j = 0; j < p.tbits; ++j) {
+            const uint32_t bit = (x >> j) & 1u;
+            so |= bit << p.tile_src_pos[j];
+            v |= bit << p.tile_u2v[j];
+            dofs |= bit << p.tile_dst_pos[j];
+        }
+        uint32_t sv = v, sx = x;
+        for (int j = 0; j < p.n_xor; ++j) {
+            sv ^= ((v >> p.xor_from[j]) & 1u) << p.xor_to[j];
+            sx ^= (((uint32_t)x >> p.xor_from[j]) & 1u) << p.xor_to[j];
+        }
+        src_off[x] = so;
+        dst_off[x] = dofs;
+        slot_u[x] = (uint16_t)sv;
+        slot_v[x] = (uint16_t)sx;
+    }
+    __syncthreads();
+    const int obits = p.rank - p.tbits;
+    const int64_t omask = (obits >= 63) ? -1 : (((int64_t)1 << obits) - 1);
+    const int64_t kmask = ((int64_t)1 << p.inner_bits) - 1;
+    for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int64_t blk = t >> obits;
+        const int64_t o = t & omask;
+        int64_t sbase = 0, dbase = 0;
+        for (int j = 0; j < p.n_outer; ++j) {
+            const int64_t bit = (o >> j) & 1;
+            sbase |= bit << p.outer_src_pos[j];
+            dbase |= bit << p.outer_dst_pos[j];
+        }
+        int64_t row = 0;
+        if (p.rows_mode == TNC_ROWS_IDENTITY) row = blk;
+        else if (p.rows_mode >= 0) row = p.rows[blk];
+        const float2* __restrict__ src = p.src + (row << p.rank) + sbase;
+        for (int u = threadIdx.x; u < tile; u += kPackThreads) data[slot_u[u]] = src[src_off[u]];
+        __syncthreads();
+        if (p.mode == PACK_COPY) {
+            float2* __restrict__ d = p.dst_hi + (blk << p.rank) + dbase;
+            for (int v = threadIdx.x; v < tile; v += kPackThreads) d[dst_off[v]] = data[slot_v[v]];
+        } else if (p.mode == PACK_SPLIT) {
+            float2* __restrict__ dh = p.dst_hi + (blk << p.rank) + dbase;
+            float2* __restrict__ dl = p.dst_lo + (blk << p.rank) + dbase;
+            for (int v = threadIdx.x; v < tile; v += kPackThreads) {
+                const float2 x = data[slot_v[v]];
+                const float2 h = make_float2(tf32_round(x.x), tf32_round(x.y));
+                dh[dst_off[v]] = h;
+                dl[dst_off[v]] = make_float2(tf32_round(x.x - h.x), tf32_round(x.y - h.y));
+            }
+        } else {
+            // B'[2n + c'][2k + c]: in float2 units the index is k | c' << inner | n << (inner + 1)
+            float2* __restrict__ dh = p.dst_hi + (blk << (p.rank + 1));
+            float2* __restrict__ dl = p.dst_lo + (blk << (p.rank + 1));
+            const int64_t K = (int64_t)1 << p.inner_bits;
+            for (int v = threadIdx.x; v < tile; v += kPackThreads) {
+                const float2 x = data[slot_v[v]];
+                const int64_t q = dbase + dst_off[v];
+                const int64_t e = (q & kmask) | ((q >> p.inner_bits) << (p.inner_bits + 1));
+                const float hr = tf32_round(x.x), hi = tf32_round(x.y);
+                const float lr = tf32_round(x.x - hr), li = tf32_round(x.y - hi);
+                dh[e] = make_float2(hr, -hi);
+                dh[e + K] = make_float2(hi, hr);
+                dl[e] = make_float2(lr, -li);
+                dl[e + K] = make_float2(li, lr);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, cudaStream_t s) {
+    if (d.rank < 0 || d.rank >= TNC_MAX_BITS || d.nb < 1) {
+        set_error("pack: bad descriptor (rank %d, blocks %d)", d.rank, d.nb);
+        return TNC_ERR_INVALID;
+    }
+    PackParams p{};
+    p.src = (const float2*)src;
+    p.dst_hi = (float2*)dst_hi;
+    p.dst_lo = (float2*)dst_lo;
+    p.rows = d.rows;
+    p.rows_mode = d.rows_mode;
+    p.rank = d.rank;
+    p.mode = d.mode;
+    p.inner_bits = d.inner_bits;
+    p.nb = d.nb;
+    const int r = d.rank;
+    const int lo = std::min(5, r);                 // contiguous run wanted on both sides: 2^5 * 8 B
+    // destination positions in the tile: the `lo` lowest destination bits and the destination
+    // bits fed by the `lo` lowest source bits
+    std::vector<int> in_tile(r, 0);
+    for (int i = 0; i < lo; ++i) in_tile[i] = 1;
+    for (int i = 0; i < r; ++i)
+        if (d.src_pos[i] < lo) in_tile[i] = 1;
+    std::vector<int> tdst;                          // destination order (ascending destination position)
+    for (int i = 0; i < r; ++i)
+        if (in_tile[i]) tdst.push_back(i);
+    const int t = (int)tdst.size();
+    if (t > kPackMaxTileBits) {
+        set_error("pack: tile of %d bits exceeds %d", t, kPackMaxTileBits);
+        return TNC_ERR_UNSUPPORTED;
+    }
+    std::vector<int> order(t);                      // source order: tile bits sorted by source position
+    for (int j = 0; j < t; ++j) order[j] = j;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return d.src_pos[tdst[x]] < d.src_pos[tdst[y]]; });
+    p.tbits = t;
+    for (int j = 0; j < t; ++j) {
+        p.tile_dst_pos[j] = (int8_t)tdst[j];
+        p.tile_src_pos[j] = d.src_pos[tdst[order[j]]];
+        p.tile_u2v[j] = (int8_t)order[j];
+    }
+    // XOR swizzle: every high tile bit driven by a low source bit is folded onto a low tile bit
+    // that no low source bit drives, so a warp walking the source order and a warp walking the
+    // destination order both touch 32 distinct 8-byte slots
+    std::vector<int> from, to;
+    std::vector<int> driven(t, 0);
+    for (int j = 0; j < std::min(lo, t); ++j) driven[order[j]] = 1;
+    for (int j = 0; j < std::min(lo, t); ++j)
+        if (order[j] >= lo) from.push_back(order[j]);
+    for (int j = 0; j < std::min(lo, t); ++j)
+        if (!driven[j]) to.push_back(j);
+    p.n_xor = (int)std::min(from.size(), to.size());
+    for (int j = 0; j < p.n_xor; ++j) {
+        p.xor_from[j] = (int8_t)from[j];
+        p.xor_to[j] = (int8_t)to[j];
+    }
+    p.n_outer = 0;
+    for (int i = 0; i < r; ++i)
+        if (!in_tile[i]) {
+            p.outer_dst_pos[p.n_outer] = (int8_t)i;
+            p.outer_src_pos[p.n_outer] = d.src_pos[i];
+            ++p.n_outer;
+        }
+    p.n_tiles = (int64_t)d.nb << (r - t);
+    const size_t smem = ((size_t)1 << t) * (sizeof(float2) + 2 * sizeof(uint32_t) + 2 * sizeof(uint16_t));
+    int64_t grid = std::min<int64_t>(p.n_tiles, (int64_t)sm_count() * 8);
+    pack_kernel<<<(unsigned)grid, kPackThreads, smem, s>>>(p);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+// =====================================================================================
+// tcgen05 GEMM
+// =====================================================================================
+namespace {
+
+constexpr int BM = 128;            // rows of A' per CTA tile (UMMA M)
+constexpr int BK = 32;             // fp32 per row per stage: 128 bytes = one 128B-swizzle atom
+constexpr int UMMA_K = 8;          // kind::tf32
+constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 epilogue
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_TILE = BM * BK * 4;
+    static constexpr int B_TILE = BN * BK * 4;
+    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int STAGES = (kSmemBudget / STAGE) > 6 ? 6 : (kSmemBudget / STAGE);
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2, "need a double buffer");
+};
+
+struct GemmArgs {
+    float* c;
+    int64_t c_batch_stride;   // floats
+    int32_t ldc;              // floats
+    int32_t M, N, K;          // real sizes: rows of A', rows of B' (= columns of C'), columns of A'/B'
+    int32_t m_tiles, n_tiles, group_m;
+    int32_t a_batched, b_batched;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: rows 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units      bits [0,14)
+    d |= (uint64_t)1 << 16;                     // leading byte offset (unused here)  bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset = 1024 B        bits [32,46)
+    d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)        bits [46,48)
+    d |= (uint64_t)2 << 61;                     // SWIZZLE_128B                       bits [61,64)
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  const GemmArgs g) {
+    using C = Cfg<BN>;
+    extern __shared__ unsigned char gemm_smem_raw[];
+    const uint32_t raw = smem_u32(gemm_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B swizzle wants 1024-byte aligned tiles
+    unsigned char* aligned = gemm_smem_raw + (base - raw);
+    const uint32_t bars = base + C::STAGES * C::STAGE;            // full[STAGES], empty[STAGES], accum, tmem slot
+    uint32_t* tmem_slot = (uint32_t*)(aligned + C::STAGES * C::STAGE + (2 * C::STAGES + 1) * 8);
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * C::STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates: groups of `group_m` row tiles sweep all column tiles, so that the CTAs
+    // resident at one time share a few A' panels and a few B' panels in L2
+    const int tiles_per_batch = g.m_tiles * g.n_tiles;
+    const int batch = blockIdx.x / tiles_per_batch;
+    const int r = blockIdx.x - batch * tiles_per_batch;
+    const int grp = r / (g.group_m * g.n_tiles);
+    const int first_m = grp * g.group_m;
+    const int gm = min(g.group_m, g.m_tiles - first_m);
+    const int within = r - grp * g.group_m * g.n_tiles;
+    const int m0 = (first_m + within % gm) * BM;
+    const int n0 = (within / gm) * BN;
+    const int nkb = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int ba = g.a_batched ? batch : 0, bb = g.b_batched ? batch : 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::STAGES;
+                const uint32_t ph = (kb / C::STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), C::STAGE);
+                const uint32_t st = base + s * C::STAGE;
+                tma_load_3d(st, &map_a_hi, full_bar(s), kb * BK, m0, ba);
+                tma_load_3d(st + C::A_TILE, &map_a_lo, full_bar(s), kb * BK, m0, ba);
+                tma_load_3d(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), kb * BK, n0, bb);
+                tma_load_3d(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), kb * BK, n0, bb);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t acc = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::STAGES;
+                const uint32_t ph = (kb / C::STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t st = base + s * C::STAGE;
+                const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::A_TILE);
+                const uint64_t b_hi = umma_desc(st + 2 * C::A_TILE), b_lo = umma_desc(st + 2 * C::A_TILE + C::B_TILE);
+                // small cross terms first, then the leading term; +2 = 32 bytes = one UMMA_K step
+#pragma unroll
+                for (int j = 0; j < BK / UMMA_K; ++j) {
+                    umma_tf32(tmem, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
+                    acc = 1;
+                }
+#pragma unroll
+                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tmem, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
+#pragma unroll
+                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tmem, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
+                umma_commit(empty_bar(s));     // frees the stage when these MMAs have read it
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                // TMEM lane quarter this warp is allowed to read
+        const int row = m0 + q * 32 + lane;
+        float* crow = g.c + (int64_t)batch * g.c_batch_stride + (int64_t)row * g.ldc + n0;
+        constexpr int CH = 16;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CH) {
+            uint32_t v[CH];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            tmem_ld_wait();
+            const int valid = g.N - (n0 + c);
+            if (row < g.M && valid > 0) {
+#pragma unroll
+                for (int j = 0; j < CH; j += 4)
+                    if (j < valid)
+                        *(float4*)(crow + c + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// fp32 panel [batch][rows][cols], cols contiguous; box = BK columns x box_rows rows, 128B swizzle
+int make_panel_map(CUtensorMap* map, void* addr, int64_t cols, int64_t rows, int64_t batch, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return TNC_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with %d (cols=%lld rows=%lld batch=%lld box_rows=%d)", (int)rc,
+                  (long long)cols, (long long)rows, (long long)batch, box_rows);
+        return TNC_ERR_CUDA;
+    }
+    return TNC_OK;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap* maps, const GemmArgs& g, int64_t tiles, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        TNC_CUDA(cudaFuncSetAttribute(gemm3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+        configured = true;
+    }
+    gemm3xtf32_kernel<BN><<<(unsigned)tiles, kGemmThreads, Cfg<BN>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], g);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct TcGemmOp {
+    PackDesc pa{}, pb{};
+    int64_t a_off = 0, b_off = 0, c_off = 0;          // operand offsets in the workspace (bytes)
+    int64_t ahi_off = 0, alo_off = 0, bhi_off = 0, blo_off = 0;
+    int64_t M = 0, N = 0, K = 0;                      // real GEMM sizes
+    int64_t batch = 1;
+    int a_batched = 0, b_batched = 0;
+    int bn = 256;
+    GemmArgs args{};
+    int64_t tiles = 0;
+    char* maps_for = nullptr;                         // workspace base the tensor maps were encoded for
+    CUtensorMap maps[4];
+};
+
+namespace {
+
+struct Shape {
+    int64_t nb_a, nb_b, batch, M, N, K;
+    int fold_rows;   // A's identity rows folded into M
+};
+
+int shape_of(const tnc_einsum& e, Shape* sh) {
+    if (e.n_h != 0) {
+        set_error("tensor-core einsum: shared kept modes are not supported");
+        return TNC_ERR_UNSUPPORTED;
+    }
+    if (e.n_k < 1 || e.n_n < 1) {
+        set_error("tensor-core einsum: needs at least one contracted and one right-only bit (k=%d, n=%d)", e.n_k, e.n_n);
+        return TNC_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < e.n_n; ++i)
+        if (e.n_c[i] >= e.n_n) {
+            set_error("tensor-core einsum: the right-only modes must occupy the %d lowest positions of the output", e.n_n);
+            return TNC_ERR_UNSUPPORTED;
+        }
+    // without rows on the right operand the gathered rows of A simply extend M
+    sh->fold_rows = e.rows_b == TNC_ROWS_NONE || e.nb == 1;
+    sh->nb_a = e.rows_a == TNC_ROWS_NONE ? 1 : e.nb;
+    sh->nb_b = e.rows_b == TNC_ROWS_NONE ? 1 : e.nb;
+    if (e.rows_a == TNC_ROWS_NONE && e.rows_b == TNC_ROWS_NONE && e.nb != 1) {
+        set_error("tensor-core einsum: %d output rows but neither operand has rows", e.nb);
+        return TNC_ERR_INVALID;
+    }
+    sh->batch = sh->fold_rows ? 1 : e.nb;
+    sh->M = ((int64_t)1 << e.n_m) * (sh->fold_rows ? sh->nb_a : 1);
+    sh->N = (int64_t)2 << e.n_n;
+    sh->K = (int64_t)2 << e.n_k;
+    if (sh->M >= ((int64_t)1 << 31) || sh->N >= ((int64_t)1 << 31) || sh->K >= ((int64_t)1 << 31) ||
+        sh->batch >= ((int64_t)1 << 31)) {
+        set_error("tensor-core einsum: a GEMM dimension exceeds 2^31");
+        return TNC_ERR_UNSUPPORTED;
+    }
+    return TNC_OK;
+}
+
+}  // namespace
+
+int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype) {
+    if (dtype != TNC_C64) {
+        set_error("tensor-core einsum: only complex64 is implemented");
+        return -1;
+    }
+    Shape sh;
+    if (shape_of(e, &sh) != TNC_OK) return -1;
+    const int64_t a_panel = align_up((sh.nb_a << (e.n_m + e.n_k)) * 8, 1024);
+    const int64_t b_panel = align_up((sh.nb_b << (e.n_n + e.n_k)) * 16, 1024);
+    return 2 * a_panel + 2 * b_panel;
+}
+
+int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, const int32_t* dev_rows_b, TcGemmOp** out) {
+    const int64_t need = tc_gemm_scratch_bytes(e, dtype);
+    if (need < 0) return TNC_ERR_UNSUPPORTED;
+    if (e.scratch_bytes < need || (e.scratch_offset & 1023)) {
+        set_error("tensor-core einsum: scratch region too small or misaligned (%lld < %lld)", (long long)e.scratch_bytes,
+                  (long long)need);
+        return TNC_ERR_NOMEM;
+    }
+    Shape sh;
+    shape_of(e, &sh);
+    for (int i = 0; i < e.n_m; ++i)
+        if (e.m_c[i] < e.n_n) {
+            set_error("tensor-core einsum: a left-only mode sits below the right-only modes in the output");
+            return TNC_ERR_UNSUPPORTED;
+        }
+    TcGemmOp* op = new TcGemmOp();
+    // A panel: [rows][m (output order)][k]  -- destination bits: k first, then m by output position
+    op->pa.rank = e.a.rank;
+    op->pa.nb = (int32_t)sh.nb_a;
+    op->pa.rows_mode = e.rows_a;
+    op->pa.rows = dev_rows_a;
+    op->pa.mode = PACK_SPLIT;
+    op->pa.inner_bits = e.n_k;
+    for (int i = 0; i < e.n_k; ++i) op->pa.src_pos[i] = e.k_a[i];
+    for (int i = 0; i < e.n_m; ++i) op->pa.src_pos[e.n_k + (e.m_c[i] - e.n_n)] = e.m_a[i];
+    // B' panel: [rows][n (output order)][c'][k][c]
+    op->pb.rank = e.b.rank;
+    op->pb.nb = (int32_t)sh.nb_b;
+    op->pb.rows_mode = e.rows_b;
+    op->pb.rows = dev_rows_b;
+    op->pb.mode = PACK_EXPAND_SPLIT;
+    op->pb.inner_bits = e.n_k;
+    for (int i = 0; i < e.n_k; ++i) op->pb.src_pos[i] = e.k_b[i];
+    for (int i = 0; i < e.n_n; ++i) op->pb.src_pos[e.n_k + e.n_c[i]] = e.n_b[i];
+    op->a_off = e.a.offset;
+    op->b_off = e.b.offset;
+    op->c_off = e.c.offset;
+    const int64_t a_panel = align_up((sh.nb_a << (e.n_m + e.n_k)) * 8, 1024);
+    const int64_t b_panel = align_up((sh.nb_b << (e.n_n + e.n_k)) * 16, 1024);
+    op->ahi_off = e.scratch_offset;
+    op->alo_off = op->ahi_off + a_panel;
+    op->bhi_off = op->alo_off + a_panel;
+    op->blo_off = op->bhi_off + b_panel;
+    op->M = sh.M;
+    op->N = sh.N;
+    op->K = sh.K;
+    op->batch = sh.batch;
+    op->a_batched = sh.batch > 1 && e.rows_a != TNC_ROWS_NONE;
+    op->b_batched = sh.batch > 1 && e.rows_b != TNC_ROWS_NONE;
+    op->bn = sh.N >= 256 ? 256 : sh.N >= 128 ? 128 : sh.N >= 64 ? 64 : sh.N >= 32 ? 32 : 16;
+    GemmArgs& g = op->args;
+    g.c_batch_stride = sh.M * sh.N;
+    g.ldc = (int32_t)sh.N;
+    g.M = (int32_t)sh.M;
+    g.N = (int32_t)sh.N;
+    g.K = (int32_t)sh.K;
+    g.m_tiles = (int32_t)((sh.M + BM - 1) / BM);
+    g.n_tiles = (int32_t)((sh.N + op->bn - 1) / op->bn);
+    g.group_m = 16;
+    g.a_batched = op->a_batched;
+    g.b_batched = op->b_batched;
+    op->tiles = (int64_t)g.m_tiles * g.n_tiles * sh.batch;
+    if (op->tiles >= ((int64_t)1 << 31)) {
+        delete op;
+        set_error("tensor-core einsum: too many tiles");
+        return TNC_ERR_UNSUPPORTED;
+    }
+    *out = op;
+    return TNC_OK;
+}
+
+int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* ctx, int* launches) {
+    int rc = launch_pack(op->pa, ws + op->a_off, ws + op->ahi_off, ws + op->alo_off, s);
+    if (rc != TNC_OK) return rc;
+    if (hook) hook(ctx);
+    rc = launch_pack(op->pb, ws + op->b_off, ws + op->bhi_off, ws + op->blo_off, s);
+    if (rc != TNC_OK) return rc;
+    if (hook) hook(ctx);
+    if (op->maps_for != ws) {
+        const int64_t rows_a = op->M;                              // folded rows are part of M
+        const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
+        if ((rc = make_panel_map(&op->maps[0], ws + op->ahi_off, op->K, rows_a, batch_a, BM)) != TNC_OK) return rc;
+        if ((rc = make_panel_map(&op->maps[1], ws + op->alo_off, op->K, rows_a, batch_a, BM)) != TNC_OK) return rc;
+        if ((rc = make_panel_map(&op->maps[2], ws + op->bhi_off, op->K, op->N, batch_b, op->bn)) != TNC_OK) return rc;
+        if ((rc = make_panel_map(&op->maps[3], ws + op->blo_off, op->K, op->N, batch_b, op->bn)) != TNC_OK) return rc;
+        op->maps_for = ws;
+    }
+    GemmArgs g = op->args;
+    g.c = (float*)(ws + op->c_off);
+    switch (op->bn) {
+        case 256: rc = launch_gemm<256>(op->maps, g, op->tiles, s); break;
+        case 128: rc = launch_gemm<128>(op->maps, g, op->tiles, s); break;
+        case 64: rc = launch_gemm<64>(op->maps, g, op->tiles, s); break;
+        case 32: rc = launch_gemm<32>(op->maps, g, op->tiles, s); break;
+        default: rc = launch_gemm<16>(op->maps, g, op->tiles, s); break;
+    }
+    if (rc != TNC_OK) return rc;
+    if (hook) hook(ctx);
+    if (launches) *launches = 3;
+    return TNC_OK;
+}
+
 void tc_gemm_destroy(TcGemmOp* op) { delete op; }
 
 }  // namespace tnc

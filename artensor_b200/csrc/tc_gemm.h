@@ -1,4 +1,6 @@
-// Tensor-core (tcgen05) lowering of one einsum step.
+// Tensor-core (tcgen05) lowering of one einsum step: two pack launches (bit-permutation of
+// each operand into a K-major panel, split into TF32 hi/lo parts; the right operand is also
+// expanded to its real 2N x 2K form) followed by one TMA-fed tcgen05 GEMM.
 #pragma once
 #include "tnc_internal.h"
 
@@ -6,10 +8,32 @@ namespace tnc {
 
 struct TcGemmOp;
 
-// Builds the device-side tables for running `e` on the tcgen05 path.  `rows_a` / `rows_b`
-// are the host copies of the row tables (nullptr for TNC_ROWS_NONE / TNC_ROWS_IDENTITY).
-int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* rows_a, const int32_t* rows_b, TcGemmOp** out);
-int tc_gemm_run(TcGemmOp* op, const void* a, const void* b, void* c, cudaStream_t s, int* launches);
+// Called after every kernel launch of an operation (profiling); may be null.
+typedef void (*LaunchHook)(void* ctx);
+
+// Bytes of scratch the lowering needs inside the workspace; <0 if the step cannot be lowered
+// (reason in tnc_last_error()).
+int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype);
+
+// `dev_rows_a` / `dev_rows_b`: device copies of the row tables (nullptr unless rows_* >= 0).
+int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
+                   TcGemmOp** out);
+int tc_gemm_run(TcGemmOp* op, char* workspace, cudaStream_t s, LaunchHook hook, void* ctx, int* launches);
 void tc_gemm_destroy(TcGemmOp* op);
+
+// ---------------------------------------------------------------- pack (bit-permutation) kernel
+// dst[b][q] = f(src[row(b)][p]) where bit i of q is bit src_pos[i] of p; tiled through shared
+// memory so that both the global reads and the global writes are contiguous runs.
+enum PackMode { PACK_COPY = 0, PACK_SPLIT = 1, PACK_EXPAND_SPLIT = 2 };
+struct PackDesc {
+    int32_t rank;                 // bits per block (source and destination)
+    int32_t nb;                   // destination blocks
+    int32_t rows_mode;            // TNC_ROWS_NONE / TNC_ROWS_IDENTITY / >= 0 (table)
+    const int32_t* rows;          // device table when rows_mode >= 0
+    int32_t mode;                 // PackMode
+    int32_t inner_bits;           // PACK_EXPAND_SPLIT: number of low destination bits that are k
+    int8_t src_pos[TNC_MAX_BITS]; // source position feeding destination position i
+};
+int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, cudaStream_t s);
 
 }  // namespace tnc

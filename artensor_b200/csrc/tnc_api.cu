@@ -331,8 +331,12 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
     for (int ph = 0; ph < 2; ++ph)
         for (auto& op : plan->ops[ph]) {
             if (op.kind != OP_EINSUM || op.e.algo != TNC_ALGO_TC) continue;
-            const int32_t* ra = op.e.rows_a >= 0 ? plan->tables[op.e.rows_a].data() : nullptr;
-            const int32_t* rb = op.e.rows_b >= 0 ? plan->tables[op.e.rows_b].data() : nullptr;
+            const int32_t* ra = op.e.rows_a >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[op.e.rows_a]) : nullptr;
+            const int32_t* rb = op.e.rows_b >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[op.e.rows_b]) : nullptr;
+            if (op.e.scratch_offset < 0 || op.e.scratch_offset + op.e.scratch_bytes > workspace_bytes) {
+                set_error("finalize: a tensor-core scratch region lies outside the declared arena");
+                return TNC_ERR_NOMEM;
+            }
             TcGemmOp* tc = nullptr;
             int rc = tc_gemm_create(op.e, plan->dtype, ra, rb, &tc);
             if (rc != TNC_OK) return rc;
@@ -353,7 +357,7 @@ int64_t tnc_plan_num_ops(const tnc_plan* plan, int32_t phase) {
 int64_t tnc_plan_last_launches(const tnc_plan* plan) { return plan ? plan->last_launches : -1; }
 
 static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_id, void* accum_out, char* ws,
-                  cudaStream_t st) {
+                  cudaStream_t st, LaunchHook hook = nullptr, void* hook_ctx = nullptr) {
     switch (op.kind) {
         case OP_LEAVES: {
             plan->last_launches += op.leaf_count > 0;
@@ -364,7 +368,7 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
             const tnc_einsum& e = op.e;
             if (op.tc) {
                 int launches = 0;
-                int rc = tc_gemm_run(op.tc.get(), ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, st, &launches);
+                int rc = tc_gemm_run(op.tc.get(), ws, st, hook, hook_ctx, &launches);
                 plan->last_launches += launches;
                 return rc;
             }
@@ -394,13 +398,22 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
             return launch_simt_einsum(p, plan->dtype, st);
         }
         case OP_PERMUTE: {
+            plan->last_launches += 1;
+            if (plan->dtype == TNC_C64) {
+                PackDesc d{};
+                d.rank = op.p.src.rank;
+                d.nb = op.p.src.rows;
+                d.rows_mode = TNC_ROWS_IDENTITY;
+                d.mode = PACK_COPY;
+                memcpy(d.src_pos, op.p.perm, sizeof(d.src_pos));
+                return launch_pack(d, ws + op.p.src.offset, ws + op.p.dst.offset, nullptr, st);
+            }
             PermuteParams p{};
             p.src = ws + op.p.src.offset;
             p.dst = ws + op.p.dst.offset;
             p.rank = op.p.src.rank;
             p.rows = op.p.src.rows;
             memcpy(p.perm, op.p.perm, sizeof(p.perm));
-            plan->last_launches += 1;
             return launch_permute(p, plan->elem_bytes(), st);
         }
         case OP_ACCUM: {
@@ -459,6 +472,75 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
     return TNC_OK;
 }
 
+namespace {
+struct ProfileCtx {
+    cudaStream_t st;
+    std::vector<cudaEvent_t> events;
+    bool failed = false;
+    void mark() {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess || cudaEventRecord(e, st) != cudaSuccess) failed = true;
+        else events.push_back(e);
+    }
+};
+void profile_hook(void* ctx) { ((ProfileCtx*)ctx)->mark(); }
+}  // namespace
+
+int tnc_plan_profile(tnc_plan* plan, const void* leaf_blob, uint64_t slice_id, void* accum_out, void* workspace,
+                     int64_t workspace_bytes, void* stream, float* ms_once, float* ms_slice) {
+    if (!plan || !plan->finalized) {
+        set_error("profile: plan is not finalized");
+        return TNC_ERR_STATE;
+    }
+    if (!leaf_blob || !accum_out || !workspace || !ms_once || !ms_slice || workspace_bytes < plan->workspace_bytes ||
+        ((uintptr_t)workspace & 255)) {
+        set_error("profile: bad arguments");
+        return TNC_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    plan->last_launches = 0;
+    float* outs[2] = {ms_once, ms_slice};
+    for (int ph = 0; ph < 2; ++ph) {
+        const size_t n = plan->ops[ph].size();
+        for (size_t i = 0; i < n * TNC_PROFILE_SLOTS; ++i) outs[ph][i] = 0.f;
+        ProfileCtx ctx;
+        ctx.st = st;
+        std::vector<size_t> first(n + 1, 0);      // index of the event that opens operation i
+        int rc = TNC_OK;
+        ctx.mark();
+        for (size_t i = 0; i < n && rc == TNC_OK; ++i) {
+            first[i] = ctx.events.size() - 1;
+            const size_t before = ctx.events.size();
+            rc = run_op(plan, plan->ops[ph][i], leaf_blob, slice_id, accum_out, ws, st, profile_hook, &ctx);
+            if (rc == TNC_OK && ctx.events.size() == before) ctx.mark();   // single-launch operation
+            if (ctx.failed && rc == TNC_OK) {
+                set_error("profile: could not record an event");
+                rc = TNC_ERR_CUDA;
+            }
+        }
+        first[n] = ctx.events.empty() ? 0 : ctx.events.size() - 1;
+        cudaError_t se = cudaStreamSynchronize(st);
+        if (rc == TNC_OK && se != cudaSuccess) rc = cuda_fail(se, "cudaStreamSynchronize");
+        if (rc == TNC_OK)
+            for (size_t i = 0; i < n; ++i) {
+                float* o = outs[ph] + i * TNC_PROFILE_SLOTS;
+                cudaEventElapsedTime(&o[0], ctx.events[first[i]], ctx.events[first[i + 1]]);
+                for (size_t k = first[i], slot = 1; k < first[i + 1] && slot < TNC_PROFILE_SLOTS; ++k, ++slot)
+                    cudaEventElapsedTime(&o[slot], ctx.events[k], ctx.events[k + 1]);
+            }
+        for (auto& e : ctx.events) cudaEventDestroy(e);
+        if (rc != TNC_OK) return rc;
+    }
+    return TNC_OK;
+}
+
+int64_t tnc_einsum_tc_scratch_bytes(int32_t dtype, const tnc_einsum* e) {
+    if (!e) return 0;
+    const int64_t n = tc_gemm_scratch_bytes(*e, dtype);
+    return n < 0 ? 0 : n;
+}
+
 int tnc_permute_bits(const void* src, void* dst, int32_t rank, int64_t rows, const int8_t* perm,
                      int32_t elem_bytes, void* stream) {
     if (!src || !dst || !perm || rank < 0 || rank >= TNC_MAX_BITS || rows < 1) {
@@ -467,6 +549,16 @@ int tnc_permute_bits(const void* src, void* dst, int32_t rank, int64_t rows, con
     }
     uint64_t seen = 0;
     if (!check_positions(perm, rank, rank, seen, "permute_bits perm")) return TNC_ERR_INVALID;
+    if (elem_bytes == 8 && rows < ((int64_t)1 << 31)) {
+        // complex64: the shared-memory tiled kernel (coalesced on both sides)
+        PackDesc d{};
+        d.rank = rank;
+        d.nb = (int32_t)rows;
+        d.rows_mode = TNC_ROWS_IDENTITY;
+        d.mode = PACK_COPY;
+        memcpy(d.src_pos, perm, rank);
+        return launch_pack(d, src, dst, nullptr, (cudaStream_t)stream);
+    }
     PermuteParams p{};
     p.src = src;
     p.dst = dst;

@@ -158,8 +158,7 @@ class TensorNetworkSimulation:
             pg = None if group is True else group
             begin, end = partition_slices(begin, end, dist.get_rank(pg), dist.get_world_size(pg))
         with torch.cuda.device(device):
-            leaves = {i: src[i].to(dtype).to(device, non_blocking=True) for i in ids}
-            blob = plan.pack_leaves(leaves)
+            blob = plan.pack_leaves({i: src[i] for i in ids}, device=device)
             collect_tensor = torch.zeros(plan.out_shape, dtype=torch.complex64, device=device)
             ws = _c.get_workspace(device, plan.workspace_bytes)
             plan.execute(blob, collect_tensor, begin, end, ws, torch.cuda.current_stream(device).cuda_stream)

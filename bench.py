@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- slice-contractions per second of the B200-native contraction executor.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N ...             (the reference's CPU torch path)
+
+Metric (BASELINE.json): slice-contractions/sec on a Sycamore n53 sliced contraction tree.
+Workload at N=1: BASELINE config 5, `n53_m20_sparse1024` -- the n53 m20 tree found by the
+reference's own order finder (sc_target=30, 50 sliced bonds), 1024 amplitudes per slice, a fixed
+subset of slice ids (the full task is 2^50 slices: time extrapolated, not run).  A *step* is one
+pass of the hot path over one batch of `--slices-per-step` slices per GPU followed by the ONE sum
+of the partial amplitudes (NCCL all-reduce when N > 1).  Weak scaling: every rank contracts its
+own `--slices-per-step` slices per step; `value` = slices all ranks contracted / max-over-ranks
+device time.
+
+Timed regions
+  value   leaf blob, plan, workspace already resident in HBM; CUDA events on the launching stream,
+          barrier + synchronize on both sides, max over ranks.  Working set per slice (8 GiB
+          intermediates) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
+  e2e     the same K steps through the public API `TensorNetworkSimulation.contraction` with HOST
+          leaf tensors: per step one pinned host->device copy of the leaf blob and one
+          device->host read of the amplitudes.
+  roofline  the dominant kernel of a slice (the fat tcgen05 GEMM) timed with CUDA events per launch
+          via tnc_plan_profile; achieved = 8*M*N*K algorithmic flops / that time.
+  cpu_baseline / --impl reference
+          the reference's own arithmetic (torch.einsum on CPU, oracle/tn_oracle_torch.py) on the
+          host cores, on a bounded sample of one slice: every step of the scheme is run on
+          synthetic operands of its true shape; steps larger than 2^24 elements are run on a
+          sub-block and scaled linearly.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "slice_contractions_per_sec"
+UNIT = "slices/s"
+DEFAULT_WORKLOAD = "n53_m20_sparse1024"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("TNC_BENCH_WORKLOAD", DEFAULT_WORKLOAD))
+    ap.add_argument("--slices-per-step", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tc-min-flops", type=float, default=None)
+    ap.add_argument("--cpu-max-elems", type=int, default=1 << 24)
+    return ap.parse_args()
+
+
+def load_workload(name):
+    from artensor_b200.cases import load_case
+    return load_case(os.path.join(ROOT, "tests", "golden", f"{name}.case.gz"))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def step_shapes_of(plan):
+    """(eq, shape_a, shape_b) of every scheme step with the shapes the reference's einsum sees
+    (gathered row counts for batched steps)."""
+    out = []
+    for st, raw in zip(plan.steps, plan.scheme_steps):
+        eq = raw[1]
+        sa, sb = [2] * st.a.rank, [2] * st.b.rank
+        if st.kind == "batched":
+            sa, sb = [st.nb] + sa, [st.nb] + sb
+        else:
+            if st.a.rows is not None:
+                sa = [st.a.rows] + sa
+            if st.b.rows is not None:
+                sb = [st.b.rows] + sb
+        out.append((eq, sa, sb))
+    return out
+
+
+def cpu_sample(plan, max_elems, budget_s=240.0):
+    import torch
+    from oracle import tn_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    secs, n, scaled, wall = OT.estimate_slice_seconds(step_shapes_of(plan), max_elems=max_elems, budget_s=budget_s)
+    return secs, n, scaled, wall
+
+
+def reference_arm(args):
+    """The reference's CPU path (torch.einsum per step) on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from artensor_b200.backend import ContractionPlan
+    case = load_workload(args.workload)
+    plan = plan_of(case, None, build_native=False)
+    cores = os.cpu_count() or 1
+    max_elems = args.cpu_max_elems
+    times = []
+    for it in range(args.warmup + args.steps):
+        secs, n, scaled, wall = cpu_sample(plan, max_elems)
+        if it >= args.warmup:
+            times.append(secs)
+    per_slice = sum(times) / len(times)
+    value = 1.0 / per_slice
+    sample = (f"one slice of {args.workload}: all {n} steps run with torch.einsum on synthetic operands of their true "
+              f"shapes; {scaled} steps above 2^{max_elems.bit_length() - 1} elements run on a sub-block and scaled "
+              f"linearly; {wall:.1f} s of CPU work per sample")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_slice * 1e3 * args.slices_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
+        "config": {"workload": args.workload, "slices_per_step_per_gpu": args.slices_per_step,
+                   "amplitudes_per_slice": int(plan.out_shape[0]) if plan.out_shape else 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "torch": torch.__version__},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def plan_of(case, tc_min_flops, build_native=True):
+    from artensor_b200.backend import ContractionPlan, PlanOptions
+    opts = PlanOptions() if tc_min_flops is None else PlanOptions(tc_min_flops=tc_min_flops)
+    plan = ContractionPlan(case.scheme, {k: tuple(v.shape) for k, v in case.leaves.items()}, case.pattern == "sparse",
+                           slicing_bonds=case.slicing_bonds, slicing_indices=case.slicing_indices(), options=opts,
+                           build_native=build_native)
+    plan.scheme_steps = case.scheme
+    return plan
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from artensor_b200 import TensorNetworkSimulation, PlanOptions
+    from artensor_b200 import _native as N
+    from artensor_b200 import contraction as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (artensor_b200 has no CPU fallback)")
+    N.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    case = load_workload(args.workload)
+    sim = TensorNetworkSimulation.from_case(case)
+    if args.tc_min_flops is not None:
+        sim.plan_options = PlanOptions(tc_min_flops=args.tc_min_flops)
+    plan = sim.plan()
+    plan.scheme_steps = case.scheme
+    S = args.slices_per_step
+    n_slices = plan.n_slices
+    total_steps = args.warmup + args.steps
+
+    def slice_range(step):
+        lo = ((step * world + rank) * S) % max(1, n_slices - S + 1) if n_slices > S else 0
+        return lo, min(lo + S, n_slices)
+
+    stream = torch.cuda.current_stream(dev)
+    blob = plan.pack_leaves(case.leaves, device=dev)
+    out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
+    ws = C.get_workspace(dev, plan.workspace_bytes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step(step):
+        lo, hi = slice_range(step)
+        out.zero_()
+        plan.execute(blob, out, lo, hi, ws, stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(out), op=dist.ReduceOp.SUM)
+        return hi - lo
+
+    # ---- device-resident throughput ("value")
+    for it in range(args.warmup):
+        one_step(it)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    done = 0
+    launches = 0
+    for it in range(args.warmup, total_steps):
+        done += one_step(it)
+        launches += plan.last_launches + 1          # + the accumulator clear
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(done)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, total_slices = float(t.item()), float(cnt.item())
+    value = total_slices / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        host = {k: v.pin_memory() for k, v in case.leaves.items()}
+
+        def e2e_step(it):
+            # the API block-partitions the range it is given over the ranks of the group
+            if world > 1:
+                glo = (it * world * S) % max(1, n_slices - world * S + 1)
+                r = sim.contraction(tensors=host, device=dev, slice_range=(glo, glo + world * S), group=True)
+            else:
+                r = sim.contraction(tensors=host, device=dev, slice_range=slice_range(it))
+            return r.cpu()          # device -> host read of the amplitudes
+
+        res = None
+        for it in range(min(2, args.warmup)):
+            res = e2e_step(it)
+        barrier()
+        t0 = time.perf_counter()
+        done2 = 0
+        for it in range(args.warmup, total_steps):
+            res = e2e_step(it)
+            done2 += S
+        barrier()
+        dt = time.perf_counter() - t0
+        t2 = torch.tensor([dt], dtype=torch.float64, device=dev)
+        c2 = torch.tensor([float(done2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c2, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(c2.item()) / float(t2.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(plan.leaf_blob_elems * 8), "d2h_bytes_per_step": int(res.numel() * 8)}
+
+    # ---- roofline of the dominant kernel, measured live (rank 0)
+    roofline, work, breakdown = None, plan.work_summary(), None
+    if rank == 0:
+        pk = peaks()
+        reps = 2
+        acc = None
+        for i in range(reps):
+            _, ms_slice = plan.profile(blob, out, slice_range(args.warmup + i)[0], ws, stream.cuda_stream)
+            acc = ms_slice if acc is None else [a + b for a, b in zip(acc, ms_slice)]
+        ms_slice = [a / reps for a in acc]
+        SL = N.TNC_PROFILE_SLOTS
+        ops = plan.ops[N.TNC_PHASE_SLICE]
+        steps = plan.op_steps[N.TNC_PHASE_SLICE]
+        slice_ms = sum(ms_slice[i * SL] for i in range(len(ops)))
+        best, best_ms = None, -1.0
+        gemm_ms = pack_ms = simt_ms = 0.0
+        for i, ((kind, rec), st) in enumerate(zip(ops, steps)):
+            if kind != "einsum":
+                continue
+            if rec.algo == N.TNC_ALGO_TC:
+                k_ms = ms_slice[i * SL + 3]
+                gemm_ms += k_ms
+                pack_ms += ms_slice[i * SL + 1] + ms_slice[i * SL + 2]
+            else:
+                k_ms = ms_slice[i * SL]
+                simt_ms += k_ms
+            if k_ms > best_ms:
+                best, best_ms = (i, rec, st), k_ms
+        i, rec, st = best
+        ai = st.flops / st.bytes_c64
+        tensor_bound = rec.algo == N.TNC_ALGO_TC and ai > 100
+        if tensor_bound:
+            ach = st.flops / (best_ms * 1e-3) / 1e12
+            peak = pk["bf16_tflops_sustained"]
+            roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": None, "peak_kind": f"bf16 dense sustained ({pk['source']})",
+                        "tensor_flops_issued_tflops": 3 * ach,
+                        "note": "achieved = 8*M*N*K useful complex64 flops; the 3xTF32 split issues 3x that on the "
+                                "tensor pipe at the TF32 rate (nominally half the bf16 rate), so the ceiling for useful "
+                                "flops is ~peak/6"}
+        else:
+            ach = st.bytes_c64 / (best_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                        "traffic": None, "peak_kind": f"copy bandwidth ({pk['source']})"}
+        roofline["kernel"] = "gemm3xtf32_kernel" if rec.algo == N.TNC_ALGO_TC else "simt_einsum_kernel"
+        roofline["step"] = {"index": st.index, "m_bits": len(st.m_modes), "n_bits": len(st.n_modes),
+                            "k_bits": len(st.k_modes), "rows": st.nb, "flops": st.flops, "bytes": st.bytes_c64,
+                            "ms": best_ms, "share_of_slice": best_ms / slice_ms}
+        breakdown = {"slice_ms_profiled": slice_ms, "gemm_ms": gemm_ms, "pack_ms": pack_ms, "simt_ms": simt_ms,
+                     "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            secs, n, scaled, wall = cpu_sample(plan, args.cpu_max_elems)
+            cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": (f"one slice of {args.workload}: all {n} steps run with torch.einsum on synthetic operands "
+                              f"of their true shapes, {scaled} steps above 2^{args.cpu_max_elems.bit_length() - 1} "
+                              f"elements on a sub-block and scaled linearly ({wall:.1f} s of CPU work)")}
+        except Exception as exc:  # the baseline must never take the GPU line down
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "complex64 (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": args.workload, "slices_per_step_per_gpu": S, "sliced_bonds": plan.n_sliced,
+                       "total_slices_of_task": f"2^{plan.n_sliced}", "amplitudes_per_slice": int(out.numel()),
+                       "scheme_steps": work["steps"], "l2": "working set >> L2 (multi-GiB intermediates), no flush"},
+            "useful_tflops": work["ref_flops_per_slice"] * value / 1e12,
+            "flops_per_slice": work["ref_flops_per_slice"], "bytes_per_slice": work["ref_bytes_per_slice"],
+            "extrapolated_full_task_seconds": (2.0 ** plan.n_sliced) / value,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "breakdown": breakdown,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

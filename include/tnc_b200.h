@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TNC_ABI_VERSION 1
+#define TNC_ABI_VERSION 2
 #define TNC_MAX_BITS 40          /* max bit modes per group / per tensor */
 #define TNC_MAX_SLICED 8         /* max sliced bonds on one leaf */
 
@@ -87,6 +87,8 @@ typedef struct tnc_einsum {
     int8_t h_a[TNC_MAX_BITS], h_b[TNC_MAX_BITS], h_c[TNC_MAX_BITS];
     int32_t algo;                /* tnc_algo */
     int32_t flags;               /* reserved, 0 */
+    int64_t scratch_offset;      /* TNC_ALGO_TC: byte offset of a scratch region of              */
+    int64_t scratch_bytes;       /* tnc_einsum_tc_scratch_bytes() bytes inside the workspace      */
 } tnc_einsum;
 
 /* dst[r][q] = src[r][p] where bit i of q equals bit perm[i] of p (a bit permutation of the
@@ -117,6 +119,9 @@ typedef struct tnc_accum {
     int8_t out_pos[TNC_MAX_BITS];        /* accumulator position of source position i */
 } tnc_accum;
 
+/* Scratch the tensor-core lowering of `e` needs (packed hi/lo operand panels); 0 on error. */
+int64_t tnc_einsum_tc_scratch_bytes(int32_t dtype, const tnc_einsum* e);
+
 /* ---- plan construction (host only, no CUDA calls until finalize) ---- */
 int tnc_abi_version(void);
 int tnc_plan_create(int32_t dtype, int32_t n_sliced_bonds, tnc_plan** out);
@@ -141,6 +146,17 @@ void tnc_plan_destroy(tnc_plan* plan);
 int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin,
                      uint64_t slice_end, void* accum_out, void* workspace,
                      int64_t workspace_bytes, void* stream);
+
+/* Same work as tnc_plan_execute for ONE slice id, but every kernel launch is bracketed by CUDA
+ * events on `stream` and the call synchronises.  ms_once / ms_slice hold TNC_PROFILE_SLOTS
+ * floats per operation (arrays sized TNC_PROFILE_SLOTS * tnc_plan_num_ops): slot 0 is the
+ * whole operation, slots 1.. are its individual launches in order (for a TNC_ALGO_TC einsum:
+ * pack A, pack B, tcgen05 GEMM), unused slots are 0.  Measurement aid for bench.py's roofline;
+ * not used on the product path. */
+#define TNC_PROFILE_SLOTS 4
+int tnc_plan_profile(tnc_plan* plan, const void* leaf_blob, uint64_t slice_id, void* accum_out,
+                     void* workspace, int64_t workspace_bytes, void* stream,
+                     float* ms_once, float* ms_slice);
 
 /* Stand-alone bit permutation (same kernel the plan uses); elem_bytes is 8 (c64) or 4. */
 int tnc_permute_bits(const void* src, void* dst, int32_t rank, int64_t rows,

@@ -42,6 +42,15 @@ def run_plan(plan, leaf_blob, slice_ids):
                 dst[:] = leaf_blob[L.src_offset + (row << L.src_rank) + so]
         elif kind == "einsum":
             E = rec
+            if E.algo == N.TNC_ALGO_TC:
+                # the scratch panels must not overlap any operand of the step, and the output
+                # must have the layout the tensor-core GEMM writes (n modes lowest)
+                lo, hi = E.scratch_offset, E.scratch_offset + E.scratch_bytes
+                assert hi <= plan.workspace_bytes and lo % 1024 == 0
+                for t in (E.a, E.b, E.c):
+                    assert t.offset + ((t.rows << t.rank) * 8) <= lo or t.offset >= hi, "scratch overlaps an operand"
+                assert sorted(E.n_c[i] for i in range(E.n_n)) == list(range(E.n_n))
+                assert E.n_k >= 1 and E.n_n >= 1 and E.n_h == 0
             A, B, Cv = _view(arena, E.a), _view(arena, E.b), _view(arena, E.c)
             e = np.arange(E.nb << E.c.rank, dtype=np.int64)
             row, cb = e >> E.c.rank, e & ((1 << E.c.rank) - 1)

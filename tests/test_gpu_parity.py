@@ -175,3 +175,88 @@ def test_native_errors_are_raised_not_fatal(dev):
     ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
     with pytest.raises(N.NativeError, match="slice range"):
         plan.execute(blob, out, 0, case.n_slices + 1, ws, torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) path
+# ---------------------------------------------------------------------------------------------
+LETTERS = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXY"
+
+
+def single_step_case(m, n, k, seed):
+    """One scheme step with m left-only, n right-only and k contracted bonds in shuffled mode
+    order, random complex64 leaves; returns (scheme, leaves, expected complex128 result)."""
+    rng = np.random.RandomState(seed)
+    lm, ln, lk = LETTERS[:m], LETTERS[m:m + n], LETTERS[m + n:m + n + k]
+    la = list(lm + lk)
+    lb = list(lk + ln)
+    lo = list(lm + ln)
+    rng.shuffle(la), rng.shuffle(lb), rng.shuffle(lo)
+    eq = "".join(la) + "," + "".join(lb) + "->" + "".join(lo)
+    a = (rng.randn(*[2] * (m + k)) + 1j * rng.randn(*[2] * (m + k))).astype(np.complex64)
+    b = (rng.randn(*[2] * (k + n)) + 1j * rng.randn(*[2] * (k + n))).astype(np.complex64)
+    want = np.einsum(eq, a.astype(np.complex128), b.astype(np.complex128), optimize=True)
+    return [((0, 1), eq)], {0: torch.from_numpy(a), 1: torch.from_numpy(b)}, want
+
+
+def run_single_step(dev, scheme, leaves, tc):
+    from artensor_b200 import ContractionPlan, PlanOptions
+    from artensor_b200 import _native as N
+    plan = ContractionPlan(scheme, {k: tuple(v.shape) for k, v in leaves.items()}, False,
+                           options=PlanOptions(tc_min_flops=0 if tc else float("inf")))
+    assert (N.TNC_ALGO_TC in plan.step_algo) == tc
+    blob = plan.pack_leaves({k: v.to(dev) for k, v in leaves.items()})
+    out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
+    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
+    plan.execute(blob, out, 0, 1, ws, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+TC_SHAPES = [(7, 3, 2), (8, 1, 1), (10, 5, 5), (6, 7, 9), (12, 4, 4), (3, 8, 6), (9, 9, 4), (5, 2, 3), (13, 6, 1),
+             (2, 1, 4), (8, 8, 8)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_single_step_matches_fp64_einsum(dev, shape):
+    m, n, k = shape
+    scheme, leaves, want = single_step_case(m, n, k, seed=m * 100 + n * 10 + k)
+    got = run_single_step(dev, scheme, leaves, tc=True)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    err = np.abs(got - want).max() / rms
+    assert err < 1e-5, f"m={m} n={n} k={k}: max err / rms = {err:.3e}"
+    ref = run_single_step(dev, scheme, leaves, tc=False)          # generic kernel on the same step
+    assert np.abs(ref - want).max() / rms < 1e-5
+
+
+def test_tc_long_contraction_keeps_fp32_accuracy(dev):
+    """K = 16384 complex (32768 real) accumulated in tensor memory: 3xTF32 must stay within the
+    complex64 bar (1e-5 of the rms amplitude) even for the longest contraction of the n53 tree."""
+    scheme, leaves, want = single_step_case(7, 6, 14, seed=5)
+    got = run_single_step(dev, scheme, leaves, tc=True)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    err = np.abs(got - want) / rms
+    print(f"K=16384 3xTF32: max err/rms {err.max():.3e}, rms err/rms {np.sqrt(np.mean(err ** 2)):.3e}")
+    assert err.max() < 1e-5
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_tc_forced_on_every_step_matches_reference(dev, name):
+    from artensor_b200 import PlanOptions
+    case, exp, sim = sim_from(name)
+    sim.plan_options = PlanOptions(tc_min_flops=0)
+    got = sim.contraction(device=dev).cpu().numpy()
+    want = exp["per_slice_c128"].sum(axis=0).reshape(exp["shape"])
+    if case.permute_dims is not None:
+        want = np.transpose(want, case.permute_dims)
+    assert_amplitudes_close(got, want)
+
+
+def test_n53_m20_one_slice_vs_reference(dev):
+    """BASELINE config 5 (the bench workload): one slice of the n53 m20 tree, 1024 amplitudes."""
+    case, exp, sim = sim_from("n53_m20_sparse1024")
+    s = int(exp["slice_ids"][0])
+    got = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()
+    assert_amplitudes_close(got, exp["per_slice_c64"][0])
+    from artensor_b200 import contraction as _c
+    _c.release_workspaces()

@@ -84,3 +84,26 @@ def test_oracle_n30_sliced_matches_reference_and_google():
     want = np.array([google[b] for b in case.bitstrings_sorted])
     rel = np.abs(total - want) / np.abs(want)
     assert np.median(rel) < 2e-4 and rel.max() < 2e-3
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_torch_oracle_matches_reference_goldens(name):
+    """The torch-on-CPU restatement (the CPU baseline that bench.py times) is pinned the same way."""
+    from oracle import tn_oracle_torch as OT
+    case, exp = load_golden(name)
+    ids = exp["slice_ids"]
+    for s in list(ids[:2]) + [ids[-1]]:
+        k = int(np.where(ids == s)[0][0])
+        r = OT.contract_slices(case, [int(s)]).reshape(-1).numpy()
+        assert _rel(r, exp["per_slice_c64"][k]) < 5e-6
+
+
+def test_torch_oracle_step_shrinking_is_linear():
+    from oracle import tn_oracle_torch as OT
+    eq, sa, sb, scale = OT._shrunk_step("abcde,efc->abdf", [2] * 5, [2, 2, 2], 8)
+    assert scale == 4 and eq == "abcde,efc->abdf" and sa == [1, 1, 2, 2, 2] and sb == [2, 2, 2]
+    # a shared row label is halved first, and only while the largest tensor is too large
+    eq, sa, sb, scale = OT._shrunk_step("zab,zbc->zac", [64, 2, 2], [64, 2, 2], 64)
+    assert scale == 4 and sa == [16, 2, 2] and sb == [16, 2, 2]
+    secs, n, scaled, _ = OT.estimate_slice_seconds([("abcde,efc->abdf", [2] * 5, [2, 2, 2])], max_elems=8)
+    assert n == 1 and scaled == 1 and secs > 0

@@ -165,3 +165,34 @@ def test_two_rank_slice_partition_gloo():
     case, exp = load_golden(name)
     want = exp["per_slice_c128"].sum(axis=0)
     assert np.abs(got.reshape(-1) - want).max() / np.abs(want).max() < 5e-6
+
+
+@pytest.mark.parametrize("name", ["n12_full", "n12_sparse64_sc9", "n12_sparse256c_sc10", "n12_sparse100_sc8"])
+def test_tensor_core_layouts_match_reference(name):
+    """Every eligible step lowered to the tensor-core form (C = [rows][m][n], scratch panels in
+    the arena): the records still evaluate to the reference's result."""
+    case, exp = load_golden(name)
+    plan = make_plan(case, options=PlanOptions(tc_min_flops=0))
+    assert N.TNC_ALGO_TC in plan.step_algo
+    blob = plan.pack_leaves(case.leaves).numpy()
+    ids = exp["slice_ids"]
+    for s in (int(ids[0]), int(ids[-1])):
+        k = int(np.where(ids == s)[0][0])
+        got = emulate.run_plan(plan, blob, [s]).reshape(-1)
+        want = exp["per_slice_c64"][k]
+        assert np.abs(got - want).max() / np.abs(want).max() < 5e-6
+
+
+def test_tc_scratch_formula_matches_library():
+    import ctypes as C
+    from artensor_b200.backend import tc_scratch_bytes
+    lib = N.load()
+    case, _ = load_golden("n12_sparse256c_sc10")
+    plan = make_plan(case, options=PlanOptions(tc_min_flops=0))
+    n = 0
+    for ph in plan.ops:
+        for (kind, rec), st in zip(plan.ops[ph], plan.op_steps[ph]):
+            if kind == "einsum" and rec.algo == N.TNC_ALGO_TC:
+                assert lib.tnc_einsum_tc_scratch_bytes(N.TNC_C64, C.byref(rec)) == tc_scratch_bytes(st) == rec.scratch_bytes
+                n += 1
+    assert n > 10
