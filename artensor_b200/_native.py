@@ -9,12 +9,12 @@ import os
 
 TNC_MAX_BITS = 40
 TNC_MAX_SLICED = 8
-TNC_ABI_VERSION = 2
+TNC_ABI_VERSION = 3
 TNC_PROFILE_SLOTS = 4
 
 TNC_C64, TNC_C32 = 0, 1
 TNC_PHASE_ONCE, TNC_PHASE_SLICE = 0, 1
-TNC_ALGO_SIMT, TNC_ALGO_TC = 0, 1
+TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM = 0, 1, 2
 TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
 
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "UNSUPPORTED", 5: "STATE"}

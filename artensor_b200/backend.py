@@ -89,7 +89,14 @@ def logical_positions(info: TensorInfo):
 
 @dataclass
 class PlanOptions:
-    tc_min_flops: float = 1e8    # steps at or above this many flops run on the tcgen05 path
+    """Algorithm selection per step:
+      * tcgen05 GEMM (3xTF32) for compute-bound steps: flops >= tc_min_flops and arithmetic
+        intensity (flops / algorithmic bytes) >= tc_min_intensity;
+      * the streaming fp32 kernel for the other large steps (HBM-bound "stem" steps);
+      * the generic kernel for the hundreds of tiny steps (< stem_min_elems output elements)."""
+    tc_min_flops: float = 1e8
+    tc_min_intensity: float = 24.0
+    stem_min_elems: int = 1 << 12
     hoist: bool = True
 
 
@@ -105,6 +112,12 @@ def tc_scratch_bytes(st: Step):
 
 def tc_eligible(st: Step):
     return len(st.k_modes) >= 1 and len(st.n_modes) >= 1 and len(st.h_modes) == 0
+
+
+def stem_eligible(st: Step):
+    """Mirror of stem_supported() in csrc/stem.cu: B[k][n] and the k offsets must fit shared memory."""
+    k, n = len(st.k_modes), len(st.n_modes)
+    return len(st.h_modes) == 0 and k <= 12 and n <= 12 and (8 << (k + n)) + (4 << k) <= 60 * 1024
 
 
 class ContractionPlan:
@@ -178,8 +191,12 @@ class ContractionPlan:
             A, B = bufs[st.i], bufs[st.j]
             phase = N.TNC_PHASE_SLICE if (A.dependent or B.dependent) else N.TNC_PHASE_ONCE
             algo = N.TNC_ALGO_SIMT
-            if st.flops >= self.options.tc_min_flops and tc_eligible(st) and self.dtype == N.TNC_C64:
-                algo = N.TNC_ALGO_TC
+            if self.dtype == N.TNC_C64:
+                o = self.options
+                if st.flops >= o.tc_min_flops and st.flops >= o.tc_min_intensity * st.bytes_c64 and tc_eligible(st):
+                    algo = N.TNC_ALGO_TC
+                elif st.c.numel >= o.stem_min_elems and stem_eligible(st):
+                    algo = N.TNC_ALGO_STEM
             cpos = self._choose_layout(st, A, B, algo)
             o, sz = arenas[phase].alloc(st.c.numel * self.elem_bytes)
             Cb = Buf(phase, o, sz, st.c, cpos, False, base)
@@ -273,7 +290,7 @@ class ContractionPlan:
         logical order.  The tensor-core GEMM writes C[rows][m][n] with the right-only modes in
         the low positions; inside each group the modes keep the order they have in their
         operand, which keeps the pack kernels' reads in long contiguous runs."""
-        if algo != N.TNC_ALGO_TC:
+        if algo == N.TNC_ALGO_SIMT:
             return logical_positions(st.c)
         pos = {}
         for i, m in enumerate(sorted(st.n_modes, key=lambda m: B.pos[m])):
@@ -388,14 +405,16 @@ class ContractionPlan:
         N.check(rc)
 
     def profile(self, leaf_blob, out, slice_id, workspace, stream_ptr):
-        """Per-operation device times (ms) of the ONCE phase and of one slice: two lists aligned
-        with self.ops[phase] (measurement aid for bench.py; synchronises)."""
+        """Per-operation device times (ms) of the ONCE phase and of one slice: two flat lists with
+        TNC_PROFILE_SLOTS entries per element of self.ops[phase] (slot 0 = whole operation, then
+        its launches).  Measurement aid for bench.py; synchronises."""
         n0, n1 = len(self.ops[N.TNC_PHASE_ONCE]), len(self.ops[N.TNC_PHASE_SLICE])
-        a0, a1 = (C.c_float * max(n0, 1))(), (C.c_float * max(n1, 1))()
+        SL = N.TNC_PROFILE_SLOTS
+        a0, a1 = (C.c_float * max(n0 * SL, 1))(), (C.c_float * max(n1 * SL, 1))()
         N.check(self._lib.tnc_plan_profile(self._handle, leaf_blob.data_ptr(), int(slice_id), out.data_ptr(),
                                            workspace.data_ptr(), workspace.numel() * workspace.element_size(),
                                            stream_ptr, a0, a1))
-        return list(a0)[:n0], list(a1)[:n1]
+        return list(a0)[:n0 * SL], list(a1)[:n1 * SL]
 
     @property
     def last_launches(self):

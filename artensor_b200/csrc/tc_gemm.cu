@@ -8,16 +8,23 @@
 //   B'[2n+1][2k] =  Bi(k,n)   B'[2n+1][2k+1] =  Br(k,n)
 // the product A' * B'^T is C in interleaved complex form (the "4M" formulation, no extra flops).
 // fp32 accuracy comes from the 3xTF32 split: x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and
-//   A'B' ~= lo*hi + hi*lo + hi*hi      (fp32 accumulation in tensor memory).
+//   A'B' ~= lo*hi + hi*lo + hi*hi.
+// The tensor core's fp32 accumulator rounds toward zero on every tcgen05.mma (measured on B200:
+// the error of a K = 32768 product grows linearly with K, 7e-4 of the rms), so tensor memory
+// only ever holds the sum of a short chunk (one k-block = 12 MMAs); the epilogue warps add the
+// chunks into fp32 registers with round-to-nearest while the next chunk is being computed in the
+// other half of tensor memory.
 //
 // Kernels in this file
 //   pack_kernel          bit-permutation of an operand into its K-major panel(s), tiled through
 //                        shared memory with an XOR swizzle (coalesced reads AND writes, no bank
 //                        conflicts); also does the hi/lo split and the B' expansion.  HBM bound.
 //   gemm3xtf32_kernel    warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B
-//                        swizzle), warp 1 = tcgen05.mma issuer (kind::tf32, accumulator in TMEM),
-//                        warps 2-5 = epilogue (tcgen05.ld -> registers -> global).  Tensor bound.
+//                        swizzle), warp 1 = tcgen05.mma issuer (kind::tf32, two accumulators in
+//                        TMEM), warps 2-9 = chunk accumulation + epilogue (tcgen05.ld -> fp32
+//                        registers -> global).  Tensor bound.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -225,7 +232,12 @@ namespace {
 constexpr int BM = 128;            // rows of A' per CTA tile (UMMA M)
 constexpr int BK = 32;             // fp32 per row per stage: 128 bytes = one 128B-swizzle atom
 constexpr int UMMA_K = 8;          // kind::tf32
-constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 epilogue
+constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter, each owning half of the columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-9 epilogue
+// k-blocks accumulated inside tensor memory before the fp32 register add.  Measured on B200
+// (tools/tc_calibrate.py): coherent shrink of the result per GEMM of -8.6e-8 at 1, -2.8e-7 at 2,
+// -6.6e-7 at 4; the fat GEMM runs within 7% of the same speed at 1.
+constexpr int kDefaultKC = 1;
 constexpr int kSmemBudget = 200 * 1024;
 
 template <int BN>
@@ -234,7 +246,8 @@ struct Cfg {
     static constexpr int B_TILE = BN * BK * 4;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
     static constexpr int STAGES = (kSmemBudget / STAGE) > 6 ? 6 : (kSmemBudget / STAGE);
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators (chunk double buffer)
+    static constexpr int CPT = BN / 2;                            // columns per epilogue thread
     static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment*/ + 256 /*barriers*/;
     static_assert(STAGES >= 2, "need a double buffer");
 };
@@ -246,6 +259,7 @@ struct GemmArgs {
     int32_t M, N, K;          // real sizes: rows of A', rows of B' (= columns of C'), columns of A'/B'
     int32_t m_tiles, n_tiles, group_m;
     int32_t a_batched, b_batched;
+    int32_t kc;               // k-blocks per TMEM accumulation chunk
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -255,6 +269,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -309,6 +326,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int BN>
@@ -321,11 +343,13 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const uint32_t raw = smem_u32(gemm_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B swizzle wants 1024-byte aligned tiles
     unsigned char* aligned = gemm_smem_raw + (base - raw);
-    const uint32_t bars = base + C::STAGES * C::STAGE;            // full[STAGES], empty[STAGES], accum, tmem slot
-    uint32_t* tmem_slot = (uint32_t*)(aligned + C::STAGES * C::STAGE + (2 * C::STAGES + 1) * 8);
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+    const uint32_t bars = base + C::STAGES * C::STAGE;
+    uint32_t* tmem_slot = (uint32_t*)(aligned + C::STAGES * C::STAGE + (2 * C::STAGES + 4) * 8);
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * C::STAGES);
+    auto tmem_full_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + b); };
+    auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + 2 + b); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -347,7 +371,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full_bar(b), 1);
+            mbar_init(tmem_empty_bar(b), kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -380,8 +407,16 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            uint32_t acc = 0;
+            const int KC = g.kc;
             for (int kb = 0; kb < nkb; ++kb) {
+                const int chunk = kb / KC;
+                const uint32_t tacc = tmem + (uint32_t)((chunk & 1) * BN);
+                uint32_t acc = 1;
+                if (kb % KC == 0) {            // a new chunk starts: its TMEM half must have been drained
+                    mbar_wait(tmem_empty_bar(chunk & 1), ((uint32_t)(chunk >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    acc = 0;
+                }
                 const int s = kb % C::STAGES;
                 const uint32_t ph = (kb / C::STAGES) & 1;
                 mbar_wait(full_bar(s), ph);
@@ -392,38 +427,58 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 // small cross terms first, then the leading term; +2 = 32 bytes = one UMMA_K step
 #pragma unroll
                 for (int j = 0; j < BK / UMMA_K; ++j) {
-                    umma_tf32(tmem, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
+                    umma_tf32(tacc, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
                     acc = 1;
                 }
 #pragma unroll
-                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tmem, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
+                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
 #pragma unroll
-                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tmem, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
+                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
                 umma_commit(empty_bar(s));     // frees the stage when these MMAs have read it
+                if (kb % KC == KC - 1 || kb == nkb - 1) umma_commit(tmem_full_bar(chunk & 1));
             }
-            umma_commit(accum_bar);
         }
         __syncwarp();
     } else {
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
         const int q = warp & 3;                // TMEM lane quarter this warp is allowed to read
-        const int row = m0 + q * 32 + lane;
-        float* crow = g.c + (int64_t)batch * g.c_batch_stride + (int64_t)row * g.ldc + n0;
-        constexpr int CH = 16;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += CH) {
-            uint32_t v[CH];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            tmem_ld_wait();
-            const int valid = g.N - (n0 + c);
-            if (row < g.M && valid > 0) {
+        const int half = (warp - 2) >> 2;      // which half of the tile's columns this warp owns
+        constexpr int CPT = C::CPT;
+        float acc[CPT];
 #pragma unroll
-                for (int j = 0; j < CH; j += 4)
-                    if (j < valid)
-                        *(float4*)(crow + c + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+        const int nchunks = (nkb + g.kc - 1) / g.kc;
+#pragma unroll 1
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            mbar_wait(tmem_full_bar(chunk & 1), (uint32_t)(chunk >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((chunk & 1) * BN + half * CPT);
+            if constexpr (CPT >= 16) {
+#pragma unroll
+                for (int c = 0; c < CPT; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[c + j] += __uint_as_float(v[j]);   // round-to-nearest fp32
+                }
+            } else {
+                uint32_t v[8];
+                tmem_ld8(taddr, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(v[j]);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(chunk & 1));
+        }
+        const int row = m0 + q * 32 + lane;
+        const int col0 = n0 + half * CPT;
+        if (row < g.M) {
+            float* crow = g.c + (int64_t)batch * g.c_batch_stride + (int64_t)row * g.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < CPT; j += 4)
+                if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
     }
     tc_fence_before();
@@ -616,6 +671,11 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     g.group_m = 16;
     g.a_batched = op->a_batched;
     g.b_batched = op->b_batched;
+    g.kc = kDefaultKC;
+    if (const char* env = getenv("TNC_TC_KC")) {       // experiment knob
+        const int v = atoi(env);
+        if (v >= 1 && v <= 64) g.kc = v;
+    }
     op->tiles = (int64_t)g.m_tiles * g.n_tiles * sh.batch;
     if (op->tiles >= ((int64_t)1 << 31)) {
         delete op;

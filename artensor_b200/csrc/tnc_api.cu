@@ -225,9 +225,14 @@ int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* e) {
                 return TNC_ERR_INVALID;
             }
     }
-    if (e->algo != TNC_ALGO_SIMT && e->algo != TNC_ALGO_TC) {
+    if (e->algo != TNC_ALGO_SIMT && e->algo != TNC_ALGO_TC && e->algo != TNC_ALGO_STEM) {
         set_error("einsum: unknown algo %d", e->algo);
         return TNC_ERR_INVALID;
+    }
+    if (e->algo == TNC_ALGO_STEM && !stem_supported(*e, plan->dtype)) {
+        set_error("einsum: the streaming kernel does not support this step (k=%d n=%d h=%d, output must be [rows][m][n])",
+                  e->n_k, e->n_n, e->n_h);
+        return TNC_ERR_UNSUPPORTED;
     }
     Op op;
     op.kind = OP_EINSUM;
@@ -371,6 +376,12 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
                 int rc = tc_gemm_run(op.tc.get(), ws, st, hook, hook_ctx, &launches);
                 plan->last_launches += launches;
                 return rc;
+            }
+            if (e.algo == TNC_ALGO_STEM) {
+                const int32_t* ra = e.rows_a >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_a]) : nullptr;
+                const int32_t* rb = e.rows_b >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_b]) : nullptr;
+                plan->last_launches += 1;
+                return launch_stem(e, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st);
             }
             SimtEinsumParams p{};
             p.a = ws + e.a.offset;

@@ -37,6 +37,12 @@ struct SimtEinsumParams {
 };
 int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s);
 
+// ---------------------------------------------------------------- streaming ("stem") einsum
+// HBM-bound steps: huge left operand, tiny right operand; output written as C[rows][m][n].
+bool stem_supported(const tnc_einsum& e, int dtype);
+int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
+                const int32_t* dev_rows_b, cudaStream_t s);
+
 // ---------------------------------------------------------------- leaves
 struct LeafDev {
     int64_t src_offset;      // elements

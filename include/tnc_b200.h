@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TNC_ABI_VERSION 2
+#define TNC_ABI_VERSION 3
 #define TNC_MAX_BITS 40          /* max bit modes per group / per tensor */
 #define TNC_MAX_SLICED 8         /* max sliced bonds on one leaf */
 
@@ -56,7 +56,8 @@ typedef enum tnc_phase {
 
 typedef enum tnc_algo {
     TNC_ALGO_SIMT = 0,           /* generic CUDA-core kernel, any shape */
-    TNC_ALGO_TC = 1              /* tcgen05 tensor-core kernel (3xTF32 for c64) */
+    TNC_ALGO_TC = 1,             /* tcgen05 tensor-core kernel (3xTF32 for c64): compute-bound steps */
+    TNC_ALGO_STEM = 2            /* streaming fp32 kernel for HBM-bound steps (tiny right operand) */
 } tnc_algo;
 
 /* Row table ids: a plan-owned int32 table (tnc_plan_add_table) or one of these. */

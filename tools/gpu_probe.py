@@ -53,7 +53,10 @@ def main():
         if "sample_idx" in exp:
             got = got[exp["sample_idx"]]
         rms = np.sqrt(np.mean(np.abs(want) ** 2))
-        print(f"check vs reference slice {a.slice}: max err / rms = {np.abs(got - want).max() / rms:.3e}", flush=True)
+        scale = (np.vdot(want.astype(np.complex128), got.astype(np.complex128)) / np.vdot(want.astype(np.complex128), want.astype(np.complex128)))
+        resid = got - scale * want
+        print(f"check vs reference slice {a.slice}: max err / rms = {np.abs(got - want).max() / rms:.3e}; best-fit scale - 1 = "
+              f"{scale - 1:.3e}; residual after scale max / rms = {np.abs(resid).max() / rms:.3e}", flush=True)
     SL = N.TNC_PROFILE_SLOTS
     rows = []
     for ph, arr in ((0, ms_once), (1, ms_slice)):
@@ -68,7 +71,7 @@ def main():
     by_algo = {}
     for r in rows:
         if r["phase"] == 1:
-            key = {None: r["kind"], 0: "simt", 1: "tc"}[r.get("algo")]
+            key = {None: r["kind"], 0: "simt", 1: "tc", 2: "stem"}[r.get("algo")]
             by_algo[key] = by_algo.get(key, 0.0) + r["ms"]
     print("by class:", {k: round(v, 3) for k, v in by_algo.items()})
     for r in sorted((r for r in rows if r["phase"] == 1), key=lambda r: -r["ms"])[:a.top]:
