@@ -59,7 +59,7 @@ struct PackParams {
     float2* dst_lo;
     const int32_t* rows;
     int32_t rows_mode;
-    int32_t rank, tbits, mode, inner_bits, nb, n_outer, n_xor;
+    int32_t rank, tbits, mode, inner_bits, nb, n_outer, n_xor, blocked, bn_log2;
     int64_t n_tiles;
     int8_t tile_src_pos[kPackMaxTileBits];   // source position of tile bit j in SOURCE order (ascending)
     int8_t tile_u2v[kPackMaxTileBits];       // destination-order tile bit that source-order bit j is
@@ -139,13 +139,24 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackParams p) 
             for (int v = threadIdx.x; v < tile; v += kPackThreads) {
                 const float2 x = data[slot_v[v]];
                 const int64_t q = dbase + dst_off[v];
-                const int64_t e = (q & kmask) | ((q >> p.inner_bits) << (p.inner_bits + 1));
+                int64_t e, second = K;
+                if (p.blocked) {
+                    // [n tile][k block][2n + c' within the tile][16 k]: one contiguous block per TMA box
+                    const int64_t k = q & kmask, n = q >> p.inner_bits;
+                    const int hb = p.bn_log2 - 1;
+                    const int64_t row = (n & (((int64_t)1 << hb) - 1)) << 1;
+                    const int64_t nkb = K >> 4;
+                    e = (k & 15) + 16 * (row + ((int64_t)1 << p.bn_log2) * ((k >> 4) + nkb * (n >> hb)));
+                    second = 16;
+                } else {
+                    e = (q & kmask) | ((q >> p.inner_bits) << (p.inner_bits + 1));
+                }
                 const float hr = tf32_round(x.x), hi = tf32_round(x.y);
                 const float lr = tf32_round(x.x - hr), li = tf32_round(x.y - hi);
                 dh[e] = make_float2(hr, -hi);
-                dh[e + K] = make_float2(hi, hr);
+                dh[e + second] = make_float2(hi, hr);
                 dl[e] = make_float2(lr, -li);
-                dl[e + K] = make_float2(li, lr);
+                dl[e + second] = make_float2(li, lr);
             }
         }
         __syncthreads();
@@ -169,6 +180,8 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
     p.mode = d.mode;
     p.inner_bits = d.inner_bits;
     p.nb = d.nb;
+    p.blocked = d.blocked;
+    p.bn_log2 = d.bn_log2;
     const int r = d.rank;
     const int lo = std::min(5, r);                 // contiguous run wanted on both sides: 2^5 * 8 B
     // destination positions in the tile: the `lo` lowest destination bits and the destination
@@ -177,6 +190,17 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
     for (int i = 0; i < lo; ++i) in_tile[i] = 1;
     for (int i = 0; i < r; ++i)
         if (d.src_pos[i] < lo) in_tile[i] = 1;
+    // a tile should carry enough elements to amortise its setup: grow it with the next lowest
+    // destination bits (keeps both sides' runs contiguous) up to 2^10 elements
+    {
+        int have = 0;
+        for (int i = 0; i < r; ++i) have += in_tile[i];
+        for (int i = 0; i < r && have < kPackMaxTileBits; ++i)
+            if (!in_tile[i]) {
+                in_tile[i] = 1;
+                ++have;
+            }
+    }
     std::vector<int> tdst;                          // destination order (ascending destination position)
     for (int i = 0; i < r; ++i)
         if (in_tile[i]) tdst.push_back(i);
@@ -260,7 +284,49 @@ struct GemmArgs {
     int32_t m_tiles, n_tiles, group_m;
     int32_t a_batched, b_batched;
     int32_t kc;               // k-blocks per TMEM accumulation chunk
+    int32_t tiles, rounds;    // persistent grid: CTA c runs tiles c, c + grid, ... (rounds of them)
+    int32_t blocked;          // panels are tile-contiguous: [tile][k-block][rows][32 floats]
+    int32_t sync_every;       // k-blocks between grid-wide lockstep barriers (0 = none)
+    uint32_t* sync_counter;   // zeroed before the launch
 };
+
+// Grid-wide barrier among the co-resident persistent CTAs (one thread per CTA calls it).  It only
+// keeps the CTAs within a few k-blocks of each other so that the operand panels they share are
+// still in L2 when the next CTA asks for them; the spin is bounded, a missing CTA costs time, not
+// correctness.
+__device__ __forceinline__ bool lockstep_barrier(uint32_t* counter, uint32_t target, bool wait) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    if (!wait) return false;
+    for (int spin = 0; spin < (1 << 15); ++spin) {
+        uint32_t v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) return true;
+        __nanosleep(64);
+    }
+    return false;      // a peer is missing (not co-resident): keep arriving but stop waiting
+}
+
+struct TileCoord {
+    int batch, m0, n0, m_tile, n_tile;
+};
+template <int BN>
+__device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
+    // groups of `group_m` row tiles sweep all column tiles, so that the CTAs resident at one time
+    // share a few A' panels and a few B' panels in L2
+    const int tiles_per_batch = g.m_tiles * g.n_tiles;
+    TileCoord t;
+    t.batch = tile / tiles_per_batch;
+    const int r = tile - t.batch * tiles_per_batch;
+    const int grp = r / (g.group_m * g.n_tiles);
+    const int first_m = grp * g.group_m;
+    const int gm = min(g.group_m, g.m_tiles - first_m);
+    const int within = r - grp * g.group_m * g.n_tiles;
+    t.m_tile = first_m + within % gm;
+    t.n_tile = within / gm;
+    t.m0 = t.m_tile * BM;
+    t.n0 = t.n_tile * BN;
+    return t;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -353,17 +419,6 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // tile coordinates: groups of `group_m` row tiles sweep all column tiles, so that the CTAs
-    // resident at one time share a few A' panels and a few B' panels in L2
-    const int tiles_per_batch = g.m_tiles * g.n_tiles;
-    const int batch = blockIdx.x / tiles_per_batch;
-    const int r = blockIdx.x - batch * tiles_per_batch;
-    const int grp = r / (g.group_m * g.n_tiles);
-    const int first_m = grp * g.group_m;
-    const int gm = min(g.group_m, g.m_tiles - first_m);
-    const int within = r - grp * g.group_m * g.n_tiles;
-    const int m0 = (first_m + within % gm) * BM;
-    const int n0 = (within / gm) * BN;
     const int nkb = (g.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -390,17 +445,39 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            const int ba = g.a_batched ? batch : 0, bb = g.b_batched ? batch : 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % C::STAGES;
-                const uint32_t ph = (kb / C::STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), C::STAGE);
-                const uint32_t st = base + s * C::STAGE;
-                tma_load_3d(st, &map_a_hi, full_bar(s), kb * BK, m0, ba);
-                tma_load_3d(st + C::A_TILE, &map_a_lo, full_bar(s), kb * BK, m0, ba);
-                tma_load_3d(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), kb * BK, n0, bb);
-                tma_load_3d(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), kb * BK, n0, bb);
+            uint32_t it = 0, epoch = 0;          // k-blocks loaded so far (stage ring position), barrier epochs
+            bool wait_peers = true;
+            for (int round = 0; round < g.rounds; ++round) {
+                const int tile = round * (int)gridDim.x + (int)blockIdx.x;
+                const bool valid = tile < g.tiles;
+                TileCoord t{};
+                if (valid) t = tile_coord<BN>(g, tile);
+                const int ba = g.a_batched ? t.batch : 0, bb = g.b_batched ? t.batch : 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (g.sync_every && kb % g.sync_every == 0)
+                        wait_peers = lockstep_barrier(g.sync_counter, ++epoch * gridDim.x, wait_peers);
+                    if (!valid) continue;
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    ++it;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), C::STAGE);
+                    const uint32_t st = base + s * C::STAGE;
+                    if (g.blocked) {
+                        // one contiguous [rows][32 floats] block per (tile, k-block)
+                        const int blk_a = kb + nkb * (t.m_tile + g.m_tiles * ba);
+                        const int blk_b = kb + nkb * (t.n_tile + g.n_tiles * bb);
+                        tma_load_3d(st, &map_a_hi, full_bar(s), 0, 0, blk_a);
+                        tma_load_3d(st + C::A_TILE, &map_a_lo, full_bar(s), 0, 0, blk_a);
+                        tma_load_3d(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), 0, 0, blk_b);
+                        tma_load_3d(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), 0, 0, blk_b);
+                    } else {
+                        tma_load_3d(st, &map_a_hi, full_bar(s), kb * BK, t.m0, ba);
+                        tma_load_3d(st + C::A_TILE, &map_a_lo, full_bar(s), kb * BK, t.m0, ba);
+                        tma_load_3d(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), kb * BK, t.n0, bb);
+                        tma_load_3d(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), kb * BK, t.n0, bb);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -408,34 +485,41 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const int KC = g.kc;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int chunk = kb / KC;
-                const uint32_t tacc = tmem + (uint32_t)((chunk & 1) * BN);
-                uint32_t acc = 1;
-                if (kb % KC == 0) {            // a new chunk starts: its TMEM half must have been drained
-                    mbar_wait(tmem_empty_bar(chunk & 1), ((uint32_t)(chunk >> 1) & 1u) ^ 1u);
+            uint32_t it = 0, gc = 0;             // k-blocks consumed, accumulation chunks produced
+            for (int round = 0; round < g.rounds; ++round) {
+                if (round * (int)gridDim.x + (int)blockIdx.x >= g.tiles) break;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t tacc = tmem + (uint32_t)((gc & 1u) * BN);
+                    uint32_t acc = 1;
+                    if (kb % KC == 0) {            // a new chunk starts: its TMEM half must have been drained
+                        mbar_wait(tmem_empty_bar(gc & 1u), ((gc >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        acc = 0;
+                    }
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    ++it;
+                    mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    acc = 0;
+                    const uint32_t st = base + s * C::STAGE;
+                    const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::A_TILE);
+                    const uint64_t b_hi = umma_desc(st + 2 * C::A_TILE), b_lo = umma_desc(st + 2 * C::A_TILE + C::B_TILE);
+                    // small cross terms first, then the leading term; +2 = 32 bytes = one UMMA_K step
+#pragma unroll
+                    for (int j = 0; j < BK / UMMA_K; ++j) {
+                        umma_tf32(tacc, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
+                        acc = 1;
+                    }
+#pragma unroll
+                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
+#pragma unroll
+                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
+                    umma_commit(empty_bar(s));     // frees the stage when these MMAs have read it
+                    if (kb % KC == KC - 1 || kb == nkb - 1) {
+                        umma_commit(tmem_full_bar(gc & 1u));
+                        ++gc;
+                    }
                 }
-                const int s = kb % C::STAGES;
-                const uint32_t ph = (kb / C::STAGES) & 1;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t st = base + s * C::STAGE;
-                const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::A_TILE);
-                const uint64_t b_hi = umma_desc(st + 2 * C::A_TILE), b_lo = umma_desc(st + 2 * C::A_TILE + C::B_TILE);
-                // small cross terms first, then the leading term; +2 = 32 bytes = one UMMA_K step
-#pragma unroll
-                for (int j = 0; j < BK / UMMA_K; ++j) {
-                    umma_tf32(tacc, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
-                    acc = 1;
-                }
-#pragma unroll
-                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
-#pragma unroll
-                for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
-                umma_commit(empty_bar(s));     // frees the stage when these MMAs have read it
-                if (kb % KC == KC - 1 || kb == nkb - 1) umma_commit(tmem_full_bar(chunk & 1));
             }
         }
         __syncwarp();
@@ -443,42 +527,55 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int q = warp & 3;                // TMEM lane quarter this warp is allowed to read
         const int half = (warp - 2) >> 2;      // which half of the tile's columns this warp owns
         constexpr int CPT = C::CPT;
-        float acc[CPT];
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
         const int nchunks = (nkb + g.kc - 1) / g.kc;
-#pragma unroll 1
-        for (int chunk = 0; chunk < nchunks; ++chunk) {
-            mbar_wait(tmem_full_bar(chunk & 1), (uint32_t)(chunk >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((chunk & 1) * BN + half * CPT);
-            if constexpr (CPT >= 16) {
+        uint32_t gc = 0;
+        for (int round = 0; round < g.rounds; ++round) {
+            const int tile = round * (int)gridDim.x + (int)blockIdx.x;
+            if (tile >= g.tiles) break;
+            const TileCoord t = tile_coord<BN>(g, tile);
+            float acc[CPT];
 #pragma unroll
-                for (int c = 0; c < CPT; c += 16) {
+            for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+#pragma unroll 1
+            for (int chunk = 0; chunk < nchunks; ++chunk, ++gc) {
+                mbar_wait(tmem_full_bar(gc & 1u), (gc >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gc & 1u) * BN + half * CPT);
+                if constexpr (CPT >= 32) {
+#pragma unroll
+                    for (int c = 0; c < CPT; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld16(taddr + c, v);
+                        tmem_ld16(taddr + c + 16, v + 16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);   // round-to-nearest fp32
+                    }
+                } else if constexpr (CPT == 16) {
                     uint32_t v[16];
-                    tmem_ld16(taddr + c, v);
+                    tmem_ld16(taddr, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[c + j] += __uint_as_float(v[j]);   // round-to-nearest fp32
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+                } else {
+                    uint32_t v[8];
+                    tmem_ld8(taddr, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(v[j]);
                 }
-            } else {
-                uint32_t v[8];
-                tmem_ld8(taddr, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(v[j]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar(gc & 1u));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(chunk & 1));
-        }
-        const int row = m0 + q * 32 + lane;
-        const int col0 = n0 + half * CPT;
-        if (row < g.M) {
-            float* crow = g.c + (int64_t)batch * g.c_batch_stride + (int64_t)row * g.ldc + col0;
+            const int row = t.m0 + q * 32 + lane;
+            const int col0 = t.n0 + half * CPT;
+            if (row < g.M) {
+                float* crow = g.c + (int64_t)t.batch * g.c_batch_stride + (int64_t)row * g.ldc + col0;
 #pragma unroll
-            for (int j = 0; j < CPT; j += 4)
-                if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                for (int j = 0; j < CPT; j += 4)
+                    if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            }
         }
     }
     tc_fence_before();
@@ -525,6 +622,26 @@ int make_panel_map(CUtensorMap* map, void* addr, int64_t cols, int64_t rows, int
     return TNC_OK;
 }
 
+// tile-contiguous panel: `blocks` blocks of [box_rows][BK floats], one block per (tile, k-block)
+int make_blocked_map(CUtensorMap* map, void* addr, int64_t blocks, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return TNC_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)box_rows, (cuuint64_t)blocks};
+    cuuint64_t strides[2] = {(cuuint64_t)BK * 4, (cuuint64_t)BK * 4 * (cuuint64_t)box_rows};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with %d (blocks=%lld box_rows=%d)", (int)rc, (long long)blocks, box_rows);
+        return TNC_ERR_CUDA;
+    }
+    return TNC_OK;
+}
+
 template <int BN>
 int launch_gemm(const CUtensorMap* maps, const GemmArgs& g, int64_t tiles, cudaStream_t s) {
     static bool configured = false;
@@ -532,7 +649,7 @@ int launch_gemm(const CUtensorMap* maps, const GemmArgs& g, int64_t tiles, cudaS
         TNC_CUDA(cudaFuncSetAttribute(gemm3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
         configured = true;
     }
-    gemm3xtf32_kernel<BN><<<(unsigned)tiles, kGemmThreads, Cfg<BN>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], g);
+    gemm3xtf32_kernel<BN><<<(unsigned)tiles, kGemmThreads, Cfg<BN>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], g);   // tiles = grid size
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }
@@ -553,6 +670,9 @@ struct TcGemmOp {
     int64_t tiles = 0;
     char* maps_for = nullptr;                         // workspace base the tensor maps were encoded for
     CUtensorMap maps[4];
+    int blocked = 0;                                  // tile-contiguous panels
+    int grid = 1;
+    uint32_t* sync_counter = nullptr;                 // device word for the lockstep barrier
 };
 
 namespace {
@@ -633,8 +753,27 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     op->pa.rows = dev_rows_a;
     op->pa.mode = PACK_SPLIT;
     op->pa.inner_bits = e.n_k;
-    for (int i = 0; i < e.n_k; ++i) op->pa.src_pos[i] = e.k_a[i];
-    for (int i = 0; i < e.n_m; ++i) op->pa.src_pos[e.n_k + (e.m_c[i] - e.n_n)] = e.m_a[i];
+    const int bn = sh.N >= 256 ? 256 : sh.N >= 128 ? 128 : sh.N >= 64 ? 64 : sh.N >= 32 ? 32 : 16;
+    // tile-contiguous panels need whole tiles: K a multiple of one k-block (16 complex), every row
+    // block a multiple of 128 rows, N a multiple of the tile width
+    op->blocked = e.n_k >= 4 && e.n_m >= 7 && sh.N >= bn;
+    if (const char* env = getenv("TNC_TC_BLOCKED"))
+        if (atoi(env) == 0) op->blocked = 0;
+    {
+        int8_t pm[TNC_MAX_BITS];                       // A position of row bit j (output order)
+        for (int i = 0; i < e.n_m; ++i) pm[e.m_c[i] - e.n_n] = e.m_a[i];
+        int d = 0;
+        if (op->blocked) {
+            // [m tile][k block][128 rows][16 k]
+            for (int i = 0; i < 4; ++i) op->pa.src_pos[d++] = e.k_a[i];
+            for (int j = 0; j < 7; ++j) op->pa.src_pos[d++] = pm[j];
+            for (int i = 4; i < e.n_k; ++i) op->pa.src_pos[d++] = e.k_a[i];
+            for (int j = 7; j < e.n_m; ++j) op->pa.src_pos[d++] = pm[j];
+        } else {
+            for (int i = 0; i < e.n_k; ++i) op->pa.src_pos[d++] = e.k_a[i];
+            for (int j = 0; j < e.n_m; ++j) op->pa.src_pos[d++] = pm[j];
+        }
+    }
     // B' panel: [rows][n (output order)][c'][k][c]
     op->pb.rank = e.b.rank;
     op->pb.nb = (int32_t)sh.nb_b;
@@ -642,6 +781,8 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     op->pb.rows = dev_rows_b;
     op->pb.mode = PACK_EXPAND_SPLIT;
     op->pb.inner_bits = e.n_k;
+    op->pb.blocked = op->blocked;
+    for (int l = 0; (1 << l) <= bn; ++l) op->pb.bn_log2 = l;
     for (int i = 0; i < e.n_k; ++i) op->pb.src_pos[i] = e.k_b[i];
     for (int i = 0; i < e.n_n; ++i) op->pb.src_pos[e.n_k + e.n_c[i]] = e.n_b[i];
     op->a_off = e.a.offset;
@@ -659,7 +800,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     op->batch = sh.batch;
     op->a_batched = sh.batch > 1 && e.rows_a != TNC_ROWS_NONE;
     op->b_batched = sh.batch > 1 && e.rows_b != TNC_ROWS_NONE;
-    op->bn = sh.N >= 256 ? 256 : sh.N >= 128 ? 128 : sh.N >= 64 ? 64 : sh.N >= 32 ? 32 : 16;
+    op->bn = bn;
     GemmArgs& g = op->args;
     g.c_batch_stride = sh.M * sh.N;
     g.ldc = (int32_t)sh.N;
@@ -682,6 +823,12 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
         set_error("tensor-core einsum: too many tiles");
         return TNC_ERR_UNSUPPORTED;
     }
+    g.tiles = (int32_t)op->tiles;
+    g.blocked = op->blocked;
+    // lockstep only pays off for long k loops shared by many tiles
+    const int nkb = (int)((sh.K + BK - 1) / BK);
+    g.sync_every = nkb >= 64 ? 16 : 0;
+    if (const char* env = getenv("TNC_TC_SYNC")) g.sync_every = nkb >= 64 ? atoi(env) : 0;
     *out = op;
     return TNC_OK;
 }
@@ -693,6 +840,16 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     rc = launch_pack(op->pb, ws + op->b_off, ws + op->bhi_off, ws + op->blo_off, s);
     if (rc != TNC_OK) return rc;
     if (hook) hook(ctx);
+    if (op->maps_for != ws && op->blocked) {
+        const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
+        const int64_t nkb = op->K / BK;
+        const int64_t blocks_a = nkb * op->args.m_tiles * batch_a, blocks_b = nkb * op->args.n_tiles * batch_b;
+        if ((rc = make_blocked_map(&op->maps[0], ws + op->ahi_off, blocks_a, BM)) != TNC_OK) return rc;
+        if ((rc = make_blocked_map(&op->maps[1], ws + op->alo_off, blocks_a, BM)) != TNC_OK) return rc;
+        if ((rc = make_blocked_map(&op->maps[2], ws + op->bhi_off, blocks_b, op->bn)) != TNC_OK) return rc;
+        if ((rc = make_blocked_map(&op->maps[3], ws + op->blo_off, blocks_b, op->bn)) != TNC_OK) return rc;
+        op->maps_for = ws;
+    }
     if (op->maps_for != ws) {
         const int64_t rows_a = op->M;                              // folded rows are part of M
         const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
@@ -704,12 +861,21 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     }
     GemmArgs g = op->args;
     g.c = (float*)(ws + op->c_off);
+    // persistent grid: one CTA per SM (the shared-memory footprint allows no more), every CTA
+    // walks tiles c, c + grid, ...
+    const int64_t grid = std::min<int64_t>(op->tiles, sm_count());
+    g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
+    if (g.sync_every) {
+        if (!op->sync_counter) TNC_CUDA(cudaMalloc((void**)&op->sync_counter, 256));
+        TNC_CUDA(cudaMemsetAsync(op->sync_counter, 0, 4, s));
+        g.sync_counter = op->sync_counter;
+    }
     switch (op->bn) {
-        case 256: rc = launch_gemm<256>(op->maps, g, op->tiles, s); break;
-        case 128: rc = launch_gemm<128>(op->maps, g, op->tiles, s); break;
-        case 64: rc = launch_gemm<64>(op->maps, g, op->tiles, s); break;
-        case 32: rc = launch_gemm<32>(op->maps, g, op->tiles, s); break;
-        default: rc = launch_gemm<16>(op->maps, g, op->tiles, s); break;
+        case 256: rc = launch_gemm<256>(op->maps, g, grid, s); break;
+        case 128: rc = launch_gemm<128>(op->maps, g, grid, s); break;
+        case 64: rc = launch_gemm<64>(op->maps, g, grid, s); break;
+        case 32: rc = launch_gemm<32>(op->maps, g, grid, s); break;
+        default: rc = launch_gemm<16>(op->maps, g, grid, s); break;
     }
     if (rc != TNC_OK) return rc;
     if (hook) hook(ctx);
@@ -717,6 +883,9 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     return TNC_OK;
 }
 
-void tc_gemm_destroy(TcGemmOp* op) { delete op; }
+void tc_gemm_destroy(TcGemmOp* op) {
+    if (op && op->sync_counter) cudaFree(op->sync_counter);
+    delete op;
+}
 
 }  // namespace tnc

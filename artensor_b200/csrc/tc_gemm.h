@@ -32,6 +32,8 @@ struct PackDesc {
     const int32_t* rows;          // device table when rows_mode >= 0
     int32_t mode;                 // PackMode
     int32_t inner_bits;           // PACK_EXPAND_SPLIT: number of low destination bits that are k
+    int32_t blocked;              // PACK_EXPAND_SPLIT: write tile-contiguous blocks [n tile][k block][rows][16 k]
+    int32_t bn_log2;              //   log2 of the rows (2n + c') per n tile
     int8_t src_pos[TNC_MAX_BITS]; // source position feeding destination position i
 };
 int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, cudaStream_t s);
