@@ -350,8 +350,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// A wait that cannot complete is a protocol bug: trap after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -585,6 +590,246 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
 }
 
+
+// =====================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x 256 tile.  Each CTA stages
+// its own 128 rows of A' and only HALF of the B' tile (128 of its 256 rows); the tensor cores of
+// both SMs read both halves.  Per k-block a CTA pulls 64 KB through L2 instead of 96 KB, and
+// three stages fit.  Rank 0 of the pair issues the MMAs; TMA completions of both CTAs signal its
+// `full` barrier; tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs; the epilogue
+// warps of both CTAs release a TMEM half by arriving on rank 0's `tmem_empty` barrier.
+// =====================================================================================
+struct Cfg2 {
+    static constexpr int BN = 256;
+    static constexpr int A_TILE = BM * BK * 4;          // this CTA's 128 rows of A'
+    static constexpr int B_TILE = (BN / 2) * BK * 4;    // this CTA's half of the B' tile
+    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int STAGES = 3;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int CPT = BN / 2;
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the barrier at the same offset in CTA rank 0
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    const uint32_t leader_bar = bar & 0xFEFFFFFFu;
+    const uint64_t evict_normal = 0x1000000000000000ull;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(evict_normal)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    const uint16_t both = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(both)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm3xtf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const GemmArgs g) {
+    using C = Cfg2;
+    constexpr int BN = C::BN;
+    extern __shared__ unsigned char gemm_smem_raw[];
+    const uint32_t raw = smem_u32(gemm_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* aligned = gemm_smem_raw + (base - raw);
+    const uint32_t bars = base + C::STAGES * C::STAGE;
+    uint32_t* tmem_slot = (uint32_t*)(aligned + C::STAGES * C::STAGE + (2 * C::STAGES + 4) * 8);
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tmem_full_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + b); };
+    auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + 2 + b); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)blockIdx.x >> 1, pairs = (int)gridDim.x >> 1;
+    const int nkb = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full_bar(b), 1);
+            mbar_init(tmem_empty_bar(b), 2 * kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers and TMEM are ready before anything targets them
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // pair tiles: g.m_tiles counts 128-row tiles; a pair covers two of them
+    GemmArgs gp = g;
+    gp.m_tiles = g.m_tiles / 2;
+    const int pair_tiles = g.tiles / 2;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, epoch = 0;
+            bool wait_peers = true;
+            for (int round = 0; round < g.rounds; ++round) {
+                const int tile = round * pairs + pair;
+                const bool valid = tile < pair_tiles;
+                TileCoord t{};
+                if (valid) t = tile_coord<BN>(gp, tile);      // m_tile counts 256-row pair tiles here
+                const int ba = g.a_batched ? t.batch : 0, bb = g.b_batched ? t.batch : 0;
+                const int m_tile128 = 2 * t.m_tile + (int)rank;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (g.sync_every && kb % g.sync_every == 0)
+                        wait_peers = lockstep_barrier(g.sync_counter, ++epoch * gridDim.x, wait_peers);
+                    if (!valid) continue;
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    ++it;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE);     // both CTAs' bytes land on rank 0's barrier
+                    const uint32_t st = base + s * C::STAGE;
+                    if (g.blocked) {
+                        const int blk_a = kb + nkb * (m_tile128 + g.m_tiles * ba);
+                        const int blk_b = kb + nkb * (t.n_tile + g.n_tiles * bb);
+                        tma_load_3d_2sm(st, &map_a_hi, full_bar(s), 0, 0, blk_a);
+                        tma_load_3d_2sm(st + C::A_TILE, &map_a_lo, full_bar(s), 0, 0, blk_a);
+                        tma_load_3d_2sm(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), 0, 128 * (int)rank, blk_b);
+                        tma_load_3d_2sm(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), 0, 128 * (int)rank, blk_b);
+                    } else {
+                        const int mrow = m_tile128 * BM, nrow = t.n0 + 128 * (int)rank;
+                        tma_load_3d_2sm(st, &map_a_hi, full_bar(s), kb * BK, mrow, ba);
+                        tma_load_3d_2sm(st + C::A_TILE, &map_a_lo, full_bar(s), kb * BK, mrow, ba);
+                        tma_load_3d_2sm(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), kb * BK, nrow, bb);
+                        tma_load_3d_2sm(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), kb * BK, nrow, bb);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // D fp32, A/B tf32, K-major, N = 256, M = 256 (128 rows in each CTA of the pair)
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const int KC = g.kc;
+            uint32_t it = 0, gc = 0;
+            for (int round = 0; round < g.rounds; ++round) {
+                if (round * pairs + pair >= pair_tiles) break;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t tacc = tmem + (uint32_t)((gc & 1u) * BN);
+                    uint32_t acc = 1;
+                    if (kb % KC == 0) {
+                        mbar_wait(tmem_empty_bar(gc & 1u), ((gc >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        acc = 0;
+                    }
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    ++it;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = base + s * C::STAGE;
+                    const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::A_TILE);
+                    const uint64_t b_hi = umma_desc(st + 2 * C::A_TILE), b_lo = umma_desc(st + 2 * C::A_TILE + C::B_TILE);
+#pragma unroll
+                    for (int j = 0; j < BK / UMMA_K; ++j) {
+                        umma_tf32_2sm(tacc, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
+                        acc = 1;
+                    }
+#pragma unroll
+                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32_2sm(tacc, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
+#pragma unroll
+                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32_2sm(tacc, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
+                    umma_commit_2sm(empty_bar(s));
+                    if (kb % KC == KC - 1 || kb == nkb - 1) {
+                        umma_commit_2sm(tmem_full_bar(gc & 1u));
+                        ++gc;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int CPT = C::CPT;
+        const int nchunks = (nkb + g.kc - 1) / g.kc;
+        uint32_t gc = 0;
+        for (int round = 0; round < g.rounds; ++round) {
+            const int tile = round * pairs + pair;
+            if (tile >= pair_tiles) break;
+            const TileCoord t = tile_coord<BN>(gp, tile);
+            float acc[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+#pragma unroll 1
+            for (int chunk = 0; chunk < nchunks; ++chunk, ++gc) {
+                mbar_wait(tmem_full_bar(gc & 1u), (gc >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gc & 1u) * BN + half * CPT);
+#pragma unroll
+                for (int c = 0; c < CPT; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld16(taddr + c + 16, v + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_on_cta(tmem_empty_bar(gc & 1u), 0);
+            }
+            const int row = (2 * t.m_tile + (int)rank) * BM + q * 32 + lane;
+            const int col0 = t.n0 + half * CPT;
+            if (row < g.M) {
+                float* crow = g.c + (int64_t)t.batch * g.c_batch_stride + (int64_t)row * g.ldc + col0;
+#pragma unroll
+                for (int j = 0; j < CPT; j += 4)
+                    if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // nobody leaves while the pair's MMAs may still read its shared memory
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -623,14 +868,14 @@ int make_panel_map(CUtensorMap* map, void* addr, int64_t cols, int64_t rows, int
 }
 
 // tile-contiguous panel: `blocks` blocks of [box_rows][BK floats], one block per (tile, k-block)
-int make_blocked_map(CUtensorMap* map, void* addr, int64_t blocks, int box_rows) {
+int make_blocked_map(CUtensorMap* map, void* addr, int64_t blocks, int block_rows, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
         return TNC_ERR_CUDA;
     }
-    cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)box_rows, (cuuint64_t)blocks};
-    cuuint64_t strides[2] = {(cuuint64_t)BK * 4, (cuuint64_t)BK * 4 * (cuuint64_t)box_rows};
+    cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)block_rows, (cuuint64_t)blocks};
+    cuuint64_t strides[2] = {(cuuint64_t)BK * 4, (cuuint64_t)BK * 4 * (cuuint64_t)block_rows};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -654,6 +899,28 @@ int launch_gemm(const CUtensorMap* maps, const GemmArgs& g, int64_t tiles, cudaS
     return TNC_OK;
 }
 
+int launch_gemm_2cta(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        TNC_CUDA(cudaFuncSetAttribute(gemm3xtf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg2::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm3xtf32_2cta_kernel, maps[0], maps[1], maps[2], maps[3], g));
+    return TNC_OK;
+}
+
 int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -671,6 +938,7 @@ struct TcGemmOp {
     char* maps_for = nullptr;                         // workspace base the tensor maps were encoded for
     CUtensorMap maps[4];
     int blocked = 0;                                  // tile-contiguous panels
+    int two_cta = 0;                                  // CTA pairs (cta_group::2) on 256 x 256 tiles
     int grid = 1;
     uint32_t* sync_counter = nullptr;                 // device word for the lockstep barrier
 };
@@ -825,6 +1093,9 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     }
     g.tiles = (int32_t)op->tiles;
     g.blocked = op->blocked;
+    op->two_cta = bn == 256 && sh.M % 256 == 0 && g.m_tiles >= 2;
+    if (const char* env = getenv("TNC_TC_2CTA"))
+        if (atoi(env) == 0) op->two_cta = 0;
     // lockstep only pays off for long k loops shared by many tiles
     const int nkb = (int)((sh.K + BK - 1) / BK);
     g.sync_every = nkb >= 64 ? 16 : 0;
@@ -844,10 +1115,10 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
         const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
         const int64_t nkb = op->K / BK;
         const int64_t blocks_a = nkb * op->args.m_tiles * batch_a, blocks_b = nkb * op->args.n_tiles * batch_b;
-        if ((rc = make_blocked_map(&op->maps[0], ws + op->ahi_off, blocks_a, BM)) != TNC_OK) return rc;
-        if ((rc = make_blocked_map(&op->maps[1], ws + op->alo_off, blocks_a, BM)) != TNC_OK) return rc;
-        if ((rc = make_blocked_map(&op->maps[2], ws + op->bhi_off, blocks_b, op->bn)) != TNC_OK) return rc;
-        if ((rc = make_blocked_map(&op->maps[3], ws + op->blo_off, blocks_b, op->bn)) != TNC_OK) return rc;
+        if ((rc = make_blocked_map(&op->maps[0], ws + op->ahi_off, blocks_a, BM, BM)) != TNC_OK) return rc;
+        if ((rc = make_blocked_map(&op->maps[1], ws + op->alo_off, blocks_a, BM, BM)) != TNC_OK) return rc;
+        if ((rc = make_blocked_map(&op->maps[2], ws + op->bhi_off, blocks_b, op->bn, op->two_cta ? 128 : op->bn)) != TNC_OK) return rc;
+        if ((rc = make_blocked_map(&op->maps[3], ws + op->blo_off, blocks_b, op->bn, op->two_cta ? 128 : op->bn)) != TNC_OK) return rc;
         op->maps_for = ws;
     }
     if (op->maps_for != ws) {
@@ -855,22 +1126,25 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
         const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
         if ((rc = make_panel_map(&op->maps[0], ws + op->ahi_off, op->K, rows_a, batch_a, BM)) != TNC_OK) return rc;
         if ((rc = make_panel_map(&op->maps[1], ws + op->alo_off, op->K, rows_a, batch_a, BM)) != TNC_OK) return rc;
-        if ((rc = make_panel_map(&op->maps[2], ws + op->bhi_off, op->K, op->N, batch_b, op->bn)) != TNC_OK) return rc;
-        if ((rc = make_panel_map(&op->maps[3], ws + op->blo_off, op->K, op->N, batch_b, op->bn)) != TNC_OK) return rc;
+        const int box_b = op->two_cta ? 128 : op->bn;
+        if ((rc = make_panel_map(&op->maps[2], ws + op->bhi_off, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
+        if ((rc = make_panel_map(&op->maps[3], ws + op->blo_off, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
         op->maps_for = ws;
     }
     GemmArgs g = op->args;
     g.c = (float*)(ws + op->c_off);
     // persistent grid: one CTA per SM (the shared-memory footprint allows no more), every CTA
     // walks tiles c, c + grid, ...
-    const int64_t grid = std::min<int64_t>(op->tiles, sm_count());
+    int64_t grid = std::min<int64_t>(op->tiles, sm_count());
+    if (op->two_cta) grid &= ~(int64_t)1;               // whole pairs; tiles is even here
     g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
     if (g.sync_every) {
         if (!op->sync_counter) TNC_CUDA(cudaMalloc((void**)&op->sync_counter, 256));
         TNC_CUDA(cudaMemsetAsync(op->sync_counter, 0, 4, s));
         g.sync_counter = op->sync_counter;
     }
-    switch (op->bn) {
+    if (op->two_cta) rc = launch_gemm_2cta(op->maps, g, grid, s);
+    else switch (op->bn) {
         case 256: rc = launch_gemm<256>(op->maps, g, grid, s); break;
         case 128: rc = launch_gemm<128>(op->maps, g, grid, s); break;
         case 64: rc = launch_gemm<64>(op->maps, g, grid, s); break;
