@@ -16,6 +16,7 @@ TNC_C64, TNC_C32 = 0, 1
 TNC_PHASE_ONCE, TNC_PHASE_SLICE = 0, 1
 TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM = 0, 1, 2
 TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
+TNC_EINSUM_OUTER_ROWS = 1
 
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "UNSUPPORTED", 5: "STATE"}
 

@@ -105,9 +105,18 @@ def tc_scratch_bytes(st: Step):
     al = lambda x: (x + 1023) // 1024 * 1024
     nb_a = st.nb if st.ra is not None else 1
     nb_b = st.nb if st.rb is not None else 1
+    if full_outer(st):
+        nb_a, nb_b = st.a.rows, st.b.rows
     a_panel = al((nb_a << (len(st.m_modes) + len(st.k_modes))) * 8)
     b_panel = al((nb_b << (len(st.n_modes) + len(st.k_modes))) * 16)
     return 2 * a_panel + 2 * b_panel
+
+
+def full_outer(st: Step):
+    """An outer step that keeps every (row of A, row of B) pair, A-major."""
+    return (st.kind == "outer" and st.a.rows is not None and st.b.rows is not None and
+            st.nb == st.a.rows * st.b.rows and np.array_equal(st.ra, np.arange(st.nb) // st.b.rows) and
+            np.array_equal(st.rb, np.arange(st.nb) % st.b.rows))
 
 
 def tc_eligible(st: Step):
@@ -331,7 +340,7 @@ class ContractionPlan:
         e.h_b = N.bits(B.pos[m] for m in st.h_modes_b)
         e.h_c = N.bits(Cb.pos[m] for m in st.h_modes)
         e.algo = algo
-        e.flags = 0
+        e.flags = N.TNC_EINSUM_OUTER_ROWS if full_outer(st) else 0
         return e
 
     def _build_native(self, ops):

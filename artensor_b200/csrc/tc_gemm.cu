@@ -286,6 +286,7 @@ struct GemmArgs {
     int32_t kc;               // k-blocks per TMEM accumulation chunk
     int32_t tiles, rounds;    // persistent grid: CTA c runs tiles c, c + grid, ... (rounds of them)
     int32_t blocked;          // panels are tile-contiguous: [tile][k-block][rows][32 floats]
+    int32_t outer_rj, outer_mb;   // outer-rows step: batch = row of B, GEMM row = (row of A, m): see c_row()
     int32_t sync_every;       // k-blocks between grid-wide lockstep barriers (0 = none)
     uint32_t* sync_counter;   // zeroed before the launch
 };
@@ -304,6 +305,14 @@ __device__ __forceinline__ bool lockstep_barrier(uint32_t* counter, uint32_t tar
         __nanosleep(64);
     }
     return false;      // a peer is missing (not co-resident): keep arriving but stop waiting
+}
+
+// Output row of C for GEMM row `row` of batch `batch`.  Outer-rows steps fold A's rows into the
+// GEMM rows and loop B's rows as the batch, while C wants the pair (ra, rb) outermost.
+__device__ __forceinline__ int64_t c_row(const GemmArgs& g, int batch, int row) {
+    if (g.outer_rj == 0) return (int64_t)batch * g.M + row;
+    const int64_t ra = row >> g.outer_mb;
+    return ((ra * g.outer_rj + batch) << g.outer_mb) + (row & ((1 << g.outer_mb) - 1));
 }
 
 struct TileCoord {
@@ -576,7 +585,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const int row = t.m0 + q * 32 + lane;
             const int col0 = t.n0 + half * CPT;
             if (row < g.M) {
-                float* crow = g.c + (int64_t)t.batch * g.c_batch_stride + (int64_t)row * g.ldc + col0;
+                float* crow = g.c + c_row(g, t.batch, row) * g.ldc + col0;
 #pragma unroll
                 for (int j = 0; j < CPT; j += 4)
                     if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -815,7 +824,7 @@ gemm3xtf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
             const int row = (2 * t.m_tile + (int)rank) * BM + q * 32 + lane;
             const int col0 = t.n0 + half * CPT;
             if (row < g.M) {
-                float* crow = g.c + (int64_t)t.batch * g.c_batch_stride + (int64_t)row * g.ldc + col0;
+                float* crow = g.c + c_row(g, t.batch, row) * g.ldc + col0;
 #pragma unroll
                 for (int j = 0; j < CPT; j += 4)
                     if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -948,6 +957,7 @@ namespace {
 struct Shape {
     int64_t nb_a, nb_b, batch, M, N, K;
     int fold_rows;   // A's identity rows folded into M
+    int outer;       // TNC_EINSUM_OUTER_ROWS lowering
 };
 
 int shape_of(const tnc_einsum& e, Shape* sh) {
@@ -973,7 +983,13 @@ int shape_of(const tnc_einsum& e, Shape* sh) {
         return TNC_ERR_INVALID;
     }
     sh->batch = sh->fold_rows ? 1 : e.nb;
-    sh->M = ((int64_t)1 << e.n_m) * (sh->fold_rows ? sh->nb_a : 1);
+    sh->outer = (e.flags & TNC_EINSUM_OUTER_ROWS) && e.nb > 1 && !sh->fold_rows;
+    if (sh->outer) {          // A's rows extend M, B's rows are the batch: nothing is gathered twice
+        sh->nb_a = e.a.rows;
+        sh->nb_b = e.b.rows;
+        sh->batch = e.b.rows;
+    }
+    sh->M = ((int64_t)1 << e.n_m) * ((sh->fold_rows || sh->outer) ? sh->nb_a : 1);
     sh->N = (int64_t)2 << e.n_n;
     sh->K = (int64_t)2 << e.n_k;
     if (sh->M >= ((int64_t)1 << 31) || sh->N >= ((int64_t)1 << 31) || sh->K >= ((int64_t)1 << 31) ||
@@ -1017,7 +1033,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     // A panel: [rows][m (output order)][k]  -- destination bits: k first, then m by output position
     op->pa.rank = e.a.rank;
     op->pa.nb = (int32_t)sh.nb_a;
-    op->pa.rows_mode = e.rows_a;
+    op->pa.rows_mode = sh.outer ? TNC_ROWS_IDENTITY : e.rows_a;
     op->pa.rows = dev_rows_a;
     op->pa.mode = PACK_SPLIT;
     op->pa.inner_bits = e.n_k;
@@ -1045,7 +1061,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     // B' panel: [rows][n (output order)][c'][k][c]
     op->pb.rank = e.b.rank;
     op->pb.nb = (int32_t)sh.nb_b;
-    op->pb.rows_mode = e.rows_b;
+    op->pb.rows_mode = sh.outer ? TNC_ROWS_IDENTITY : e.rows_b;
     op->pb.rows = dev_rows_b;
     op->pb.mode = PACK_EXPAND_SPLIT;
     op->pb.inner_bits = e.n_k;
@@ -1066,11 +1082,13 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     op->N = sh.N;
     op->K = sh.K;
     op->batch = sh.batch;
-    op->a_batched = sh.batch > 1 && e.rows_a != TNC_ROWS_NONE;
+    op->a_batched = sh.batch > 1 && e.rows_a != TNC_ROWS_NONE && !sh.outer;
     op->b_batched = sh.batch > 1 && e.rows_b != TNC_ROWS_NONE;
     op->bn = bn;
     GemmArgs& g = op->args;
     g.c_batch_stride = sh.M * sh.N;
+    g.outer_rj = sh.outer ? (int32_t)sh.nb_b : 0;
+    g.outer_mb = e.n_m;
     g.ldc = (int32_t)sh.N;
     g.M = (int32_t)sh.M;
     g.N = (int32_t)sh.N;

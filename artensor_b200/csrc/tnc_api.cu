@@ -225,6 +225,18 @@ int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* e) {
                 return TNC_ERR_INVALID;
             }
     }
+    if (e->flags & TNC_EINSUM_OUTER_ROWS) {
+        bool ok = (int64_t)e->a.rows * e->b.rows == e->nb && e->rows_a != TNC_ROWS_NONE && e->rows_b != TNC_ROWS_NONE;
+        for (int i = 0; ok && i < e->nb; ++i) {
+            const int ra = e->rows_a >= 0 ? plan->tables[e->rows_a][i] : i;
+            const int rb = e->rows_b >= 0 ? plan->tables[e->rows_b][i] : i;
+            ok = ra == i / e->b.rows && rb == i % e->b.rows;
+        }
+        if (!ok) {
+            set_error("einsum: TNC_EINSUM_OUTER_ROWS set but the rows are not all (A row, B row) pairs, A-major");
+            return TNC_ERR_INVALID;
+        }
+    }
     if (e->algo != TNC_ALGO_SIMT && e->algo != TNC_ALGO_TC && e->algo != TNC_ALGO_STEM) {
         set_error("einsum: unknown algo %d", e->algo);
         return TNC_ERR_INVALID;

@@ -60,6 +60,12 @@ typedef enum tnc_algo {
     TNC_ALGO_STEM = 2            /* streaming fp32 kernel for HBM-bound steps (tiny right operand) */
 } tnc_algo;
 
+/* tnc_einsum.flags.  OUTER_ROWS: the output rows enumerate ALL pairs of operand rows, A-major
+ * (row b = ra * b.rows + rb; the reference's two-batch-label einsum + reshape,
+ * artensor/contraction.py:180-185).  The row tables must say the same; the flag lets the
+ * tensor-core path fold A's rows into M and loop over B's rows instead of gathering copies. */
+#define TNC_EINSUM_OUTER_ROWS 1
+
 /* Row table ids: a plan-owned int32 table (tnc_plan_add_table) or one of these. */
 #define TNC_ROWS_NONE (-1)       /* operand has no row mode: always block 0 */
 #define TNC_ROWS_IDENTITY (-2)   /* source row == output row */
@@ -87,7 +93,7 @@ typedef struct tnc_einsum {
     int8_t k_a[TNC_MAX_BITS], k_b[TNC_MAX_BITS];
     int8_t h_a[TNC_MAX_BITS], h_b[TNC_MAX_BITS], h_c[TNC_MAX_BITS];
     int32_t algo;                /* tnc_algo */
-    int32_t flags;               /* reserved, 0 */
+    int32_t flags;               /* TNC_EINSUM_* bits */
     int64_t scratch_offset;      /* TNC_ALGO_TC: byte offset of a scratch region of              */
     int64_t scratch_bytes;       /* tnc_einsum_tc_scratch_bytes() bytes inside the workspace      */
 } tnc_einsum;

@@ -54,6 +54,8 @@ def run_plan(plan, leaf_blob, slice_ids):
             if E.algo == N.TNC_ALGO_STEM:
                 assert sorted(E.n_c[i] for i in range(E.n_n)) == list(range(E.n_n)) and E.n_h == 0
                 assert (8 << (E.n_k + E.n_n)) + (4 << E.n_k) <= 60 * 1024
+            if E.flags & N.TNC_EINSUM_OUTER_ROWS:
+                assert E.nb == E.a.rows * E.b.rows and E.rows_a != N.TNC_ROWS_NONE and E.rows_b != N.TNC_ROWS_NONE
             A, B, Cv = _view(arena, E.a), _view(arena, E.b), _view(arena, E.c)
             e = np.arange(E.nb << E.c.rank, dtype=np.int64)
             row, cb = e >> E.c.rank, e & ((1 << E.c.rank) - 1)
@@ -74,6 +76,8 @@ def run_plan(plan, leaf_blob, slice_ids):
                 if mode == N.TNC_ROWS_IDENTITY:
                     return row
                 return plan.tables[mode].astype(np.int64)[row]
+            if E.flags & N.TNC_EINSUM_OUTER_ROWS:
+                assert np.array_equal(rows(E.rows_a), row // E.b.rows) and np.array_equal(rows(E.rows_b), row % E.b.rows)
             oa += rows(E.rows_a) << E.a.rank
             ob += rows(E.rows_b) << E.b.rank
             k = np.arange(1 << E.n_k, dtype=np.int64)

@@ -284,3 +284,35 @@ def test_n53_m20_one_slice_vs_reference(dev):
     assert_amplitudes_close(got, exp["per_slice_c64"][0])
     from artensor_b200 import contraction as _c
     _c.release_workspaces()
+
+
+def test_n30_full_amplitude_slice_vs_reference(dev):
+    """BASELINE config 2: n30 m14 full amplitude (2^30 complex64 per slice, 4 slices).  The fixture
+    holds 8192 sampled entries of slice 0 in the executor's own output order and the slice's
+    squared norm."""
+    from artensor_b200 import contraction as _c
+    case, exp, sim = sim_from("n30_full")
+    sim.permute_dims = None
+    got = sim.contraction(device=dev, slice_range=(0, 1)).reshape(-1)
+    idx = torch.from_numpy(exp["sample_idx"]).to(dev)
+    assert_amplitudes_close(got[idx].cpu().numpy(), exp["per_slice_c64"][0])
+    norm2 = float(torch.view_as_real(got).double().pow(2).sum())
+    assert abs(norm2 / float(exp["per_slice_norm2"][0]) - 1.0) < 1e-5
+    del got
+    _c.release_workspaces()
+    torch.cuda.empty_cache()
+
+
+def test_n30_sparse_10000_amplitudes_vs_reference_and_google(dev):
+    """BASELINE config 3: n30 m14, the 10000 bitstrings of Google's amplitude file, unsliced
+    (sc_target 30): outer steps up to 1024 x 2^20, row subsets, one chunked batched step."""
+    from artensor_b200 import contraction as _c
+    case, exp, sim = sim_from("n30_sparse10000")
+    got = sim.contraction(device=dev).cpu().numpy()
+    assert_amplitudes_close(got, exp["per_slice_c64"][0])
+    google = dict(zip(case.extra["bitstrings_in"], case.extra["google_amplitudes"]))
+    want = np.array([google[b] for b in case.bitstrings_sorted])
+    rel = np.abs(got - want) / np.abs(want)
+    assert np.median(rel) < 2e-4 and np.quantile(rel, 0.99) < 5e-3
+    _c.release_workspaces()
+    torch.cuda.empty_cache()
