@@ -126,6 +126,36 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measure_tf32_peak(dev, seconds=1.0):
+    """cuBLAS TF32 GEMM 8192^3 (allow_tf32), the same way MEASURED_PEAKS.json measures bf16: best of
+    10 (burst) and back-to-back for `seconds` (sustained).  Only a denominator, never timed work."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(seconds * 1e3 / best))
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record(); torch.cuda.synchronize(dev)
+        flops = 2.0 * n ** 3
+        return {"burst": flops / (best * 1e-3) / 1e12, "sustained": flops * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def step_shapes_of(plan):
     """(eq, shape_a, shape_b) of every scheme step with the shapes the reference's einsum sees
     (gathered row counts for batched steps)."""
@@ -272,11 +302,11 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(done)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(done), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_max, total_slices = float(t.item()), float(cnt.item())
+    ms_max, total_slices, launches = float(t.item()), float(cnt[0].item()), int(cnt[1].item())
     value = total_slices / (ms_max * 1e-3)
 
     # ---- end to end through the public API with host buffers
@@ -327,7 +357,7 @@ def main():
         steps = plan.op_steps[N.TNC_PHASE_SLICE]
         slice_ms = sum(ms_slice[i * SL] for i in range(len(ops)))
         best, best_ms = None, -1.0
-        gemm_ms = pack_ms = simt_ms = 0.0
+        gemm_ms = pack_ms = simt_ms = stem_ms = 0.0
         for i, ((kind, rec), st) in enumerate(zip(ops, steps)):
             if kind != "einsum":
                 continue
@@ -335,6 +365,9 @@ def main():
                 k_ms = ms_slice[i * SL + 3]
                 gemm_ms += k_ms
                 pack_ms += ms_slice[i * SL + 1] + ms_slice[i * SL + 2]
+            elif rec.algo == N.TNC_ALGO_STEM:
+                k_ms = ms_slice[i * SL]
+                stem_ms += k_ms
             else:
                 k_ms = ms_slice[i * SL]
                 simt_ms += k_ms
@@ -346,22 +379,26 @@ def main():
         if tensor_bound:
             ach = st.flops / (best_ms * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
+            tf32 = measure_tf32_peak(dev)
             roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                         "traffic": None, "peak_kind": f"bf16 dense sustained ({pk['source']})",
-                        "tensor_flops_issued_tflops": 3 * ach,
-                        "note": "achieved = 8*M*N*K useful complex64 flops; the 3xTF32 split issues 3x that on the "
-                                "tensor pipe at the TF32 rate (nominally half the bf16 rate), so the ceiling for useful "
-                                "flops is ~peak/6"}
+                        "tf32": {"issued_tflops": 3 * ach, "cublas_tf32_burst": tf32["burst"],
+                                 "cublas_tf32_sustained": tf32["sustained"], "frac_of_sustained": 3 * ach / tf32["sustained"]},
+                        "note": "achieved = 8*M*N*K useful complex64 flops.  The kernel computes in TF32 (3xTF32 split): "
+                                "it issues 3x that many tensor flops at the TF32 rate, so the useful-flop ceiling is "
+                                "cublas_tf32/3; `tf32` compares issued TF32 flops with cuBLAS TF32 8192^3 measured in "
+                                "this run"}
         else:
             ach = st.bytes_c64 / (best_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "traffic": None, "peak_kind": f"copy bandwidth ({pk['source']})"}
-        roofline["kernel"] = "gemm3xtf32_kernel" if rec.algo == N.TNC_ALGO_TC else "simt_einsum_kernel"
+        roofline["kernel"] = {N.TNC_ALGO_TC: "gemm3xtf32_2cta_kernel", N.TNC_ALGO_STEM: "stem_kernel",
+                              N.TNC_ALGO_SIMT: "simt_einsum_kernel"}[rec.algo]
         roofline["step"] = {"index": st.index, "m_bits": len(st.m_modes), "n_bits": len(st.n_modes),
                             "k_bits": len(st.k_modes), "rows": st.nb, "flops": st.flops, "bytes": st.bytes_c64,
                             "ms": best_ms, "share_of_slice": best_ms / slice_ms}
-        breakdown = {"slice_ms_profiled": slice_ms, "gemm_ms": gemm_ms, "pack_ms": pack_ms, "simt_ms": simt_ms,
-                     "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms}
+        breakdown = {"slice_ms_profiled": slice_ms, "gemm_ms": gemm_ms, "pack_ms": pack_ms, "stem_ms": stem_ms,
+                     "generic_ms": simt_ms, "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms - stem_ms}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only)
     cpu = None
