@@ -9,7 +9,7 @@ import os
 
 TNC_MAX_BITS = 40
 TNC_MAX_SLICED = 8
-TNC_ABI_VERSION = 3
+TNC_ABI_VERSION = 4
 TNC_PROFILE_SLOTS = 4
 
 TNC_C64, TNC_C32 = 0, 1
@@ -17,6 +17,9 @@ TNC_PHASE_ONCE, TNC_PHASE_SLICE = 0, 1
 TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM = 0, 1, 2
 TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
 TNC_EINSUM_OUTER_ROWS = 1
+TNC_TC_3XTF32, TNC_TC_3XF16, TNC_TC_F16 = 0, 1, 2
+TNC_OPT_TC_PRECISION = 0
+TC_PRECISIONS = {"3xtf32": TNC_TC_3XTF32, "3xf16": TNC_TC_3XF16, "f16": TNC_TC_F16}
 
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "UNSUPPORTED", 5: "STATE"}
 
@@ -63,6 +66,7 @@ SYMBOLS = {
     "tnc_abi_version": (C.c_int, []),
     "tnc_einsum_tc_scratch_bytes": (C.c_int64, [C.c_int32, C.POINTER(TncEinsum)]),
     "tnc_plan_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "tnc_plan_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     "tnc_plan_add_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int32)]),
     "tnc_plan_add_leaves": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(TncLeaf), C.c_int32]),
     "tnc_plan_add_einsum": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(TncEinsum)]),

@@ -11,7 +11,8 @@ What is decided here:
   * arena offsets with liveness-based reuse (the reference lets torch allocate per einsum).
 """
 import ctypes as C
-from dataclasses import dataclass
+import os
+from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -90,14 +91,22 @@ def logical_positions(info: TensorInfo):
 @dataclass
 class PlanOptions:
     """Algorithm selection per step:
-      * tcgen05 GEMM (3xTF32) for compute-bound steps: flops >= tc_min_flops and arithmetic
-        intensity (flops / algorithmic bytes) >= tc_min_intensity;
+      * tcgen05 GEMM for compute-bound steps: flops >= tc_min_flops and arithmetic intensity
+        (flops / algorithmic bytes) >= tc_min_intensity;
       * the streaming fp32 kernel for the other large steps (HBM-bound "stem" steps);
-      * the generic kernel for the hundreds of tiny steps (< stem_min_elems output elements)."""
+      * the generic kernel for the hundreds of tiny steps (< stem_min_elems output elements).
+    tc_precision: operand precision of the tensor-core steps (include/tnc_b200.h tnc_tc_precision):
+      "3xf16" / "3xtf32" are fp32-accurate split products (complex64 mode), "f16" is the
+      reduced-precision complex-half mode."""
     tc_min_flops: float = 1e8
     tc_min_intensity: float = 24.0
     stem_min_elems: int = 1 << 12
     hoist: bool = True
+    tc_precision: str = field(default_factory=lambda: os.environ.get("TNC_TC_PRECISION", "3xf16"))
+
+    def __post_init__(self):
+        if self.tc_precision not in N.TC_PRECISIONS:
+            raise ValueError(f"tc_precision {self.tc_precision!r}: expected one of {sorted(N.TC_PRECISIONS)}")
 
 
 def tc_scratch_bytes(st: Step):
@@ -119,8 +128,11 @@ def full_outer(st: Step):
             np.array_equal(st.rb, np.arange(st.nb) % st.b.rows))
 
 
-def tc_eligible(st: Step):
-    return len(st.k_modes) >= 1 and len(st.n_modes) >= 1 and len(st.h_modes) == 0
+def tc_eligible(st: Step, precision="3xtf32"):
+    """Mirror of the checks in tc_gemm_create(): the fp16 panels need rows of >= 16 bytes (TMA),
+    i.e. at least 4 complex k per row."""
+    min_k = 1 if precision == "3xtf32" else 2
+    return len(st.k_modes) >= min_k and len(st.n_modes) >= 1 and len(st.h_modes) == 0
 
 
 def stem_eligible(st: Step):
@@ -202,7 +214,7 @@ class ContractionPlan:
             algo = N.TNC_ALGO_SIMT
             if self.dtype == N.TNC_C64:
                 o = self.options
-                if st.flops >= o.tc_min_flops and st.flops >= o.tc_min_intensity * st.bytes_c64 and tc_eligible(st):
+                if st.flops >= o.tc_min_flops and st.flops >= o.tc_min_intensity * st.bytes_c64 and tc_eligible(st, o.tc_precision):
                     algo = N.TNC_ALGO_TC
                 elif st.c.numel >= o.stem_min_elems and stem_eligible(st):
                     algo = N.TNC_ALGO_STEM
@@ -349,6 +361,7 @@ class ContractionPlan:
         N.check(lib.tnc_plan_create(self.dtype, self.n_sliced, C.byref(handle)))
         self._lib, self._handle = lib, handle
         try:
+            N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_TC_PRECISION, N.TC_PRECISIONS[self.options.tc_precision]))
             for t in self.tables:
                 tid = C.c_int32()
                 N.check(lib.tnc_plan_add_table(handle, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t), C.byref(tid)))
@@ -391,7 +404,7 @@ class ContractionPlan:
             t = leaves[tid]
             if tuple(t.shape) != self.full_leaf_shapes[tid]:
                 raise SchemeError(f"leaf {tid}: shape {tuple(t.shape)} differs from the planned {self.full_leaf_shapes[tid]}")
-            parts.append(t.reshape(-1))
+            parts.append(t.reshape(-1) if t.dtype == torch.complex64 else t.reshape(-1).to(torch.complex64))
         on_host = all(p.device.type == "cpu" for p in parts)
         if device is None or not on_host:
             blob = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
@@ -402,7 +415,7 @@ class ContractionPlan:
             pin = torch.device(device).type == "cuda" and torch.cuda.is_available()
             stage = torch.empty(self.leaf_blob_elems, dtype=torch.complex64, pin_memory=pin)
             self._stage = stage
-        torch.cat(parts, out=stage) if parts[0].dtype == torch.complex64 else stage.copy_(torch.cat(parts))
+        torch.cat(parts, out=stage)
         return stage.to(device, non_blocking=True)
 
     def execute(self, leaf_blob, out, slice_begin, slice_end, workspace, stream_ptr):

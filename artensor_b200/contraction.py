@@ -26,7 +26,18 @@ from . import _native as N
 from .backend import ContractionPlan, PlanOptions
 from .plan import SchemeError
 
-_DTYPES = {torch.complex64: "c64"}
+# torch dtype -> compute mode.  complex64: fp32-accurate split-precision tensor-core products.
+# complex32 (the reference would run torch.einsum in complex-half): the reduced-precision
+# tensor-core mode -- fp16 operands in the GEMM steps, fp32 accumulation, intermediates and the
+# returned amplitudes stay complex64 (n53 amplitudes are ~1e-8, below the fp16 range).
+_DTYPES = {torch.complex64: "c64", torch.complex32: "chalf"}
+
+
+def mode_options(mode, options=None):
+    """Plan options for a compute mode: "chalf" forces the single-product fp16 precision."""
+    from dataclasses import replace
+    options = options or default_options()
+    return replace(options, tc_precision="f16") if mode == "chalf" else options
 
 # scheme object id -> (weakref-free) cache of compiled plans keyed by leaf shapes / dtype.
 # Schemes are plain lists; we key on id() and keep a reference to the scheme so the id stays valid.
@@ -107,7 +118,7 @@ def _run(tensors, scheme, sparse):
     dt = tensors[ids[0]].dtype
     if dt not in _DTYPES:
         raise RuntimeError(f"artensor_b200: unsupported dtype {dt}; supported: {list(_DTYPES)}")
-    plan = get_plan(scheme, tensors, sparse, dtype=_DTYPES[dt])
+    plan = get_plan(scheme, tensors, sparse, options=mode_options(_DTYPES[dt]))
     with torch.cuda.device(dev):
         blob = plan.pack_leaves(tensors, device=dev)
         out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)

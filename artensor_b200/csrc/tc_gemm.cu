@@ -15,15 +15,30 @@
 // chunks into fp32 registers with round-to-nearest while the next chunk is being computed in the
 // other half of tensor memory.
 //
+//
+// Operand precisions (TcPrecision, tc_gemm.h) -- all accumulate in fp32:
+//   3xTF32   hi/lo are TF32 (11 + 11 significant bits), kind::tf32, 3 MMAs per useful one.
+//   3xF16    hi/lo are fp16 (11 + 11 significant bits, the same operand precision), kind::f16:
+//            the tensor pipe runs fp16 at twice the TF32 rate and the panels are half as large.
+//            fp16 has a 5-bit exponent, so each operand is first multiplied by a power of two
+//            that brings its largest magnitude into [2^14, 2^15) (amax_kernel finds it, the pack
+//            kernel applies it, the GEMM epilogue undoes it -- all exact); elements more than
+//            2^17 below the maximum lose low bits to fp16 subnormals, an absolute error below
+//            2^-39 of the maximum.
+//   F16      hi only: the reduced-precision complex-half mode (Pan et al. 2023), 1 MMA per
+//            useful one.
+//
 // Kernels in this file
+//   amax_kernel          largest |re|, |im| of both operands (one launch), fp16 precisions only.
 //   pack_kernel          bit-permutation of an operand into its K-major panel(s), tiled through
 //                        shared memory with an XOR swizzle (coalesced reads AND writes, no bank
 //                        conflicts); also does the hi/lo split and the B' expansion.  HBM bound.
-//   gemm3xtf32_kernel    warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B
-//                        swizzle), warp 1 = tcgen05.mma issuer (kind::tf32, two accumulators in
-//                        TMEM), warps 2-9 = chunk accumulation + epilogue (tcgen05.ld -> fp32
+//   gemm_kernel          warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B
+//   gemm_2cta_kernel     swizzle), warp 1 = tcgen05.mma issuer (two accumulators in TMEM),
+//                        warps 2-9 = chunk accumulation + epilogue (tcgen05.ld -> fp32
 //                        registers -> global).  Tensor bound.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -58,8 +73,9 @@ struct PackParams {
     float2* dst_hi;
     float2* dst_lo;
     const int32_t* rows;
+    const uint32_t* amax;                    // fp16 modes: bits of the operand's largest magnitude
     int32_t rows_mode;
-    int32_t rank, tbits, mode, inner_bits, nb, n_outer, n_xor, blocked, bn_log2;
+    int32_t rank, tbits, mode, inner_bits, nb, n_outer, n_xor, blocked, bn_log2, kb_log2;
     int64_t n_tiles;
     int8_t tile_src_pos[kPackMaxTileBits];   // source position of tile bit j in SOURCE order (ascending)
     int8_t tile_u2v[kPackMaxTileBits];       // destination-order tile bit that source-order bit j is
@@ -72,6 +88,48 @@ __device__ __forceinline__ float tf32_round(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+
+// Power-of-two scaling of an fp16-split operand.  e = biased exponent of the operand's largest
+// magnitude (clamped): scale = 2^(141 - e) maps it into [2^14, 2^15); inv_scale undoes it.
+__device__ __forceinline__ uint32_t amax_exponent(uint32_t amax_bits) {
+    const uint32_t e = (amax_bits >> 23) & 0xffu;
+    return e < 15u ? 15u : (e > 254u ? 254u : e);
+}
+__device__ __forceinline__ float f16_scale(uint32_t amax_bits) { return __uint_as_float((268u - amax_exponent(amax_bits)) << 23); }
+__device__ __forceinline__ float f16_inv_scale(uint32_t amax_bits) { return __uint_as_float((amax_exponent(amax_bits) - 14u) << 23); }
+
+// Largest |component| of two tensors in one launch: blocks [0, split) reduce `a`, the rest `b`;
+// out[0] / out[1] (zeroed before the launch) receive the float bits (non-negative floats order
+// like unsigned integers).
+__global__ void __launch_bounds__(256) amax_kernel(const float4* __restrict__ a, int64_t n4_a, const float4* __restrict__ b,
+                                                   int64_t n4_b, int split, uint32_t* out) {
+    const bool second = (int)blockIdx.x >= split;
+    const float4* __restrict__ src = second ? b : a;
+    const int64_t n4 = second ? n4_b : n4_a;
+    const int64_t nblk = second ? (int64_t)gridDim.x - split : split;
+    const int64_t blk = second ? (int64_t)blockIdx.x - split : blockIdx.x;
+    float m0 = 0.f, m1 = 0.f;
+    int64_t i = blk * 256 + threadIdx.x;
+    const int64_t stride = nblk * 256;
+    for (; i + stride < n4; i += 2 * stride) {          // two independent loads in flight
+        const float4 x = src[i], y = src[i + stride];
+        m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+        m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+    }
+    if (i < n4) {
+        const float4 x = src[i];
+        m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+    }
+    uint32_t bits = __float_as_uint(fmaxf(m0, m1));
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    __shared__ uint32_t warp_max[8];
+    if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        bits = __reduce_max_sync(0xffu, warp_max[threadIdx.x]);
+        if (threadIdx.x == 0 && bits) atomicMax(out + (second ? 1 : 0), bits);
+    }
 }
 
 __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackParams p) {
@@ -131,32 +189,65 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackParams p) 
                 dh[dst_off[v]] = h;
                 dl[dst_off[v]] = make_float2(tf32_round(x.x - h.x), tf32_round(x.y - h.y));
             }
+        } else if (p.mode == PACK_SPLIT_F16) {
+            // A panel in fp16: one __half2 (re, im) per amplitude, scaled by a power of two
+            const float sc = f16_scale(*p.amax);
+            __half2* __restrict__ dh = (__half2*)p.dst_hi + (blk << p.rank) + dbase;
+            __half2* __restrict__ dl = p.dst_lo ? (__half2*)p.dst_lo + (blk << p.rank) + dbase : nullptr;
+            for (int v = threadIdx.x; v < tile; v += kPackThreads) {
+                const float2 x = data[slot_v[v]];
+                const float xr = x.x * sc, xi = x.y * sc;
+                const __half2 h = __floats2half2_rn(xr, xi);
+                dh[dst_off[v]] = h;
+                if (dl) {
+                    const float2 hf = __half22float2(h);
+                    dl[dst_off[v]] = __floats2half2_rn(xr - hf.x, xi - hf.y);
+                }
+            }
         } else {
-            // B'[2n + c'][2k + c]: in float2 units the index is k | c' << inner | n << (inner + 1)
+            // B'[2n + c'][2k + c]: in (re, im)-pair units the index is k | c' << inner | n << (inner + 1)
+            const bool f16 = p.mode == PACK_EXPAND_SPLIT_F16;
+            const int64_t K = (int64_t)1 << p.inner_bits;
+            const int kbl = p.kb_log2;                       // complex k per k-block: 16 (tf32) or 32 (fp16)
+            const int64_t kbm = ((int64_t)1 << kbl) - 1;
+            const float sc = f16 ? f16_scale(*p.amax) : 1.f;
             float2* __restrict__ dh = p.dst_hi + (blk << (p.rank + 1));
             float2* __restrict__ dl = p.dst_lo + (blk << (p.rank + 1));
-            const int64_t K = (int64_t)1 << p.inner_bits;
+            __half2* __restrict__ hh = (__half2*)p.dst_hi + (blk << (p.rank + 1));
+            __half2* __restrict__ hl = p.dst_lo ? (__half2*)p.dst_lo + (blk << (p.rank + 1)) : nullptr;
             for (int v = threadIdx.x; v < tile; v += kPackThreads) {
                 const float2 x = data[slot_v[v]];
                 const int64_t q = dbase + dst_off[v];
                 int64_t e, second = K;
                 if (p.blocked) {
-                    // [n tile][k block][2n + c' within the tile][16 k]: one contiguous block per TMA box
+                    // [n tile][k block][2n + c' within the tile][k within the block]: one contiguous block per TMA box
                     const int64_t k = q & kmask, n = q >> p.inner_bits;
                     const int hb = p.bn_log2 - 1;
                     const int64_t row = (n & (((int64_t)1 << hb) - 1)) << 1;
-                    const int64_t nkb = K >> 4;
-                    e = (k & 15) + 16 * (row + ((int64_t)1 << p.bn_log2) * ((k >> 4) + nkb * (n >> hb)));
-                    second = 16;
+                    const int64_t nkb = K >> kbl;
+                    e = (k & kbm) + ((row + ((int64_t)1 << p.bn_log2) * ((k >> kbl) + nkb * (n >> hb))) << kbl);
+                    second = kbm + 1;
                 } else {
                     e = (q & kmask) | ((q >> p.inner_bits) << (p.inner_bits + 1));
                 }
-                const float hr = tf32_round(x.x), hi = tf32_round(x.y);
-                const float lr = tf32_round(x.x - hr), li = tf32_round(x.y - hi);
-                dh[e] = make_float2(hr, -hi);
-                dh[e + second] = make_float2(hi, hr);
-                dl[e] = make_float2(lr, -li);
-                dl[e + second] = make_float2(li, lr);
+                if (f16) {
+                    const float xr = x.x * sc, xi = x.y * sc;
+                    const __half hr = __float2half_rn(xr), hi = __float2half_rn(xi);
+                    hh[e] = __halves2half2(hr, __hneg(hi));
+                    hh[e + second] = __halves2half2(hi, hr);
+                    if (hl) {
+                        const __half lr = __float2half_rn(xr - __half2float(hr)), li = __float2half_rn(xi - __half2float(hi));
+                        hl[e] = __halves2half2(lr, __hneg(li));
+                        hl[e + second] = __halves2half2(li, lr);
+                    }
+                } else {
+                    const float hr = tf32_round(x.x), hi = tf32_round(x.y);
+                    const float lr = tf32_round(x.x - hr), li = tf32_round(x.y - hi);
+                    dh[e] = make_float2(hr, -hi);
+                    dh[e + second] = make_float2(hi, hr);
+                    dl[e] = make_float2(lr, -li);
+                    dl[e + second] = make_float2(li, lr);
+                }
             }
         }
         __syncthreads();
@@ -170,11 +261,17 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
         set_error("pack: bad descriptor (rank %d, blocks %d)", d.rank, d.nb);
         return TNC_ERR_INVALID;
     }
+    if ((d.mode == PACK_SPLIT_F16 || d.mode == PACK_EXPAND_SPLIT_F16) && !d.amax) {
+        set_error("pack: the fp16 modes need the operand's amax word");
+        return TNC_ERR_INVALID;
+    }
     PackParams p{};
     p.src = (const float2*)src;
     p.dst_hi = (float2*)dst_hi;
     p.dst_lo = (float2*)dst_lo;
     p.rows = d.rows;
+    p.amax = d.amax;
+    p.kb_log2 = d.kb_log2 ? d.kb_log2 : 4;
     p.rows_mode = d.rows_mode;
     p.rank = d.rank;
     p.mode = d.mode;
@@ -254,22 +351,51 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
 namespace {
 
 constexpr int BM = 128;            // rows of A' per CTA tile (UMMA M)
-constexpr int BK = 32;             // fp32 per row per stage: 128 bytes = one 128B-swizzle atom
-constexpr int UMMA_K = 8;          // kind::tf32
+constexpr int BKB = 128;           // bytes per operand row per stage: one 128B-swizzle atom
+constexpr int kMmaPerKb = BKB / 32;   // every tcgen05.mma consumes 32 bytes of K per row (8 tf32 / 16 fp16)
 constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter, each owning half of the columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-9 epilogue
-// k-blocks accumulated inside tensor memory before the fp32 register add.  Measured on B200
-// (tools/tc_calibrate.py): coherent shrink of the result per GEMM of -8.6e-8 at 1, -2.8e-7 at 2,
-// -6.6e-7 at 4; the fat GEMM runs within 7% of the same speed at 1.
-constexpr int kDefaultKC = 1;
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int BN>
+// k-blocks accumulated inside tensor memory before the fp32 register add.  Measured on B200
+// (tools/tc_calibrate.py, 3xTF32): coherent shrink of the result per GEMM of -8.6e-8 at 1,
+// -2.8e-7 at 2, -6.6e-7 at 4; the fat GEMM runs within 7% of the same speed at 1.  The
+// reduced-precision mode tolerates the bias and drains less often.
+constexpr int kDefaultKC[3] = {1, 1, 4};
+
+template <int PREC>
+struct Prec;
+template <>
+struct Prec<TNC_TC_3XTF32> {
+    static constexpr int ELEM = 4, PANELS = 2;
+    static constexpr uint32_t FMT = 2;      // instruction-descriptor operand format: TF32
+    static constexpr bool F16 = false;
+};
+template <>
+struct Prec<TNC_TC_3XF16> {
+    static constexpr int ELEM = 2, PANELS = 2;
+    static constexpr uint32_t FMT = 0;      // F16
+    static constexpr bool F16 = true;
+};
+template <>
+struct Prec<TNC_TC_F16> {
+    static constexpr int ELEM = 2, PANELS = 1;
+    static constexpr uint32_t FMT = 0;
+    static constexpr bool F16 = true;
+};
+
+// elements of K per k-block
+constexpr int bk_of(int prec) { return prec == TNC_TC_3XTF32 ? BKB / 4 : BKB / 2; }
+
+template <int BN, int PREC>
 struct Cfg {
-    static constexpr int A_TILE = BM * BK * 4;
-    static constexpr int B_TILE = BN * BK * 4;
-    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int STAGES = (kSmemBudget / STAGE) > 6 ? 6 : (kSmemBudget / STAGE);
+    static constexpr int PANELS = Prec<PREC>::PANELS;
+    static constexpr int BK = BKB / Prec<PREC>::ELEM;
+    static constexpr int A_TILE = BM * BKB;
+    static constexpr int B_TILE = BN * BKB;
+    static constexpr int A_LO = A_TILE, B_HI = PANELS * A_TILE, B_LO = PANELS * A_TILE + B_TILE;   // offsets in a stage
+    static constexpr int STAGE = PANELS * (A_TILE + B_TILE);
+    static constexpr int STAGES = (kSmemBudget / STAGE) > 8 ? 8 : (kSmemBudget / STAGE);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators (chunk double buffer)
     static constexpr int CPT = BN / 2;                            // columns per epilogue thread
     static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment*/ + 256 /*barriers*/;
@@ -285,10 +411,11 @@ struct GemmArgs {
     int32_t a_batched, b_batched;
     int32_t kc;               // k-blocks per TMEM accumulation chunk
     int32_t tiles, rounds;    // persistent grid: CTA c runs tiles c, c + grid, ... (rounds of them)
-    int32_t blocked;          // panels are tile-contiguous: [tile][k-block][rows][32 floats]
+    int32_t blocked;          // panels are tile-contiguous: [tile][k-block][rows][128 bytes]
     int32_t outer_rj, outer_mb;   // outer-rows step: batch = row of B, GEMM row = (row of A, m): see c_row()
     int32_t sync_every;       // k-blocks between grid-wide lockstep barriers (0 = none)
     uint32_t* sync_counter;   // zeroed before the launch
+    const uint32_t* amax;     // fp16 precisions: amax words of A and B (the epilogue undoes their scaling)
 };
 
 // Grid-wide barrier among the co-resident persistent CTAs (one thread per CTA calls it).  It only
@@ -387,13 +514,67 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                     // SWIZZLE_128B                       bits [61,64)
     return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
+// instruction descriptor: D fp32, A/B in the precision's format, both K-major
+template <int PREC>
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
+    return (1u << 4) | (Prec<PREC>::FMT << 7) | (Prec<PREC>::FMT << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T; CG = cta_group
+template <int PREC, int CG>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (Prec<PREC>::F16) {
+        if constexpr (CG == 1) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                : "memory");
+        }
+    } else {
+        if constexpr (CG == 1) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                : "memory");
+        }
+    }
+}
+// One k-block of the split product into the accumulator at `tacc`: small cross terms first, then
+// the leading term (hi part only in the reduced-precision mode); +2 = 32 bytes = one MMA K step.
+template <int PREC, int CG>
+__device__ __forceinline__ void umma_kblock(uint32_t tacc, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                            uint32_t idesc, uint32_t acc) {
+    if constexpr (Prec<PREC>::PANELS == 2) {
+#pragma unroll
+        for (int j = 0; j < kMmaPerKb; ++j) {
+            umma<PREC, CG>(tacc, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
+            acc = 1;
+        }
+#pragma unroll
+        for (int j = 0; j < kMmaPerKb; ++j) umma<PREC, CG>(tacc, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
+    }
+#pragma unroll
+    for (int j = 0; j < kMmaPerKb; ++j) {
+        umma<PREC, CG>(tacc, a_hi + 2 * j, b_hi + 2 * j, idesc, acc);
+        acc = 1;
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -413,12 +594,58 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int BN>
+// Adds one finished TMEM chunk (CPT columns of this thread's lane) into the fp32 registers,
+// round-to-nearest.
+template <int CPT>
+__device__ __forceinline__ void drain_chunk(uint32_t taddr, float* acc) {
+    if constexpr (CPT >= 32) {
+#pragma unroll
+        for (int c = 0; c < CPT; c += 32) {
+            uint32_t v[32];
+            tmem_ld16(taddr + c, v);
+            tmem_ld16(taddr + c + 16, v + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);
+        }
+    } else if constexpr (CPT == 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+    } else {
+        uint32_t v[8];
+        tmem_ld8(taddr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(v[j]);
+    }
+}
+
+// Stores a thread's CPT finished columns of one output row; fp16 precisions undo the operand scaling.
+template <int CPT, bool F16>
+__device__ __forceinline__ void store_row(const GemmArgs& g, float* crow, int col0, const float* acc) {
+    float sa = 1.f, sb = 1.f;
+    if constexpr (F16) {
+        sa = f16_inv_scale(g.amax[0]);
+        sb = f16_inv_scale(g.amax[1]);
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; j += 4)
+        if (col0 + j < g.N) {
+            float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if constexpr (F16) o = make_float4(o.x * sa * sb, o.y * sa * sb, o.z * sa * sb, o.w * sa * sb);
+            *(float4*)(crow + j) = o;
+        }
+}
+
+template <int BN, int PREC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  const GemmArgs g) {
-    using C = Cfg<BN>;
+gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmArgs g) {
+    using C = Cfg<BN, PREC>;
+    constexpr int BK = C::BK;
     extern __shared__ unsigned char gemm_smem_raw[];
     const uint32_t raw = smem_u32(gemm_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B swizzle wants 1024-byte aligned tiles
@@ -478,26 +705,29 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     mbar_expect_tx(full_bar(s), C::STAGE);
                     const uint32_t st = base + s * C::STAGE;
                     if (g.blocked) {
-                        // one contiguous [rows][32 floats] block per (tile, k-block)
+                        // one contiguous [rows][128 bytes] block per (tile, k-block)
                         const int blk_a = kb + nkb * (t.m_tile + g.m_tiles * ba);
                         const int blk_b = kb + nkb * (t.n_tile + g.n_tiles * bb);
                         tma_load_3d(st, &map_a_hi, full_bar(s), 0, 0, blk_a);
-                        tma_load_3d(st + C::A_TILE, &map_a_lo, full_bar(s), 0, 0, blk_a);
-                        tma_load_3d(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), 0, 0, blk_b);
-                        tma_load_3d(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), 0, 0, blk_b);
+                        tma_load_3d(st + C::B_HI, &map_b_hi, full_bar(s), 0, 0, blk_b);
+                        if constexpr (C::PANELS == 2) {
+                            tma_load_3d(st + C::A_LO, &map_a_lo, full_bar(s), 0, 0, blk_a);
+                            tma_load_3d(st + C::B_LO, &map_b_lo, full_bar(s), 0, 0, blk_b);
+                        }
                     } else {
                         tma_load_3d(st, &map_a_hi, full_bar(s), kb * BK, t.m0, ba);
-                        tma_load_3d(st + C::A_TILE, &map_a_lo, full_bar(s), kb * BK, t.m0, ba);
-                        tma_load_3d(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), kb * BK, t.n0, bb);
-                        tma_load_3d(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), kb * BK, t.n0, bb);
+                        tma_load_3d(st + C::B_HI, &map_b_hi, full_bar(s), kb * BK, t.n0, bb);
+                        if constexpr (C::PANELS == 2) {
+                            tma_load_3d(st + C::A_LO, &map_a_lo, full_bar(s), kb * BK, t.m0, ba);
+                            tma_load_3d(st + C::B_LO, &map_b_lo, full_bar(s), kb * BK, t.n0, bb);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t idesc = umma_idesc<PREC>(BM, BN);
             const int KC = g.kc;
             uint32_t it = 0, gc = 0;             // k-blocks consumed, accumulation chunks produced
             for (int round = 0; round < g.rounds; ++round) {
@@ -516,18 +746,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t st = base + s * C::STAGE;
-                    const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::A_TILE);
-                    const uint64_t b_hi = umma_desc(st + 2 * C::A_TILE), b_lo = umma_desc(st + 2 * C::A_TILE + C::B_TILE);
-                    // small cross terms first, then the leading term; +2 = 32 bytes = one UMMA_K step
-#pragma unroll
-                    for (int j = 0; j < BK / UMMA_K; ++j) {
-                        umma_tf32(tacc, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
-                        acc = 1;
-                    }
-#pragma unroll
-                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
-#pragma unroll
-                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32(tacc, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
+                    umma_kblock<PREC, 1>(tacc, umma_desc(st), umma_desc(st + C::A_LO), umma_desc(st + C::B_HI),
+                                         umma_desc(st + C::B_LO), idesc, acc);
                     umma_commit(empty_bar(s));     // frees the stage when these MMAs have read it
                     if (kb % KC == KC - 1 || kb == nkb - 1) {
                         umma_commit(tmem_full_bar(gc & 1u));
@@ -554,42 +774,14 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             for (int chunk = 0; chunk < nchunks; ++chunk, ++gc) {
                 mbar_wait(tmem_full_bar(gc & 1u), (gc >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gc & 1u) * BN + half * CPT);
-                if constexpr (CPT >= 32) {
-#pragma unroll
-                    for (int c = 0; c < CPT; c += 32) {
-                        uint32_t v[32];
-                        tmem_ld16(taddr + c, v);
-                        tmem_ld16(taddr + c + 16, v + 16);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);   // round-to-nearest fp32
-                    }
-                } else if constexpr (CPT == 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
-                } else {
-                    uint32_t v[8];
-                    tmem_ld8(taddr, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(v[j]);
-                }
+                drain_chunk<CPT>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gc & 1u) * BN + half * CPT), acc);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar(gc & 1u));
             }
             const int row = t.m0 + q * 32 + lane;
             const int col0 = t.n0 + half * CPT;
-            if (row < g.M) {
-                float* crow = g.c + c_row(g, t.batch, row) * g.ldc + col0;
-#pragma unroll
-                for (int j = 0; j < CPT; j += 4)
-                    if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            }
+            if (row < g.M) store_row<CPT, Prec<PREC>::F16>(g, g.c + c_row(g, t.batch, row) * g.ldc + col0, col0, acc);
         }
     }
     tc_fence_before();
@@ -608,12 +800,16 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 // `full` barrier; tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs; the epilogue
 // warps of both CTAs release a TMEM half by arriving on rank 0's `tmem_empty` barrier.
 // =====================================================================================
+template <int PREC>
 struct Cfg2 {
     static constexpr int BN = 256;
-    static constexpr int A_TILE = BM * BK * 4;          // this CTA's 128 rows of A'
-    static constexpr int B_TILE = (BN / 2) * BK * 4;    // this CTA's half of the B' tile
-    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int STAGES = 3;
+    static constexpr int PANELS = Prec<PREC>::PANELS;
+    static constexpr int BK = BKB / Prec<PREC>::ELEM;
+    static constexpr int A_TILE = BM * BKB;             // this CTA's 128 rows of A'
+    static constexpr int B_TILE = (BN / 2) * BKB;       // this CTA's half of the B' tile
+    static constexpr int A_LO = A_TILE, B_HI = PANELS * A_TILE, B_LO = PANELS * A_TILE + B_TILE;
+    static constexpr int STAGE = PANELS * (A_TILE + B_TILE);
+    static constexpr int STAGES = (kSmemBudget / STAGE) > 6 ? 6 : (kSmemBudget / STAGE);
     static constexpr int TMEM_COLS = 512;
     static constexpr int CPT = BN / 2;
     static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
@@ -637,14 +833,6 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(evict_normal)
         : "memory");
 }
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
     const uint16_t both = 3;
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -660,12 +848,13 @@ __device__ __forceinline__ void mbar_arrive_on_cta(uint32_t bar, uint32_t cta) {
         : "memory");
 }
 
+template <int PREC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm3xtf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                       const GemmArgs g) {
-    using C = Cfg2;
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmArgs g) {
+    using C = Cfg2<PREC>;
     constexpr int BN = C::BN;
+    constexpr int BK = C::BK;
     extern __shared__ unsigned char gemm_smem_raw[];
     const uint32_t raw = smem_u32(gemm_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -735,23 +924,27 @@ gemm3xtf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
                         const int blk_a = kb + nkb * (m_tile128 + g.m_tiles * ba);
                         const int blk_b = kb + nkb * (t.n_tile + g.n_tiles * bb);
                         tma_load_3d_2sm(st, &map_a_hi, full_bar(s), 0, 0, blk_a);
-                        tma_load_3d_2sm(st + C::A_TILE, &map_a_lo, full_bar(s), 0, 0, blk_a);
-                        tma_load_3d_2sm(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), 0, 128 * (int)rank, blk_b);
-                        tma_load_3d_2sm(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), 0, 128 * (int)rank, blk_b);
+                        tma_load_3d_2sm(st + C::B_HI, &map_b_hi, full_bar(s), 0, 128 * (int)rank, blk_b);
+                        if constexpr (C::PANELS == 2) {
+                            tma_load_3d_2sm(st + C::A_LO, &map_a_lo, full_bar(s), 0, 0, blk_a);
+                            tma_load_3d_2sm(st + C::B_LO, &map_b_lo, full_bar(s), 0, 128 * (int)rank, blk_b);
+                        }
                     } else {
                         const int mrow = m_tile128 * BM, nrow = t.n0 + 128 * (int)rank;
                         tma_load_3d_2sm(st, &map_a_hi, full_bar(s), kb * BK, mrow, ba);
-                        tma_load_3d_2sm(st + C::A_TILE, &map_a_lo, full_bar(s), kb * BK, mrow, ba);
-                        tma_load_3d_2sm(st + 2 * C::A_TILE, &map_b_hi, full_bar(s), kb * BK, nrow, bb);
-                        tma_load_3d_2sm(st + 2 * C::A_TILE + C::B_TILE, &map_b_lo, full_bar(s), kb * BK, nrow, bb);
+                        tma_load_3d_2sm(st + C::B_HI, &map_b_hi, full_bar(s), kb * BK, nrow, bb);
+                        if constexpr (C::PANELS == 2) {
+                            tma_load_3d_2sm(st + C::A_LO, &map_a_lo, full_bar(s), kb * BK, mrow, ba);
+                            tma_load_3d_2sm(st + C::B_LO, &map_b_lo, full_bar(s), kb * BK, nrow, bb);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
-            // D fp32, A/B tf32, K-major, N = 256, M = 256 (128 rows in each CTA of the pair)
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            // N = 256, M = 256 (128 rows in each CTA of the pair)
+            constexpr uint32_t idesc = umma_idesc<PREC>(256, BN);
             const int KC = g.kc;
             uint32_t it = 0, gc = 0;
             for (int round = 0; round < g.rounds; ++round) {
@@ -770,17 +963,8 @@ gemm3xtf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t st = base + s * C::STAGE;
-                    const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::A_TILE);
-                    const uint64_t b_hi = umma_desc(st + 2 * C::A_TILE), b_lo = umma_desc(st + 2 * C::A_TILE + C::B_TILE);
-#pragma unroll
-                    for (int j = 0; j < BK / UMMA_K; ++j) {
-                        umma_tf32_2sm(tacc, a_lo + 2 * j, b_hi + 2 * j, idesc, acc);
-                        acc = 1;
-                    }
-#pragma unroll
-                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32_2sm(tacc, a_hi + 2 * j, b_lo + 2 * j, idesc, 1);
-#pragma unroll
-                    for (int j = 0; j < BK / UMMA_K; ++j) umma_tf32_2sm(tacc, a_hi + 2 * j, b_hi + 2 * j, idesc, 1);
+                    umma_kblock<PREC, 2>(tacc, umma_desc(st), umma_desc(st + C::A_LO), umma_desc(st + C::B_HI),
+                                         umma_desc(st + C::B_LO), idesc, acc);
                     umma_commit_2sm(empty_bar(s));
                     if (kb % KC == KC - 1 || kb == nkb - 1) {
                         umma_commit_2sm(tmem_full_bar(gc & 1u));
@@ -807,28 +991,14 @@ gemm3xtf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
             for (int chunk = 0; chunk < nchunks; ++chunk, ++gc) {
                 mbar_wait(tmem_full_bar(gc & 1u), (gc >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gc & 1u) * BN + half * CPT);
-#pragma unroll
-                for (int c = 0; c < CPT; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld16(taddr + c, v);
-                    tmem_ld16(taddr + c + 16, v + 16);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);
-                }
+                drain_chunk<CPT>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gc & 1u) * BN + half * CPT), acc);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_on_cta(tmem_empty_bar(gc & 1u), 0);
             }
             const int row = (2 * t.m_tile + (int)rank) * BM + q * 32 + lane;
             const int col0 = t.n0 + half * CPT;
-            if (row < g.M) {
-                float* crow = g.c + c_row(g, t.batch, row) * g.ldc + col0;
-#pragma unroll
-                for (int j = 0; j < CPT; j += 4)
-                    if (col0 + j < g.N) *(float4*)(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            }
+            if (row < g.M) store_row<CPT, Prec<PREC>::F16>(g, g.c + c_row(g, t.batch, row) * g.ldc + col0, col0, acc);
         }
     }
     tc_fence_before();
@@ -855,69 +1025,63 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 panel [batch][rows][cols], cols contiguous; box = BK columns x box_rows rows, 128B swizzle
-int make_panel_map(CUtensorMap* map, void* addr, int64_t cols, int64_t rows, int64_t batch, int box_rows) {
+// 3-D map over elements of `elem` bytes (4: fp32/tf32, 2: fp16): dims {d0, d1, d2}, d0 contiguous;
+// box = one 128-byte swizzle atom of d0 x box_rows of d1
+int make_map(CUtensorMap* map, void* addr, int elem, int64_t d0, int64_t d1, int64_t d2, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
         return TNC_ERR_CUDA;
     }
-    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (cuuint64_t)rows};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)d0 * elem, (cuuint64_t)d0 * elem * (cuuint64_t)d1};
+    cuuint32_t box[3] = {(cuuint32_t)(BKB / elem), (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult rc = fn(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, addr, dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with %d (cols=%lld rows=%lld batch=%lld box_rows=%d)", (int)rc,
-                  (long long)cols, (long long)rows, (long long)batch, box_rows);
+        set_error("cuTensorMapEncodeTiled failed with %d (elem=%d dims=%lld x %lld x %lld box_rows=%d)", (int)rc, elem,
+                  (long long)d0, (long long)d1, (long long)d2, box_rows);
         return TNC_ERR_CUDA;
     }
     return TNC_OK;
 }
 
-// tile-contiguous panel: `blocks` blocks of [box_rows][BK floats], one block per (tile, k-block)
-int make_blocked_map(CUtensorMap* map, void* addr, int64_t blocks, int block_rows, int box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return TNC_ERR_CUDA;
-    }
-    cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)block_rows, (cuuint64_t)blocks};
-    cuuint64_t strides[2] = {(cuuint64_t)BK * 4, (cuuint64_t)BK * 4 * (cuuint64_t)block_rows};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with %d (blocks=%lld box_rows=%d)", (int)rc, (long long)blocks, box_rows);
-        return TNC_ERR_CUDA;
-    }
-    return TNC_OK;
-}
-
-template <int BN>
-int launch_gemm(const CUtensorMap* maps, const GemmArgs& g, int64_t tiles, cudaStream_t s) {
+template <int BN, int PREC>
+int launch_gemm(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        TNC_CUDA(cudaFuncSetAttribute(gemm3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+        TNC_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, PREC>::SMEM));
         configured = true;
     }
-    gemm3xtf32_kernel<BN><<<(unsigned)tiles, kGemmThreads, Cfg<BN>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], g);   // tiles = grid size
+    gemm_kernel<BN, PREC><<<(unsigned)grid, kGemmThreads, Cfg<BN, PREC>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], g);
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }
 
+template <int PREC>
+int launch_gemm_bn(int bn, const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
+    switch (bn) {
+        case 256: return launch_gemm<256, PREC>(maps, g, grid, s);
+        case 128: return launch_gemm<128, PREC>(maps, g, grid, s);
+        case 64: return launch_gemm<64, PREC>(maps, g, grid, s);
+        case 32: return launch_gemm<32, PREC>(maps, g, grid, s);
+        default: return launch_gemm<16, PREC>(maps, g, grid, s);
+    }
+}
+
+template <int PREC>
 int launch_gemm_2cta(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        TNC_CUDA(cudaFuncSetAttribute(gemm3xtf32_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM));
+        TNC_CUDA(cudaFuncSetAttribute(gemm_2cta_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<PREC>::SMEM));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg2::SMEM;
+    cfg.dynamicSmemBytes = Cfg2<PREC>::SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -926,7 +1090,7 @@ int launch_gemm_2cta(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm3xtf32_2cta_kernel, maps[0], maps[1], maps[2], maps[3], g));
+    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm_2cta_kernel<PREC>, maps[0], maps[1], maps[2], maps[3], g));
     return TNC_OK;
 }
 
@@ -936,7 +1100,9 @@ int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct TcGemmOp {
     PackDesc pa{}, pb{};
+    int precision = TNC_TC_3XTF32;
     int64_t a_off = 0, b_off = 0, c_off = 0;          // operand offsets in the workspace (bytes)
+    int64_t a_elems = 0, b_elems = 0;                 // complex elements of the whole source tensors (amax range)
     int64_t ahi_off = 0, alo_off = 0, bhi_off = 0, blo_off = 0;
     int64_t M = 0, N = 0, K = 0;                      // real GEMM sizes
     int64_t batch = 1;
@@ -949,7 +1115,7 @@ struct TcGemmOp {
     int blocked = 0;                                  // tile-contiguous panels
     int two_cta = 0;                                  // CTA pairs (cta_group::2) on 256 x 256 tiles
     int grid = 1;
-    uint32_t* sync_counter = nullptr;                 // device word for the lockstep barrier
+    uint32_t* dev_words = nullptr;                    // [0], [1]: amax bits of A, B; [32]: lockstep barrier counter
 };
 
 namespace {
@@ -1002,6 +1168,8 @@ int shape_of(const tnc_einsum& e, Shape* sh) {
 
 }  // namespace
 
+// Sized for the largest panels of any precision (3xTF32: 8 bytes per amplitude of A per part, 16
+// per amplitude of B'); the fp16 precisions use half of it or less.
 int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype) {
     if (dtype != TNC_C64) {
         set_error("tensor-core einsum: only complex64 is implemented");
@@ -1014,13 +1182,24 @@ int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype) {
     return 2 * a_panel + 2 * b_panel;
 }
 
-int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, const int32_t* dev_rows_b, TcGemmOp** out) {
+int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
+                   TcGemmOp** out) {
     const int64_t need = tc_gemm_scratch_bytes(e, dtype);
     if (need < 0) return TNC_ERR_UNSUPPORTED;
     if (e.scratch_bytes < need || (e.scratch_offset & 1023)) {
         set_error("tensor-core einsum: scratch region too small or misaligned (%lld < %lld)", (long long)e.scratch_bytes,
                   (long long)need);
         return TNC_ERR_NOMEM;
+    }
+    if (precision != TNC_TC_3XTF32 && precision != TNC_TC_3XF16 && precision != TNC_TC_F16) {
+        set_error("tensor-core einsum: unknown precision %d", precision);
+        return TNC_ERR_INVALID;
+    }
+    const bool f16 = precision != TNC_TC_3XTF32;
+    if (f16 && e.n_k < 2) {
+        // a row of the fp16 panel must be a multiple of 16 bytes for TMA: K >= 4 complex
+        set_error("tensor-core einsum: the fp16 precisions need at least 2 contracted bits (k=%d)", e.n_k);
+        return TNC_ERR_UNSUPPORTED;
     }
     Shape sh;
     shape_of(e, &sh);
@@ -1030,17 +1209,20 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
             return TNC_ERR_UNSUPPORTED;
         }
     TcGemmOp* op = new TcGemmOp();
+    op->precision = precision;
+    const int kbl = f16 ? 5 : 4;                       // log2 of the complex k per k-block (128 bytes per row)
     // A panel: [rows][m (output order)][k]  -- destination bits: k first, then m by output position
     op->pa.rank = e.a.rank;
     op->pa.nb = (int32_t)sh.nb_a;
     op->pa.rows_mode = sh.outer ? TNC_ROWS_IDENTITY : e.rows_a;
     op->pa.rows = dev_rows_a;
-    op->pa.mode = PACK_SPLIT;
+    op->pa.mode = f16 ? PACK_SPLIT_F16 : PACK_SPLIT;
     op->pa.inner_bits = e.n_k;
+    op->pa.kb_log2 = kbl;
     const int bn = sh.N >= 256 ? 256 : sh.N >= 128 ? 128 : sh.N >= 64 ? 64 : sh.N >= 32 ? 32 : 16;
-    // tile-contiguous panels need whole tiles: K a multiple of one k-block (16 complex), every row
-    // block a multiple of 128 rows, N a multiple of the tile width
-    op->blocked = e.n_k >= 4 && e.n_m >= 7 && sh.N >= bn;
+    // tile-contiguous panels need whole tiles: K a multiple of one k-block, every row block a
+    // multiple of 128 rows, N a multiple of the tile width
+    op->blocked = e.n_k >= kbl && e.n_m >= 7 && sh.N >= bn;
     if (const char* env = getenv("TNC_TC_BLOCKED"))
         if (atoi(env) == 0) op->blocked = 0;
     {
@@ -1048,10 +1230,10 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
         for (int i = 0; i < e.n_m; ++i) pm[e.m_c[i] - e.n_n] = e.m_a[i];
         int d = 0;
         if (op->blocked) {
-            // [m tile][k block][128 rows][16 k]
-            for (int i = 0; i < 4; ++i) op->pa.src_pos[d++] = e.k_a[i];
+            // [m tile][k block][128 rows][k within the block]
+            for (int i = 0; i < kbl; ++i) op->pa.src_pos[d++] = e.k_a[i];
             for (int j = 0; j < 7; ++j) op->pa.src_pos[d++] = pm[j];
-            for (int i = 4; i < e.n_k; ++i) op->pa.src_pos[d++] = e.k_a[i];
+            for (int i = kbl; i < e.n_k; ++i) op->pa.src_pos[d++] = e.k_a[i];
             for (int j = 7; j < e.n_m; ++j) op->pa.src_pos[d++] = pm[j];
         } else {
             for (int i = 0; i < e.n_k; ++i) op->pa.src_pos[d++] = e.k_a[i];
@@ -1063,8 +1245,9 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     op->pb.nb = (int32_t)sh.nb_b;
     op->pb.rows_mode = sh.outer ? TNC_ROWS_IDENTITY : e.rows_b;
     op->pb.rows = dev_rows_b;
-    op->pb.mode = PACK_EXPAND_SPLIT;
+    op->pb.mode = f16 ? PACK_EXPAND_SPLIT_F16 : PACK_EXPAND_SPLIT;
     op->pb.inner_bits = e.n_k;
+    op->pb.kb_log2 = kbl;
     op->pb.blocked = op->blocked;
     for (int l = 0; (1 << l) <= bn; ++l) op->pb.bn_log2 = l;
     for (int i = 0; i < e.n_k; ++i) op->pb.src_pos[i] = e.k_b[i];
@@ -1072,6 +1255,8 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     op->a_off = e.a.offset;
     op->b_off = e.b.offset;
     op->c_off = e.c.offset;
+    op->a_elems = (int64_t)e.a.rows << e.a.rank;
+    op->b_elems = (int64_t)e.b.rows << e.b.rank;
     const int64_t a_panel = align_up((sh.nb_a << (e.n_m + e.n_k)) * 8, 1024);
     const int64_t b_panel = align_up((sh.nb_b << (e.n_n + e.n_k)) * 16, 1024);
     op->ahi_off = e.scratch_offset;
@@ -1098,7 +1283,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     g.group_m = 16;
     g.a_batched = op->a_batched;
     g.b_batched = op->b_batched;
-    g.kc = kDefaultKC;
+    g.kc = kDefaultKC[precision];
     if (const char* env = getenv("TNC_TC_KC")) {       // experiment knob
         const int v = atoi(env);
         if (v >= 1 && v <= 64) g.kc = v;
@@ -1115,38 +1300,68 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, co
     if (const char* env = getenv("TNC_TC_2CTA"))
         if (atoi(env) == 0) op->two_cta = 0;
     // lockstep only pays off for long k loops shared by many tiles
-    const int nkb = (int)((sh.K + BK - 1) / BK);
+    const int bk = bk_of(precision);
+    const int nkb = (int)((sh.K + bk - 1) / bk);
     g.sync_every = nkb >= 64 ? 16 : 0;
     if (const char* env = getenv("TNC_TC_SYNC")) g.sync_every = nkb >= 64 ? atoi(env) : 0;
+    if (cudaMalloc((void**)&op->dev_words, 256) != cudaSuccess) {
+        delete op;
+        set_error("tensor-core einsum: cudaMalloc of the amax / barrier words failed");
+        return TNC_ERR_CUDA;
+    }
+    op->pa.amax = f16 ? op->dev_words : nullptr;
+    op->pb.amax = f16 ? op->dev_words + 1 : nullptr;
+    g.amax = f16 ? op->dev_words : nullptr;
+    g.sync_counter = op->dev_words + 32;
     *out = op;
     return TNC_OK;
 }
 
 int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* ctx, int* launches) {
-    int rc = launch_pack(op->pa, ws + op->a_off, ws + op->ahi_off, ws + op->alo_off, s);
-    if (rc != TNC_OK) return rc;
-    if (hook) hook(ctx);
-    rc = launch_pack(op->pb, ws + op->b_off, ws + op->bhi_off, ws + op->blo_off, s);
-    if (rc != TNC_OK) return rc;
-    if (hook) hook(ctx);
-    if (op->maps_for != ws && op->blocked) {
-        const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
-        const int64_t nkb = op->K / BK;
-        const int64_t blocks_a = nkb * op->args.m_tiles * batch_a, blocks_b = nkb * op->args.n_tiles * batch_b;
-        if ((rc = make_blocked_map(&op->maps[0], ws + op->ahi_off, blocks_a, BM, BM)) != TNC_OK) return rc;
-        if ((rc = make_blocked_map(&op->maps[1], ws + op->alo_off, blocks_a, BM, BM)) != TNC_OK) return rc;
-        if ((rc = make_blocked_map(&op->maps[2], ws + op->bhi_off, blocks_b, op->bn, op->two_cta ? 128 : op->bn)) != TNC_OK) return rc;
-        if ((rc = make_blocked_map(&op->maps[3], ws + op->blo_off, blocks_b, op->bn, op->two_cta ? 128 : op->bn)) != TNC_OK) return rc;
-        op->maps_for = ws;
+    const bool f16 = op->precision != TNC_TC_3XTF32;
+    const bool lo = op->precision != TNC_TC_F16;
+    const int elem = f16 ? 2 : 4;
+    int n_launch = 3;
+    if (f16 || op->args.sync_every) TNC_CUDA(cudaMemsetAsync(op->dev_words, 0, 256, s));
+    if (f16) {
+        // one launch finds the largest magnitude of both operands (whole source tensors: an upper
+        // bound of the gathered rows is all the scaling needs)
+        const int64_t n4_a = op->a_elems / 2, n4_b = op->b_elems / 2;       // float4 = two amplitudes; ranks >= 2
+        const int64_t cap = (int64_t)sm_count() * 8;
+        const int ga = (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_a + 511) / 512));
+        const int gb = (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_b + 511) / 512));
+        amax_kernel<<<ga + gb, 256, 0, s>>>((const float4*)(ws + op->a_off), n4_a, (const float4*)(ws + op->b_off), n4_b, ga,
+                                            op->dev_words);
+        TNC_CUDA(cudaGetLastError());
+        n_launch = 4;
     }
+    int rc = launch_pack(op->pa, ws + op->a_off, ws + op->ahi_off, lo ? ws + op->alo_off : nullptr, s);
+    if (rc != TNC_OK) return rc;
+    if (hook) hook(ctx);
+    rc = launch_pack(op->pb, ws + op->b_off, ws + op->bhi_off, lo ? ws + op->blo_off : nullptr, s);
+    if (rc != TNC_OK) return rc;
+    if (hook) hook(ctx);
     if (op->maps_for != ws) {
-        const int64_t rows_a = op->M;                              // folded rows are part of M
         const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
-        if ((rc = make_panel_map(&op->maps[0], ws + op->ahi_off, op->K, rows_a, batch_a, BM)) != TNC_OK) return rc;
-        if ((rc = make_panel_map(&op->maps[1], ws + op->alo_off, op->K, rows_a, batch_a, BM)) != TNC_OK) return rc;
         const int box_b = op->two_cta ? 128 : op->bn;
-        if ((rc = make_panel_map(&op->maps[2], ws + op->bhi_off, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
-        if ((rc = make_panel_map(&op->maps[3], ws + op->blo_off, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
+        const int bk = bk_of(op->precision);
+        char* lo_a = ws + (lo ? op->alo_off : op->ahi_off);
+        char* lo_b = ws + (lo ? op->blo_off : op->bhi_off);
+        if (op->blocked) {
+            // `blocks` blocks of [rows][128 bytes], one per (tile, k-block)
+            const int64_t nkb = op->K / bk;
+            const int64_t blocks_a = nkb * op->args.m_tiles * batch_a, blocks_b = nkb * op->args.n_tiles * batch_b;
+            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[1], lo_a, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[2], ws + op->bhi_off, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[3], lo_b, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
+        } else {
+            // K-major panels [batch][rows][K]; folded rows are part of M
+            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[1], lo_a, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[2], ws + op->bhi_off, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[3], lo_b, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
+        }
         op->maps_for = ws;
     }
     GemmArgs g = op->args;
@@ -1156,27 +1371,27 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     int64_t grid = std::min<int64_t>(op->tiles, sm_count());
     if (op->two_cta) grid &= ~(int64_t)1;               // whole pairs; tiles is even here
     g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
-    if (g.sync_every) {
-        if (!op->sync_counter) TNC_CUDA(cudaMalloc((void**)&op->sync_counter, 256));
-        TNC_CUDA(cudaMemsetAsync(op->sync_counter, 0, 4, s));
-        g.sync_counter = op->sync_counter;
-    }
-    if (op->two_cta) rc = launch_gemm_2cta(op->maps, g, grid, s);
-    else switch (op->bn) {
-        case 256: rc = launch_gemm<256>(op->maps, g, grid, s); break;
-        case 128: rc = launch_gemm<128>(op->maps, g, grid, s); break;
-        case 64: rc = launch_gemm<64>(op->maps, g, grid, s); break;
-        case 32: rc = launch_gemm<32>(op->maps, g, grid, s); break;
-        default: rc = launch_gemm<16>(op->maps, g, grid, s); break;
+    if (op->two_cta) {
+        switch (op->precision) {
+            case TNC_TC_3XF16: rc = launch_gemm_2cta<TNC_TC_3XF16>(op->maps, g, grid, s); break;
+            case TNC_TC_F16: rc = launch_gemm_2cta<TNC_TC_F16>(op->maps, g, grid, s); break;
+            default: rc = launch_gemm_2cta<TNC_TC_3XTF32>(op->maps, g, grid, s); break;
+        }
+    } else {
+        switch (op->precision) {
+            case TNC_TC_3XF16: rc = launch_gemm_bn<TNC_TC_3XF16>(op->bn, op->maps, g, grid, s); break;
+            case TNC_TC_F16: rc = launch_gemm_bn<TNC_TC_F16>(op->bn, op->maps, g, grid, s); break;
+            default: rc = launch_gemm_bn<TNC_TC_3XTF32>(op->bn, op->maps, g, grid, s); break;
+        }
     }
     if (rc != TNC_OK) return rc;
     if (hook) hook(ctx);
-    if (launches) *launches = 3;
+    if (launches) *launches = n_launch;
     return TNC_OK;
 }
 
 void tc_gemm_destroy(TcGemmOp* op) {
-    if (op && op->sync_counter) cudaFree(op->sync_counter);
+    if (op && op->dev_words) cudaFree(op->dev_words);
     delete op;
 }
 

@@ -1,6 +1,7 @@
 // Tensor-core (tcgen05) lowering of one einsum step: two pack launches (bit-permutation of
-// each operand into a K-major panel, split into TF32 hi/lo parts; the right operand is also
-// expanded to its real 2N x 2K form) followed by one TMA-fed tcgen05 GEMM.
+// each operand into a K-major panel, split into hi/lo parts; the right operand is also
+// expanded to its real 2N x 2K form) followed by one TMA-fed tcgen05 GEMM.  The fp16
+// precisions add one amax launch in front (power-of-two operand scaling).
 #pragma once
 #include "tnc_internal.h"
 
@@ -16,7 +17,8 @@ typedef void (*LaunchHook)(void* ctx);
 int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype);
 
 // `dev_rows_a` / `dev_rows_b`: device copies of the row tables (nullptr unless rows_* >= 0).
-int tc_gemm_create(const tnc_einsum& e, int dtype, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
+// `precision` is a tnc_tc_precision.
+int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
                    TcGemmOp** out);
 int tc_gemm_run(TcGemmOp* op, char* workspace, cudaStream_t s, LaunchHook hook, void* ctx, int* launches);
 void tc_gemm_destroy(TcGemmOp* op);
@@ -24,7 +26,7 @@ void tc_gemm_destroy(TcGemmOp* op);
 // ---------------------------------------------------------------- pack (bit-permutation) kernel
 // dst[b][q] = f(src[row(b)][p]) where bit i of q is bit src_pos[i] of p; tiled through shared
 // memory so that both the global reads and the global writes are contiguous runs.
-enum PackMode { PACK_COPY = 0, PACK_SPLIT = 1, PACK_EXPAND_SPLIT = 2 };
+enum PackMode { PACK_COPY = 0, PACK_SPLIT = 1, PACK_EXPAND_SPLIT = 2, PACK_SPLIT_F16 = 3, PACK_EXPAND_SPLIT_F16 = 4 };
 struct PackDesc {
     int32_t rank;                 // bits per block (source and destination)
     int32_t nb;                   // destination blocks
@@ -34,6 +36,9 @@ struct PackDesc {
     int32_t inner_bits;           // PACK_EXPAND_SPLIT: number of low destination bits that are k
     int32_t blocked;              // PACK_EXPAND_SPLIT: write tile-contiguous blocks [n tile][k block][rows][16 k]
     int32_t bn_log2;              //   log2 of the rows (2n + c') per n tile
+    int32_t kb_log2;              //   log2 of the complex k per k-block: 4 (tf32, default) or 5 (fp16)
+    const uint32_t* amax;         // fp16 modes: device word with the bits of the operand's largest magnitude;
+                                  //   dst_lo may be null (hi part only)
     int8_t src_pos[TNC_MAX_BITS]; // source position feeding destination position i
 };
 int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, cudaStream_t s);

@@ -44,6 +44,7 @@ using namespace tnc;
 
 struct tnc_plan {
     int dtype = TNC_C64;
+    int tc_precision = TNC_TC_3XF16;
     int n_sliced = 0;
     bool finalized = false;
     std::vector<std::vector<int32_t>> tables;
@@ -103,6 +104,24 @@ int tnc_plan_create(int32_t dtype, int32_t n_sliced_bonds, tnc_plan** out) {
     p->n_sliced = n_sliced_bonds;
     *out = p;
     return TNC_OK;
+}
+
+int tnc_plan_set_option(tnc_plan* plan, int32_t option, int64_t value) {
+    if (!plan || plan->finalized) {
+        set_error("set_option: no plan or plan already finalized");
+        return plan ? TNC_ERR_STATE : TNC_ERR_INVALID;
+    }
+    switch (option) {
+        case TNC_OPT_TC_PRECISION:
+            if (value != TNC_TC_3XTF32 && value != TNC_TC_3XF16 && value != TNC_TC_F16) {
+                set_error("set_option: unknown tensor-core precision %lld", (long long)value);
+                return TNC_ERR_INVALID;
+            }
+            plan->tc_precision = (int)value;
+            return TNC_OK;
+    }
+    set_error("set_option: unknown option %d", option);
+    return TNC_ERR_INVALID;
 }
 
 void tnc_plan_destroy(tnc_plan* plan) {
@@ -355,7 +374,7 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
                 return TNC_ERR_NOMEM;
             }
             TcGemmOp* tc = nullptr;
-            int rc = tc_gemm_create(op.e, plan->dtype, ra, rb, &tc);
+            int rc = tc_gemm_create(op.e, plan->dtype, plan->tc_precision, ra, rb, &tc);
             if (rc != TNC_OK) return rc;
             op.tc.reset(tc, tc_gemm_destroy);
         }

@@ -123,13 +123,16 @@ class TensorNetworkSimulation:
         self._plan_cache.clear()
 
     # ---- the hot path ----
-    def plan(self, dtype="c64"):
-        key = (dtype, repr(self.plan_options))
+    def plan(self, mode="c64"):
+        """Compiled plan for a compute mode: "c64" (fp32-accurate) or "chalf" (reduced-precision
+        tensor-core products, see contraction._DTYPES)."""
+        options = _c.mode_options(mode, self.plan_options)
+        key = repr(options)
         if key not in self._plan_cache:
             self._plan_cache[key] = _c.ContractionPlan(
                 self.scheme, {i: tuple(self.tensors[i].shape) for i in self._ids()},
                 self.pattern == 'sparse', slicing_bonds=self.slicing_bonds,
-                slicing_indices=self.slicing_indices, dtype=dtype, options=self.plan_options)
+                slicing_indices=self.slicing_indices, dtype="c64", options=options)
         return self._plan_cache[key]
 
     def _ids(self):
@@ -139,6 +142,8 @@ class TensorNetworkSimulation:
                     reduce_result=True):
         """Sum of the contraction over slices (simulation.py:90-117).
 
+        dtype:       torch.complex64 (fp32-accurate) or torch.complex32 (reduced-precision
+                     complex-half tensor-core mode); the result is complex64 in both.
         slice_range: (begin, end) subset of slice ids, default all 2^S.
         group:       torch.distributed process group (or True for the default group): the slice
                      range is block-partitioned over its ranks and the partial amplitude tensors are

@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tc-min-flops", type=float, default=None)
     ap.add_argument("--cpu-max-elems", type=int, default=1 << 24)
+    ap.add_argument("--tc-precision", default=None, choices=["3xtf32", "3xf16", "f16"],
+                    help="operand precision of the tensor-core steps (default: the library default, 3xf16)")
+    ap.add_argument("--no-half", action="store_true", help="skip the complex-half mode measurement")
     return ap.parse_args()
 
 
@@ -126,16 +129,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measure_tf32_peak(dev, seconds=1.0):
-    """cuBLAS TF32 GEMM 8192^3 (allow_tf32), the same way MEASURED_PEAKS.json measures bf16: best of
-    10 (burst) and back-to-back for `seconds` (sustained).  Only a denominator, never timed work."""
+def measure_cublas_peak(dev, kind, seconds=1.0):
+    """cuBLAS GEMM 8192^3 in the operand type the kernel issues ("tf32": fp32 inputs with allow_tf32,
+    "f16": fp16 inputs), measured the way MEASURED_PEAKS.json measures bf16: best of 10 (burst) and
+    back-to-back for `seconds` (sustained).  Only a denominator, never timed work."""
     import torch
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
         n = 8192
-        a = torch.randn(n, n, device=dev)
-        b = torch.randn(n, n, device=dev)
+        dt = torch.float32 if kind == "tf32" else torch.float16
+        a = torch.randn(n, n, device=dev, dtype=dt)
+        b = torch.randn(n, n, device=dev, dtype=dt)
         for _ in range(3):
             a @ b
         torch.cuda.synchronize(dev)
@@ -253,8 +258,13 @@ def main():
 
     case = load_workload(args.workload)
     sim = TensorNetworkSimulation.from_case(case)
+    opt_kw = {}
     if args.tc_min_flops is not None:
-        sim.plan_options = PlanOptions(tc_min_flops=args.tc_min_flops)
+        opt_kw["tc_min_flops"] = args.tc_min_flops
+    if args.tc_precision is not None:
+        opt_kw["tc_precision"] = args.tc_precision
+    sim.plan_options = PlanOptions(**opt_kw)
+    precision = sim.plan_options.tc_precision
     plan = sim.plan()
     plan.scheme_steps = case.scheme
     S = args.slices_per_step
@@ -379,26 +389,63 @@ def main():
         if tensor_bound:
             ach = st.flops / (best_ms * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
-            tf32 = measure_tf32_peak(dev)
+            kind = "tf32" if precision == "3xtf32" else "f16"
+            products = 1 if precision == "f16" else 3
+            lib = measure_cublas_peak(dev, kind)
             roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                         "traffic": None, "peak_kind": f"bf16 dense sustained ({pk['source']})",
-                        "tf32": {"issued_tflops": 3 * ach, "cublas_tf32_burst": tf32["burst"],
-                                 "cublas_tf32_sustained": tf32["sustained"], "frac_of_sustained": 3 * ach / tf32["sustained"]},
-                        "note": "achieved = 8*M*N*K useful complex64 flops.  The kernel computes in TF32 (3xTF32 split): "
-                                "it issues 3x that many tensor flops at the TF32 rate, so the useful-flop ceiling is "
-                                "cublas_tf32/3; `tf32` compares issued TF32 flops with cuBLAS TF32 8192^3 measured in "
-                                "this run"}
+                        "issued": {"operand_type": kind, "products_per_useful_flop": products,
+                                   "issued_tflops": products * ach, f"cublas_{kind}_burst": lib["burst"],
+                                   f"cublas_{kind}_sustained": lib["sustained"],
+                                   "frac_of_cublas_sustained": products * ach / lib["sustained"],
+                                   "frac_of_peak": products * ach / peak},
+                        "note": "achieved = 8*M*N*K useful complex64 flops.  The fp32-accurate precisions split every "
+                                "operand in hi + lo and issue 3 tensor-core products per useful one, so the useful-flop "
+                                "ceiling is peak/3; `issued` compares the issued tensor flops with cuBLAS 8192^3 in the "
+                                "same operand type measured in this run"}
         else:
             ach = st.bytes_c64 / (best_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "traffic": None, "peak_kind": f"copy bandwidth ({pk['source']})"}
-        roofline["kernel"] = {N.TNC_ALGO_TC: "gemm3xtf32_2cta_kernel", N.TNC_ALGO_STEM: "stem_kernel",
+        roofline["kernel"] = {N.TNC_ALGO_TC: f"gemm_2cta_kernel<{precision}>", N.TNC_ALGO_STEM: "stem_kernel",
                               N.TNC_ALGO_SIMT: "simt_einsum_kernel"}[rec.algo]
         roofline["step"] = {"index": st.index, "m_bits": len(st.m_modes), "n_bits": len(st.n_modes),
                             "k_bits": len(st.k_modes), "rows": st.nb, "flops": st.flops, "bytes": st.bytes_c64,
                             "ms": best_ms, "share_of_slice": best_ms / slice_ms}
         breakdown = {"slice_ms_profiled": slice_ms, "gemm_ms": gemm_ms, "pack_ms": pack_ms, "stem_ms": stem_ms,
                      "generic_ms": simt_ms, "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms - stem_ms}
+
+    # ---- the reduced-precision complex-half mode on the same slices (rank 0, N = 1): throughput and
+    # fidelity against the complex64 result
+    half = None
+    if rank == 0 and world == 1 and not args.no_half and precision != "f16":
+        from dataclasses import replace
+        hplan = C.ContractionPlan(case.scheme, {k: tuple(v.shape) for k, v in case.leaves.items()},
+                                  case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
+                                  slicing_indices=case.slicing_indices(), options=replace(sim.plan_options, tc_precision="f16"))
+        lo, hi = slice_range(args.warmup)
+        ws = C.get_workspace(dev, max(plan.workspace_bytes, hplan.workspace_bytes))
+        out.zero_()
+        plan.execute(blob, out, lo, hi, ws, stream.cuda_stream)
+        ref64 = out.clone()
+        hout = torch.zeros_like(out)
+        for _ in range(2):
+            hout.zero_()
+            hplan.execute(blob, hout, lo, hi, ws, stream.cuda_stream)
+        torch.cuda.synchronize(dev)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for _ in range(2):
+            hout.zero_()
+            hplan.execute(blob, hout, lo, hi, ws, stream.cuda_stream)
+        h1.record(stream)
+        torch.cuda.synchronize(dev)
+        a, b = ref64.reshape(-1).to(torch.complex128), hout.reshape(-1).to(torch.complex128)
+        fid = (torch.vdot(a, b).abs() ** 2 / (torch.vdot(a, a).real * torch.vdot(b, b).real)).item()
+        half = {"value": 2 * (hi - lo) / (h0.elapsed_time(h1) * 1e-3), "unit": UNIT, "tc_precision": "f16",
+                "fidelity_vs_complex64": fid,
+                "max_err_over_rms": ((a - b).abs().max() / a.abs().pow(2).mean().sqrt()).item()}
+        del hplan
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only)
     cpu = None
@@ -416,7 +463,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "complex64 (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "dtype": f"complex64 ({precision} split-precision products on tcgen05, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": args.workload, "slices_per_step_per_gpu": S, "sliced_bonds": plan.n_sliced,
                        "total_slices_of_task": f"2^{plan.n_sliced}", "amplitudes_per_slice": int(out.numel()),
                        "scheme_steps": work["steps"], "l2": "working set >> L2 (multi-GiB intermediates), no flush"},
@@ -424,7 +471,7 @@ def main():
             "flops_per_slice": work["ref_flops_per_slice"], "bytes_per_slice": work["ref_bytes_per_slice"],
             "extrapolated_full_task_seconds": (2.0 ** plan.n_sliced) / value,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "breakdown": breakdown,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "half_mode": half,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TNC_ABI_VERSION 3
+#define TNC_ABI_VERSION 4
 #define TNC_MAX_BITS 40          /* max bit modes per group / per tensor */
 #define TNC_MAX_SLICED 8         /* max sliced bonds on one leaf */
 
@@ -54,9 +54,22 @@ typedef enum tnc_phase {
     TNC_PHASE_SLICE = 1          /* runs for every slice id */
 } tnc_phase;
 
+/* Operand precision of the tensor-core steps of a complex64 plan (fp32 accumulation always). */
+typedef enum tnc_tc_precision {
+    TNC_TC_3XTF32 = 0,           /* fp32-accurate: TF32 hi/lo split, 3 MMAs per useful one */
+    TNC_TC_3XF16 = 1,            /* fp32-accurate: fp16 hi/lo split with power-of-two operand scaling,
+                                    3 MMAs per useful one at twice the TF32 rate (default) */
+    TNC_TC_F16 = 2               /* reduced precision: fp16 operands, 1 MMA per useful one -- the
+                                    complex-half tensor-core mode of Pan et al. 2023 */
+} tnc_tc_precision;
+
+typedef enum tnc_option {
+    TNC_OPT_TC_PRECISION = 0     /* value: tnc_tc_precision */
+} tnc_option;
+
 typedef enum tnc_algo {
     TNC_ALGO_SIMT = 0,           /* generic CUDA-core kernel, any shape */
-    TNC_ALGO_TC = 1,             /* tcgen05 tensor-core kernel (3xTF32 for c64): compute-bound steps */
+    TNC_ALGO_TC = 1,             /* tcgen05 tensor-core kernel (split-precision for c64): compute-bound steps */
     TNC_ALGO_STEM = 2            /* streaming fp32 kernel for HBM-bound steps (tiny right operand) */
 } tnc_algo;
 
@@ -132,6 +145,8 @@ int64_t tnc_einsum_tc_scratch_bytes(int32_t dtype, const tnc_einsum* e);
 /* ---- plan construction (host only, no CUDA calls until finalize) ---- */
 int tnc_abi_version(void);
 int tnc_plan_create(int32_t dtype, int32_t n_sliced_bonds, tnc_plan** out);
+/* Before finalize.  Unknown options / values return TNC_ERR_INVALID. */
+int tnc_plan_set_option(tnc_plan* plan, int32_t option, int64_t value);
 int tnc_plan_add_table(tnc_plan* plan, const int32_t* data, int64_t n, int32_t* table_id);
 int tnc_plan_add_leaves(tnc_plan* plan, int32_t phase, const tnc_leaf* leaves, int32_t n);
 int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* op);

@@ -200,17 +200,19 @@ def single_step_case(m, n, k, seed):
     return [((0, 1), eq)], {0: torch.from_numpy(a), 1: torch.from_numpy(b)}, want
 
 
-def force_options(algo):
+def force_options(algo, precision=None):
     from artensor_b200 import PlanOptions
-    return {"tc": PlanOptions(tc_min_flops=0, tc_min_intensity=0),
+    extra = {} if precision is None else {"tc_precision": precision}
+    return {"tc": PlanOptions(tc_min_flops=0, tc_min_intensity=0, **extra),
             "stem": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=0),
             "simt": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=1 << 62)}[algo]
 
 
-def run_single_step(dev, scheme, leaves, algo):
+def run_single_step(dev, scheme, leaves, algo, precision=None):
     from artensor_b200 import ContractionPlan
     from artensor_b200 import _native as N
-    plan = ContractionPlan(scheme, {k: tuple(v.shape) for k, v in leaves.items()}, False, options=force_options(algo))
+    plan = ContractionPlan(scheme, {k: tuple(v.shape) for k, v in leaves.items()}, False,
+                           options=force_options(algo, precision))
     assert plan.step_algo == [{"tc": N.TNC_ALGO_TC, "stem": N.TNC_ALGO_STEM, "simt": N.TNC_ALGO_SIMT}[algo]]
     blob = plan.pack_leaves({k: v.to(dev) for k, v in leaves.items()})
     out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
@@ -224,16 +226,52 @@ TC_SHAPES = [(7, 3, 2), (8, 1, 1), (10, 5, 5), (6, 7, 9), (12, 4, 4), (3, 8, 6),
              (2, 1, 4), (8, 8, 8)]
 
 
+# fp32-accurate precisions must meet the complex64 bar; the complex-half mode (fp16 operands, one
+# product) is held to fp16 round-off: 2^-11 per operand, ~1e-3 of the rms after the k-sum.
+TC_PRECISIONS = [("3xtf32", 1e-5), ("3xf16", 1e-5), ("f16", 2e-3)]
+
+
+@pytest.mark.parametrize("precision,tol", TC_PRECISIONS)
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_tc_single_step_matches_fp64_einsum(dev, shape):
+def test_tc_single_step_matches_fp64_einsum(dev, shape, precision, tol):
     m, n, k = shape
+    if precision != "3xtf32" and k < 2:
+        pytest.skip("fp16 panels need >= 2 contracted bits (16-byte TMA rows); such steps run on the streaming kernel")
     scheme, leaves, want = single_step_case(m, n, k, seed=m * 100 + n * 10 + k)
-    got = run_single_step(dev, scheme, leaves, "tc")
+    got = run_single_step(dev, scheme, leaves, "tc", precision)
     rms = np.sqrt(np.mean(np.abs(want) ** 2))
     err = np.abs(got - want).max() / rms
-    assert err < 1e-5, f"m={m} n={n} k={k}: max err / rms = {err:.3e}"
+    assert err < tol, f"{precision} m={m} n={n} k={k}: max err / rms = {err:.3e}"
     ref = run_single_step(dev, scheme, leaves, "simt")          # generic kernel on the same step
     assert np.abs(ref - want).max() / rms < 5e-6
+
+
+@pytest.mark.parametrize("scale_a,scale_b", [(1e-9, 1.0), (3e-7, 2e-8), (1e6, 1e-12), (5e4, 7e3)])
+def test_tc_3xf16_operand_scaling(dev, scale_a, scale_b):
+    """The fp16 split scales each operand by a power of two found by the amax kernel: results
+    must not depend on the magnitude of the inputs (n53 amplitudes are ~1e-8, far below the fp16
+    range), and entries spread over many orders of magnitude must keep the fp32 bar."""
+    scheme, leaves, _ = single_step_case(9, 6, 7, seed=77)
+    rng = np.random.RandomState(3)
+    a = leaves[0].numpy() * scale_a
+    b = leaves[1].numpy() * scale_b
+    # wide dynamic range inside one operand: a quarter of the entries 2^-20 smaller
+    a = a * np.where(rng.rand(*a.shape) < 0.25, 2.0 ** -20, 1.0).astype(np.float32)
+    leaves = {0: torch.from_numpy(a.astype(np.complex64)), 1: torch.from_numpy(b.astype(np.complex64))}
+    want = np.einsum(scheme[0][1], a.astype(np.complex128), b.astype(np.complex128), optimize=True)
+    got = run_single_step(dev, scheme, leaves, "tc", "3xf16")
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    err = np.abs(got - want).max() / rms
+    assert err < 1e-5, f"scales {scale_a:g}, {scale_b:g}: max err / rms = {err:.3e}"
+
+
+def test_tc_zero_operand(dev):
+    """amax == 0 must not poison the scaling (no inf/nan): the result is exactly zero."""
+    scheme, leaves, _ = single_step_case(8, 5, 6, seed=9)
+    leaves[1] = torch.zeros_like(leaves[1])
+    for precision in ("3xf16", "f16"):
+        got = run_single_step(dev, scheme, leaves, "tc", precision)
+        assert np.all(got == 0)
 
 
 # k + n <= 12: B[k][n] has to fit the streaming kernel's shared memory
@@ -251,24 +289,37 @@ def test_stem_single_step_matches_fp64_einsum(dev, shape):
     assert np.abs(got - want).max() / rms < 2e-6, f"m={m} n={n} k={k}"
 
 
-def test_tc_long_contraction_keeps_fp32_accuracy(dev):
-    """K = 16384 complex (32768 real) accumulated in tensor memory: 3xTF32 must stay within the
-    complex64 bar (1e-5 of the rms amplitude) even for the longest contraction of the n53 tree."""
+@pytest.mark.parametrize("precision", ["3xtf32", "3xf16"])
+def test_tc_long_contraction_keeps_fp32_accuracy(dev, precision):
+    """K = 16384 complex (32768 real) accumulated in tensor memory: the split product must stay
+    within the complex64 bar (1e-5 of the rms amplitude) even for the longest contraction of the
+    n53 tree."""
     scheme, leaves, want = single_step_case(7, 6, 14, seed=5)
-    got = run_single_step(dev, scheme, leaves, "tc")
+    got = run_single_step(dev, scheme, leaves, "tc", precision)
     rms = np.sqrt(np.mean(np.abs(want) ** 2))
     err = np.abs(got - want) / rms
-    print(f"K=16384 3xTF32: max err/rms {err.max():.3e}, rms err/rms {np.sqrt(np.mean(err ** 2)):.3e}")
+    print(f"K=16384 {precision}: max err/rms {err.max():.3e}, rms err/rms {np.sqrt(np.mean(err ** 2)):.3e}")
     assert err.max() < 1e-5
 
 
-@pytest.mark.parametrize("algo", ["tc", "stem"])
+def test_tc_two_cta_blocked_tiles(dev):
+    """M, N, K large enough for the cta_group::2 kernel on tile-contiguous panels (the shape
+    class of the fat GEMM of the n53 tree), every precision."""
+    scheme, leaves, want = single_step_case(10, 8, 8, seed=21)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    for precision, tol in TC_PRECISIONS:
+        got = run_single_step(dev, scheme, leaves, "tc", precision)
+        err = np.abs(got - want).max() / rms
+        assert err < tol, f"{precision}: max err / rms = {err:.3e}"
+
+
+@pytest.mark.parametrize("algo", ["tc", "tc:3xtf32", "stem"])
 @pytest.mark.parametrize("name", SMALL)
 def test_forced_algorithm_on_every_step_matches_reference(dev, name, algo):
     """Whole schemes (plain, outer and chunked batched steps, sliced) with every eligible step
-    forced onto the tensor-core path / onto the streaming kernel."""
+    forced onto the tensor-core path (default 3xF16 and 3xTF32) / onto the streaming kernel."""
     case, exp, sim = sim_from(name)
-    sim.plan_options = force_options(algo)
+    sim.plan_options = force_options(*algo.split(":"))
     got = sim.contraction(device=dev).cpu().numpy()
     want = exp["per_slice_c128"].sum(axis=0).reshape(exp["shape"])
     if case.permute_dims is not None:
@@ -316,3 +367,48 @@ def test_n30_sparse_10000_amplitudes_vs_reference_and_google(dev):
     assert np.median(rel) < 2e-4 and np.quantile(rel, 0.99) < 5e-3
     _c.release_workspaces()
     torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------
+# reduced-precision complex-half mode (dtype=torch.complex32): fidelity against complex64
+# ---------------------------------------------------------------------------------------------
+def fidelity(a, b):
+    """|<a|b>|^2 / (<a|a><b|b>): the notebook's measure (examples/sycamore.ipynb:169-172)."""
+    a, b = np.asarray(a, np.complex128).reshape(-1), np.asarray(b, np.complex128).reshape(-1)
+    return abs(np.vdot(a, b)) ** 2 / (np.vdot(a, a).real * np.vdot(b, b).real)
+
+
+# Stated tolerance of the half mode: fidelity >= 0.9999 against the complex64 result, and every
+# amplitude within 1e-2 of the rms.  (fp16 operands carry 2^-11 relative error each; the errors of
+# a k-sum add incoherently.)
+HALF_MIN_FIDELITY = 0.9999
+HALF_MAX_ERR = 1e-2
+
+
+@pytest.mark.parametrize("name", ["n12_full", "n12_sparse64_sc9", "n12_sparse256c_sc10"])
+def test_half_mode_fidelity_small(dev, name):
+    case, exp, sim = sim_from(name)
+    sim.plan_options = force_options("tc")            # every eligible step through the fp16 GEMM
+    c64 = sim.contraction(device=dev).cpu().numpy()
+    half = sim.contraction(device=dev, dtype=torch.complex32).cpu().numpy()
+    assert half.dtype == np.complex64
+    f = fidelity(c64, half)
+    rms = np.sqrt(np.mean(np.abs(c64) ** 2))
+    err = np.abs(half - c64).max() / rms
+    print(f"{name}: half-mode fidelity {f:.8f}, max err / rms {err:.3e}")
+    assert f >= HALF_MIN_FIDELITY and err < HALF_MAX_ERR
+    assert err > 0            # it really is a different arithmetic, not the complex64 plan again
+
+
+def test_half_mode_n53_m12_vs_complex64(dev):
+    """BASELINE config 4: n53 m12 sliced sparse-state, complex-half tensor-core mode vs complex64."""
+    case, exp, sim = sim_from("n53_m12_sparse1024")
+    s = int(exp["slice_ids"][0])
+    c64 = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()
+    half = sim.contraction(device=dev, slice_range=(s, s + 1), dtype=torch.complex32).cpu().numpy()
+    f = fidelity(c64, half)
+    rms = np.sqrt(np.mean(np.abs(c64) ** 2))
+    err = np.abs(half - c64).max() / rms
+    print(f"n53_m12 slice {s}: half-mode fidelity {f:.8f}, max err / rms {err:.3e}")
+    assert f >= HALF_MIN_FIDELITY and err < HALF_MAX_ERR
+    assert_amplitudes_close(c64, exp["per_slice_c64"][0])

@@ -29,11 +29,18 @@ def main():
     ap.add_argument("--top", type=int, default=25)
     ap.add_argument("--slice", type=int, default=0)
     ap.add_argument("--check", action="store_true", help="compare with the golden per-slice amplitudes")
+    ap.add_argument("--precision", default=None, choices=["3xtf32", "3xf16", "f16"])
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
     case = load_case(os.path.join(ROOT, "tests", "golden", f"{a.case}.case.gz"))
     sim = TensorNetworkSimulation.from_case(case)
+    kw = {}
     if a.tc_min_flops is not None:
-        sim.plan_options = PlanOptions(tc_min_flops=a.tc_min_flops)
+        kw["tc_min_flops"] = a.tc_min_flops
+    if a.precision is not None:
+        kw["tc_precision"] = a.precision
+    sim.plan_options = PlanOptions(**kw)
+    print(f"options: {sim.plan_options}", flush=True)
     plan = sim.plan()
     dev = torch.device("cuda:0")
     blob = plan.pack_leaves(case.leaves, device=dev)
@@ -87,7 +94,7 @@ def main():
         else:
             print(f"  op {r['op']:4d} {r['kind']:8s} {r['ms']:9.3f} ms")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"probe_{a.case}.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"probe_{a.case}{a.tag}.json"), "w") as f:
         json.dump({"case": a.case, "slice_ms": tot, "by_class": by_algo, "ops": rows}, f)
 
 
