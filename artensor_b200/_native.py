@@ -14,7 +14,7 @@ TNC_PROFILE_SLOTS = 4
 
 TNC_C64, TNC_C32 = 0, 1
 TNC_PHASE_ONCE, TNC_PHASE_SLICE = 0, 1
-TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM = 0, 1, 2
+TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM, TNC_ALGO_SKINNY = 0, 1, 2, 3
 TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
 TNC_EINSUM_OUTER_ROWS = 1
 TNC_TC_3XTF32, TNC_TC_3XF16, TNC_TC_F16 = 0, 1, 2

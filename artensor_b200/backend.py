@@ -93,6 +93,9 @@ class PlanOptions:
     """Algorithm selection per step:
       * tcgen05 GEMM for compute-bound steps: flops >= tc_min_flops and arithmetic intensity
         (flops / algorithmic bytes) >= tc_min_intensity;
+      * the streaming tcgen05 kernel ("skinny": A read in place, small right operand resident in
+        shared memory) for steps of its shape class whose left operand has >= skinny_min_elems
+        amplitudes -- it replaces both the pack + GEMM lowering and the fp32 streaming kernel there;
       * the streaming fp32 kernel for the other large steps (HBM-bound "stem" steps);
       * the generic kernel for the hundreds of tiny steps (< stem_min_elems output elements).
     tc_precision: operand precision of the tensor-core steps (include/tnc_b200.h tnc_tc_precision):
@@ -101,6 +104,10 @@ class PlanOptions:
     tc_min_flops: float = 1e8
     tc_min_intensity: float = 24.0
     stem_min_elems: int = 1 << 12
+    skinny_min_elems: int = 1 << 20
+    # rows of <= 8 outputs leave the tensor-core kernel latency-bound (measured on n53 m20: 1.4-3.0
+    # TB/s against 2.9-4.8 TB/s of the fp32 streaming kernel, whose FMA load is light there)
+    skinny_min_n: int = 4
     hoist: bool = True
     tc_precision: str = field(default_factory=lambda: os.environ.get("TNC_TC_PRECISION", "3xf16"))
 
@@ -139,6 +146,19 @@ def stem_eligible(st: Step):
     """Mirror of stem_supported() in csrc/stem.cu: B[k][n] and the k offsets must fit shared memory."""
     k, n = len(st.k_modes), len(st.n_modes)
     return len(st.h_modes) == 0 and k <= 12 and n <= 12 and (8 << (k + n)) + (4 << k) <= 60 * 1024
+
+
+def skinny_eligible(st: Step, precision, min_n=1):
+    """Mirror of skinny_supported() in csrc/skinny.cu; `min_n` is the planner's own cut-off
+    (PlanOptions.skinny_min_n)."""
+    k, n, m = len(st.k_modes), len(st.n_modes), len(st.m_modes)
+    if precision == "3xtf32" or len(st.h_modes) != 0:
+        return False
+    if not (2 <= k <= 5 and max(1, min_n) <= n <= 7 and m >= 7):
+        return False
+    if st.rb is not None and st.nb != 1:
+        return False
+    return not (st.ra is None and st.nb != 1)
 
 
 class ContractionPlan:
@@ -214,7 +234,9 @@ class ContractionPlan:
             algo = N.TNC_ALGO_SIMT
             if self.dtype == N.TNC_C64:
                 o = self.options
-                if st.flops >= o.tc_min_flops and st.flops >= o.tc_min_intensity * st.bytes_c64 and tc_eligible(st, o.tc_precision):
+                if st.a.numel >= o.skinny_min_elems and skinny_eligible(st, o.tc_precision, o.skinny_min_n):
+                    algo = N.TNC_ALGO_SKINNY
+                elif st.flops >= o.tc_min_flops and st.flops >= o.tc_min_intensity * st.bytes_c64 and tc_eligible(st, o.tc_precision):
                     algo = N.TNC_ALGO_TC
                 elif st.c.numel >= o.stem_min_elems and stem_eligible(st):
                     algo = N.TNC_ALGO_STEM

@@ -46,6 +46,7 @@
 #include <vector>
 
 #include "tc_gemm.h"
+#include "tc_common.cuh"
 
 namespace tnc {
 
@@ -89,15 +90,6 @@ __device__ __forceinline__ float tf32_round(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-
-// Power-of-two scaling of an fp16-split operand.  e = biased exponent of the operand's largest
-// magnitude (clamped): scale = 2^(141 - e) maps it into [2^14, 2^15); inv_scale undoes it.
-__device__ __forceinline__ uint32_t amax_exponent(uint32_t amax_bits) {
-    const uint32_t e = (amax_bits >> 23) & 0xffu;
-    return e < 15u ? 15u : (e > 254u ? 254u : e);
-}
-__device__ __forceinline__ float f16_scale(uint32_t amax_bits) { return __uint_as_float((268u - amax_exponent(amax_bits)) << 23); }
-__device__ __forceinline__ float f16_inv_scale(uint32_t amax_bits) { return __uint_as_float((amax_exponent(amax_bits) - 14u) << 23); }
 
 // Largest |component| of two tensors in one launch: blocks [0, split) reduce `a`, the rest `b`;
 // out[0] / out[1] (zeroed before the launch) receive the float bits (non-negative floats order
@@ -363,27 +355,6 @@ constexpr int kSmemBudget = 200 * 1024;
 // reduced-precision mode tolerates the bias and drains less often.
 constexpr int kDefaultKC[3] = {1, 1, 4};
 
-template <int PREC>
-struct Prec;
-template <>
-struct Prec<TNC_TC_3XTF32> {
-    static constexpr int ELEM = 4, PANELS = 2;
-    static constexpr uint32_t FMT = 2;      // instruction-descriptor operand format: TF32
-    static constexpr bool F16 = false;
-};
-template <>
-struct Prec<TNC_TC_3XF16> {
-    static constexpr int ELEM = 2, PANELS = 2;
-    static constexpr uint32_t FMT = 0;      // F16
-    static constexpr bool F16 = true;
-};
-template <>
-struct Prec<TNC_TC_F16> {
-    static constexpr int ELEM = 2, PANELS = 1;
-    static constexpr uint32_t FMT = 0;
-    static constexpr bool F16 = true;
-};
-
 // elements of K per k-block
 constexpr int bk_of(int prec) { return prec == TNC_TC_3XTF32 ? BKB / 4 : BKB / 2; }
 
@@ -464,98 +435,6 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
     return t;
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// A wait that cannot complete is a protocol bug: trap after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    uint32_t polls = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile, 128-byte rows, SWIZZLE_128B: rows 128 B apart, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units      bits [0,14)
-    d |= (uint64_t)1 << 16;                     // leading byte offset (unused here)  bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset = 1024 B        bits [32,46)
-    d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)        bits [46,48)
-    d |= (uint64_t)2 << 61;                     // SWIZZLE_128B                       bits [61,64)
-    return d;
-}
-// instruction descriptor: D fp32, A/B in the precision's format, both K-major
-template <int PREC>
-__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
-    return (1u << 4) | (Prec<PREC>::FMT << 7) | (Prec<PREC>::FMT << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-// D[tmem] (+)= A[smem] * B[smem]^T; CG = cta_group
-template <int PREC, int CG>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (Prec<PREC>::F16) {
-        if constexpr (CG == 1) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-                : "memory");
-        } else {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-                : "memory");
-        }
-    } else {
-        if constexpr (CG == 1) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-                : "memory");
-        } else {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-                : "memory");
-        }
-    }
-}
 // One k-block of the split product into the accumulator at `tacc`: small cross terms first, then
 // the leading term (hi part only in the reduced-precision mode); +2 = 32 bytes = one MMA K step.
 template <int PREC, int CG>
@@ -576,24 +455,6 @@ __device__ __forceinline__ void umma_kblock(uint32_t tacc, uint64_t a_hi, uint64
         acc = 1;
     }
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // Adds one finished TMEM chunk (CPT columns of this thread's lane) into the fp32 registers,
 // round-to-nearest.
 template <int CPT>

@@ -256,13 +256,19 @@ int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* e) {
             return TNC_ERR_INVALID;
         }
     }
-    if (e->algo != TNC_ALGO_SIMT && e->algo != TNC_ALGO_TC && e->algo != TNC_ALGO_STEM) {
+    if (e->algo != TNC_ALGO_SIMT && e->algo != TNC_ALGO_TC && e->algo != TNC_ALGO_STEM && e->algo != TNC_ALGO_SKINNY) {
         set_error("einsum: unknown algo %d", e->algo);
         return TNC_ERR_INVALID;
     }
     if (e->algo == TNC_ALGO_STEM && !stem_supported(*e, plan->dtype)) {
         set_error("einsum: the streaming kernel does not support this step (k=%d n=%d h=%d, output must be [rows][m][n])",
                   e->n_k, e->n_n, e->n_h);
+        return TNC_ERR_UNSUPPORTED;
+    }
+    if (e->algo == TNC_ALGO_SKINNY && !skinny_supported(*e, plan->dtype, plan->tc_precision)) {
+        set_error("einsum: the streaming tensor-core kernel does not support this step (m=%d k=%d n=%d h=%d nb=%d, "
+                  "precision %d; needs 2 <= k <= 5, 1 <= n <= 7, m >= 7, one right operand, output [rows][m][n])",
+                  e->n_m, e->n_k, e->n_n, e->n_h, e->nb, plan->tc_precision);
         return TNC_ERR_UNSUPPORTED;
     }
     Op op;
@@ -408,10 +414,12 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
                 plan->last_launches += launches;
                 return rc;
             }
-            if (e.algo == TNC_ALGO_STEM) {
+            if (e.algo == TNC_ALGO_STEM || e.algo == TNC_ALGO_SKINNY) {
                 const int32_t* ra = e.rows_a >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_a]) : nullptr;
                 const int32_t* rb = e.rows_b >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_b]) : nullptr;
                 plan->last_launches += 1;
+                if (e.algo == TNC_ALGO_SKINNY)
+                    return launch_skinny(e, plan->tc_precision, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st);
                 return launch_stem(e, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st);
             }
             SimtEinsumParams p{};

@@ -43,6 +43,12 @@ bool stem_supported(const tnc_einsum& e, int dtype);
 int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
                 const int32_t* dev_rows_b, cudaStream_t s);
 
+// ---------------------------------------------------------------- streaming tensor-core ("skinny") einsum
+// Same operand shapes and output layout as the streaming kernel, multiplied on tcgen05 (skinny.cu).
+bool skinny_supported(const tnc_einsum& e, int dtype, int precision);
+int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
+                  const int32_t* dev_rows_b, cudaStream_t s);
+
 // ---------------------------------------------------------------- leaves
 struct LeafDev {
     int64_t src_offset;      // elements

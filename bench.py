@@ -367,7 +367,7 @@ def main():
         steps = plan.op_steps[N.TNC_PHASE_SLICE]
         slice_ms = sum(ms_slice[i * SL] for i in range(len(ops)))
         best, best_ms = None, -1.0
-        gemm_ms = pack_ms = simt_ms = stem_ms = 0.0
+        gemm_ms = pack_ms = simt_ms = stem_ms = skinny_ms = 0.0
         for i, ((kind, rec), st) in enumerate(zip(ops, steps)):
             if kind != "einsum":
                 continue
@@ -378,6 +378,9 @@ def main():
             elif rec.algo == N.TNC_ALGO_STEM:
                 k_ms = ms_slice[i * SL]
                 stem_ms += k_ms
+            elif rec.algo == N.TNC_ALGO_SKINNY:
+                k_ms = ms_slice[i * SL]
+                skinny_ms += k_ms
             else:
                 k_ms = ms_slice[i * SL]
                 simt_ms += k_ms
@@ -407,13 +410,14 @@ def main():
             ach = st.bytes_c64 / (best_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "traffic": None, "peak_kind": f"copy bandwidth ({pk['source']})"}
-        roofline["kernel"] = {N.TNC_ALGO_TC: f"gemm_2cta_kernel<{precision}>", N.TNC_ALGO_STEM: "stem_kernel",
+        roofline["kernel"] = {N.TNC_ALGO_TC: f"gemm_2cta_kernel<{precision}>", N.TNC_ALGO_STEM: "stem_kernel", N.TNC_ALGO_SKINNY: "skinny_kernel",
                               N.TNC_ALGO_SIMT: "simt_einsum_kernel"}[rec.algo]
         roofline["step"] = {"index": st.index, "m_bits": len(st.m_modes), "n_bits": len(st.n_modes),
                             "k_bits": len(st.k_modes), "rows": st.nb, "flops": st.flops, "bytes": st.bytes_c64,
                             "ms": best_ms, "share_of_slice": best_ms / slice_ms}
         breakdown = {"slice_ms_profiled": slice_ms, "gemm_ms": gemm_ms, "pack_ms": pack_ms, "stem_ms": stem_ms,
-                     "generic_ms": simt_ms, "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms - stem_ms}
+                     "skinny_ms": skinny_ms, "generic_ms": simt_ms,
+                     "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms - stem_ms - skinny_ms}
 
     # ---- the reduced-precision complex-half mode on the same slices (rank 0, N = 1): throughput and
     # fidelity against the complex64 result

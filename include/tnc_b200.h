@@ -70,7 +70,9 @@ typedef enum tnc_option {
 typedef enum tnc_algo {
     TNC_ALGO_SIMT = 0,           /* generic CUDA-core kernel, any shape */
     TNC_ALGO_TC = 1,             /* tcgen05 tensor-core kernel (split-precision for c64): compute-bound steps */
-    TNC_ALGO_STEM = 2            /* streaming fp32 kernel for HBM-bound steps (tiny right operand) */
+    TNC_ALGO_STEM = 2,           /* streaming fp32 kernel for HBM-bound steps (tiny right operand) */
+    TNC_ALGO_SKINNY = 3          /* streaming tcgen05 kernel: A read in place (no pack pass), small right
+                                    operand resident in shared memory; 4..32 flop/byte steps */
 } tnc_algo;
 
 /* tnc_einsum.flags.  OUTER_ROWS: the output rows enumerate ALL pairs of operand rows, A-major

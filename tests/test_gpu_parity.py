@@ -203,9 +203,11 @@ def single_step_case(m, n, k, seed):
 def force_options(algo, precision=None):
     from artensor_b200 import PlanOptions
     extra = {} if precision is None else {"tc_precision": precision}
-    return {"tc": PlanOptions(tc_min_flops=0, tc_min_intensity=0, **extra),
-            "stem": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=0),
-            "simt": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=1 << 62)}[algo]
+    off = 1 << 62
+    return {"tc": PlanOptions(tc_min_flops=0, tc_min_intensity=0, skinny_min_elems=off, **extra),
+            "skinny": PlanOptions(skinny_min_elems=0, skinny_min_n=1, **extra),
+            "stem": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=0, skinny_min_elems=off),
+            "simt": PlanOptions(tc_min_flops=float("inf"), stem_min_elems=off, skinny_min_elems=off)}[algo]
 
 
 def run_single_step(dev, scheme, leaves, algo, precision=None):
@@ -213,7 +215,8 @@ def run_single_step(dev, scheme, leaves, algo, precision=None):
     from artensor_b200 import _native as N
     plan = ContractionPlan(scheme, {k: tuple(v.shape) for k, v in leaves.items()}, False,
                            options=force_options(algo, precision))
-    assert plan.step_algo == [{"tc": N.TNC_ALGO_TC, "stem": N.TNC_ALGO_STEM, "simt": N.TNC_ALGO_SIMT}[algo]]
+    assert plan.step_algo == [{"tc": N.TNC_ALGO_TC, "stem": N.TNC_ALGO_STEM, "simt": N.TNC_ALGO_SIMT,
+                               "skinny": N.TNC_ALGO_SKINNY}[algo]]
     blob = plan.pack_leaves({k: v.to(dev) for k, v in leaves.items()})
     out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
     ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
@@ -289,6 +292,52 @@ def test_stem_single_step_matches_fp64_einsum(dev, shape):
     assert np.abs(got - want).max() / rms < 2e-6, f"m={m} n={n} k={k}"
 
 
+# streaming tensor-core kernel: 2 <= k <= 5, 1 <= n <= 7, m >= 7
+SKINNY_SHAPES = [(7, 1, 2), (8, 3, 3), (9, 5, 5), (10, 7, 4), (12, 2, 5), (13, 6, 2), (9, 4, 3), (14, 7, 5), (16, 5, 4),
+                 (11, 7, 2), (15, 1, 5)]
+
+
+@pytest.mark.parametrize("precision,tol", [("3xf16", 2e-6), ("f16", 2e-3)])
+@pytest.mark.parametrize("shape", SKINNY_SHAPES)
+def test_skinny_single_step_matches_fp64_einsum(dev, shape, precision, tol):
+    """One K <= 64 accumulation chunk per tile and 22-bit operands: the fp32-accurate precision
+    must sit near fp32 round-off, not merely inside the 1e-5 bar."""
+    m, n, k = shape
+    scheme, leaves, want = single_step_case(m, n, k, seed=3 + m * 100 + n * 10 + k)
+    got = run_single_step(dev, scheme, leaves, "skinny", precision)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    err = np.abs(got - want).max() / rms
+    assert err < tol, f"{precision} m={m} n={n} k={k}: max err / rms = {err:.3e}"
+
+
+def test_skinny_row_scaling(dev):
+    """Every row of A is scaled by its own power of two: rows 2^40 apart in magnitude (and a zero
+    row) must all keep full relative accuracy, whatever the magnitude of B."""
+    scheme, leaves, _ = single_step_case(10, 5, 4, seed=12)
+    eq = scheme[0][1]
+    a = leaves[0].numpy().astype(np.complex128)
+    b = leaves[1].numpy().astype(np.complex128) * 3e-9
+    lhs = eq.split(",")[0]
+    mode = next(ch for ch in lhs if ch in eq.split("->")[1])           # a left-only mode of A
+    ax = lhs.index(mode)
+    sl = [slice(None)] * a.ndim
+    sl[ax] = 1
+    a[tuple(sl)] *= 2.0 ** -40
+    leaves = {0: torch.from_numpy(a.astype(np.complex64)), 1: torch.from_numpy(b.astype(np.complex64))}
+    a64, b64 = leaves[0].numpy().astype(np.complex128), leaves[1].numpy().astype(np.complex128)
+    want = np.einsum(eq, a64, b64, optimize=True)
+    got = run_single_step(dev, scheme, leaves, "skinny", "3xf16")
+    out_ax = eq.split("->")[1].index(mode)
+    for half in (0, 1):
+        so = [slice(None)] * want.ndim
+        so[out_ax] = half
+        w, g = want[tuple(so)], got[tuple(so)]
+        rms = np.sqrt(np.mean(np.abs(w) ** 2))
+        assert np.abs(g - w).max() / rms < 2e-6, f"half {half}"
+    leaves[0] = torch.zeros_like(leaves[0])
+    assert np.all(run_single_step(dev, scheme, leaves, "skinny", "3xf16") == 0)
+
+
 @pytest.mark.parametrize("precision", ["3xtf32", "3xf16"])
 def test_tc_long_contraction_keeps_fp32_accuracy(dev, precision):
     """K = 16384 complex (32768 real) accumulated in tensor memory: the split product must stay
@@ -313,7 +362,7 @@ def test_tc_two_cta_blocked_tiles(dev):
         assert err < tol, f"{precision}: max err / rms = {err:.3e}"
 
 
-@pytest.mark.parametrize("algo", ["tc", "tc:3xtf32", "stem"])
+@pytest.mark.parametrize("algo", ["tc", "tc:3xtf32", "stem", "skinny"])
 @pytest.mark.parametrize("name", SMALL)
 def test_forced_algorithm_on_every_step_matches_reference(dev, name, algo):
     """Whole schemes (plain, outer and chunked batched steps, sliced) with every eligible step

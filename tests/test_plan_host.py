@@ -214,13 +214,18 @@ def test_streaming_kernel_layouts_match_reference(name):
 
 
 def test_default_options_pick_algorithms_by_intensity():
-    """n53 m20 (the bench workload): the fat GEMM goes to tcgen05, the stem to the streaming
-    kernel, the tiny steps to the generic kernel."""
+    """n53 m20 (the bench workload): the fat GEMM goes to the pack + tcgen05 GEMM lowering, the
+    stem to the streaming kernels (tcgen05 for 2 <= k <= 5, fp32 otherwise), the tiny steps to the
+    generic kernel."""
     case, _ = load_golden("n53_m20_sparse1024")
     plan = make_plan(case)
-    by = {a: [st for st, x in zip(plan.steps, plan.step_algo) if x == a] for a in (0, 1, 2)}
+    by = {a: [st for st, x in zip(plan.steps, plan.step_algo) if x == a] for a in (0, 1, 2, 3)}
     fat = max(plan.steps, key=lambda s: s.flops)
     assert fat in by[N.TNC_ALGO_TC] and fat.flops > 5e13
     assert all(s.flops >= 24 * s.bytes_c64 for s in by[N.TNC_ALGO_TC])
-    assert sum(s.bytes_c64 for s in by[N.TNC_ALGO_STEM]) > 0.7 * sum(s.bytes_c64 for s in plan.steps if s is not fat)
+    streamed = by[N.TNC_ALGO_STEM] + by[N.TNC_ALGO_SKINNY]
+    assert sum(s.bytes_c64 for s in streamed) > 0.7 * sum(s.bytes_c64 for s in plan.steps if s is not fat)
+    for s in by[N.TNC_ALGO_SKINNY]:
+        assert 2 <= len(s.k_modes) <= 5 and 1 <= len(s.n_modes) <= 7 and s.a.numel >= 1 << 20 and (s.rb is None or s.nb == 1)
+    assert sum(s.bytes_c64 for s in by[N.TNC_ALGO_SKINNY]) > 4 * sum(s.bytes_c64 for s in by[N.TNC_ALGO_STEM])
     assert len(by[N.TNC_ALGO_SIMT]) > 100 and max(s.c.numel for s in by[N.TNC_ALGO_SIMT]) < 1 << 12

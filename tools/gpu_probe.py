@@ -78,7 +78,7 @@ def main():
     by_algo = {}
     for r in rows:
         if r["phase"] == 1:
-            key = {None: r["kind"], 0: "simt", 1: "tc", 2: "stem"}[r.get("algo")]
+            key = {None: r["kind"], 0: "simt", 1: "tc", 2: "stem", 3: "skinny"}[r.get("algo")]
             by_algo[key] = by_algo.get(key, 0.0) + r["ms"]
     print("by class:", {k: round(v, 3) for k, v in by_algo.items()})
     for r in sorted((r for r in rows if r["phase"] == 1), key=lambda r: -r["ms"])[:a.top]:
