@@ -10,14 +10,15 @@
 //   * the right operand is gathered once per CTA into shared memory as B[k][n] and read with
 //     warp-uniform (broadcast) 128-bit loads: 8 FMAs per shared-memory instruction;
 //   * consecutive threads own consecutive rows, rows are numbered by A's lowest address bits, and
-//     the output is written as C[rows][m][n]: every global access is a full 32-byte sector.
+//     the output is written as C[rows][m][n] through a per-warp shared-memory staging buffer, so
+//     that a store instruction covers full 128-byte lines instead of one line per lane.
 //
 // HBM traffic is the algorithmic minimum (A read once, C written once).  fp32 FMA throughput
 // (~70 TFLOP/s) becomes the limit above ~11 flop/byte; steps above ~24 flop/byte go to the
 // tcgen05 path instead.
 #include <algorithm>
 
-#include "tnc_internal.h"
+#include "tc_common.cuh"
 
 namespace tnc {
 
@@ -56,6 +57,9 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const StemParams 
     const int K = 1 << p.kb, N = 1 << p.nb;
     float2* Bs = (float2*)stem_smem;                    // [K][N]
     uint32_t* koff = (uint32_t*)(Bs + (size_t)K * N);   // A offset of contracted index k
+    const uint32_t stage = ((smem_u32(koff + K) + 15u) & ~15u) + (threadIdx.x >> 5) * 4096u;   // this warp's staging buffer
+    const bool staged = NCH >= 2 && p.mb >= 5;           // whole warps only
+    const int lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < K; k += kStemThreads) {
         uint32_t o = 0;
         for (int i = 0; i < p.kb; ++i) o |= ((uint32_t)(k >> i) & 1u) << p.k_a[i];
@@ -129,9 +133,13 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const StemParams 
             if constexpr (NCH == 1) {
                 cp[n0] = acc[0];
             } else {
+                if (staged) {
+                    store_rows_coalesced<NCH / 2>(stage, (const float*)acc, (float*)(cp - (int64_t)lane * N + n0), 2 * (int64_t)N, lane);
+                } else {
 #pragma unroll
-                for (int i = 0; i < NCH; i += 2)
-                    *(float4*)(cp + n0 + i) = make_float4(acc[i].x, acc[i].y, acc[i + 1].x, acc[i + 1].y);
+                    for (int i = 0; i < NCH; i += 2)
+                        *(float4*)(cp + n0 + i) = make_float4(acc[i].x, acc[i].y, acc[i + 1].x, acc[i + 1].y);
+                }
             }
         }
     }
@@ -152,7 +160,7 @@ template <int NCH, int KCH>
 int launch(const StemParams& p, size_t smem, int grid, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        TNC_CUDA(cudaFuncSetAttribute(stem_kernel<NCH, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        TNC_CUDA(cudaFuncSetAttribute(stem_kernel<NCH, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }
     stem_kernel<NCH, KCH><<<grid, kStemThreads, smem, s>>>(p);
@@ -220,7 +228,7 @@ int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, cons
         ++p.n_runs;
         j += len;
     }
-    const size_t smem = ((size_t)8 << (e.n_k + e.n_n)) + ((size_t)4 << e.n_k);
+    const size_t smem = ((size_t)8 << (e.n_k + e.n_n)) + ((size_t)4 << e.n_k) + 16 + (kStemThreads / 32) * 4096;
     const int64_t tiles = ((((int64_t)1 << e.n_m) + kStemThreads - 1) / kStemThreads) * e.nb;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 2 * 4);
     switch (e.n_n) {

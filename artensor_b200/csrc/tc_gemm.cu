@@ -43,6 +43,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #include "tc_gemm.h"
@@ -246,6 +249,294 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackParams p) 
     }
 }
 
+
+// -------------------------------------------------------------------------------------
+// Fast path of the pack kernel (copy / hi-lo split, no B' expansion).  Same tiling idea -- the
+// tile is the union of the lowest destination bits and of the destination bits fed by the lowest
+// source bits, so that both the global reads and the global writes are long contiguous runs --
+// but built for instruction economy: every thread keeps the offsets and shared-memory slots of
+// its 8 elements in registers (no index tables), reads two source-adjacent amplitudes per
+// 16-byte load, writes four destination-adjacent amplitudes per 16/32-byte store, tiles are 2^11
+// amplitudes, the shared-memory tile is double buffered and the next tile's loads are in flight
+// while the current one is written out.  Shared-memory slot of tile element v (destination
+// order): the low nibble of v XOR a fold of its high bits, chosen on the host so that the 16
+// lanes of a half-warp hit 16 different 8-byte bank pairs on the write side AND on the read side.
+constexpr int kPack2TileBits = 11;
+constexpr int kPack2Threads = 256;
+
+struct Pack2Params {
+    const float2* src;
+    void* dst_hi;
+    void* dst_lo;
+    const int32_t* rows;
+    const uint32_t* amax;
+    int32_t rows_mode, rank, tbits, mode, n_outer;
+    int64_t n_tiles;
+    int8_t tile_src_pos[kPack2TileBits];   // source position of tile bit j in SOURCE order
+    int8_t u2v[kPack2TileBits];            // destination-order bit that source-order bit j is
+    int8_t tile_dst_pos[kPack2TileBits];   // destination position of tile bit j in DESTINATION order
+    uint8_t fold[kPack2TileBits];          // nibble XORed into the slot when destination-order bit j is set (j >= 4)
+    int8_t outer_dst_pos[TNC_MAX_BITS], outer_src_pos[TNC_MAX_BITS];
+};
+
+__device__ __forceinline__ uint32_t pack2_slot(const Pack2Params& p, uint32_t v) {
+    uint32_t s = v;
+    for (int j = 4; j < p.tbits; ++j)
+        if ((v >> j) & 1u) s ^= p.fold[j];
+    return s;
+}
+
+__global__ void __launch_bounds__(kPack2Threads, 4) pack2_kernel(const Pack2Params p) {
+    extern __shared__ __align__(16) unsigned char pack2_smem[];
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(pack2_smem);
+    const uint32_t tile = 1u << p.tbits;
+    const uint32_t buf_bytes = tile * 8u;
+    const uint32_t t = threadIdx.x;
+    const uint32_t n_pairs = tile >> 1, n_quads = tile >> 2;
+    // this thread's elements: pairs (source order) t + 256 i, quads (destination order) t + 256 i
+    uint32_t soff[4], doff[2];
+    uint32_t ls[4][2], ss[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t u = 2u * (t + kPack2Threads * i);
+        uint32_t so = 0, v = 0;
+        for (int j = 0; j < p.tbits; ++j) {
+            const uint32_t bit = (u >> j) & 1u;
+            so |= bit << p.tile_src_pos[j];
+            v |= bit << p.u2v[j];
+        }
+        soff[i] = so;
+        ls[i][0] = pack2_slot(p, v) << 3;
+        ls[i][1] = pack2_slot(p, v | (1u << p.u2v[0])) << 3;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const uint32_t v0 = 4u * (t + kPack2Threads * i);
+        uint32_t dofs = 0;
+        for (int j = 0; j < p.tbits; ++j) dofs |= ((v0 >> j) & 1u) << p.tile_dst_pos[j];
+        doff[i] = dofs;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ss[i][e] = pack2_slot(p, v0 + e) << 3;
+    }
+    const int obits = p.rank - p.tbits;
+    const int64_t omask = (((int64_t)1 << obits) - 1);
+    const int lane = t & 31;
+    float sc = 1.f;
+    if (p.mode == PACK_SPLIT_F16) sc = f16_scale(*p.amax);
+
+    auto bases = [&](int64_t tl, int64_t& sb, int64_t& db) {
+        const int64_t blk = tl >> obits;
+        const int64_t o = tl & omask;
+        // lane j contributes outer bit j; OR-reduce the two 32-bit halves of both offsets
+        uint32_t slo = 0, shi = 0, dlo = 0, dhi = 0;
+        if (lane < p.n_outer && ((o >> lane) & 1)) {
+            const int sp = p.outer_src_pos[lane], dp = p.outer_dst_pos[lane];
+            if (sp < 32) slo = 1u << sp; else shi = 1u << (sp - 32);
+            if (dp < 32) dlo = 1u << dp; else dhi = 1u << (dp - 32);
+        }
+        slo = __reduce_or_sync(0xffffffffu, slo);
+        shi = __reduce_or_sync(0xffffffffu, shi);
+        dlo = __reduce_or_sync(0xffffffffu, dlo);
+        dhi = __reduce_or_sync(0xffffffffu, dhi);
+        int64_t row = 0;
+        if (p.rows_mode == TNC_ROWS_IDENTITY) row = blk;
+        else if (p.rows_mode >= 0) row = p.rows[blk];
+        sb = (row << p.rank) + (int64_t)(((uint64_t)shi << 32) | slo);
+        db = (blk << p.rank) + (int64_t)(((uint64_t)dhi << 32) | dlo);
+    };
+
+    float4 r[4];
+    int64_t sb, db;
+    int64_t tl = blockIdx.x;
+    if (tl >= p.n_tiles) return;
+    bases(tl, sb, db);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (t + kPack2Threads * i < n_pairs) r[i] = *(const float4*)(p.src + sb + soff[i]);
+    uint32_t buf = 0;
+    for (;;) {
+        const uint32_t sbuf = sm0 + buf * buf_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (t + kPack2Threads * i < n_pairs) {
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sbuf + ls[i][0]), "f"(r[i].x), "f"(r[i].y) : "memory");
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sbuf + ls[i][1]), "f"(r[i].z), "f"(r[i].w) : "memory");
+            }
+        __syncthreads();
+        const int64_t cur_db = db;
+        const int64_t next = tl + gridDim.x;
+        const bool more = next < p.n_tiles;
+        if (more) {                                   // next tile's loads fly while this one is written out
+            bases(next, sb, db);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (t + kPack2Threads * i < n_pairs) r[i] = *(const float4*)(p.src + sb + soff[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (t + kPack2Threads * i >= n_quads) continue;
+            float2 x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x[e].x), "=f"(x[e].y) : "r"(sbuf + ss[i][e]) : "memory");
+            const int64_t d = cur_db + doff[i];
+            if (p.mode == PACK_COPY) {
+                float4* o = (float4*)((float2*)p.dst_hi + d);
+                o[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+                o[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+            } else if (p.mode == PACK_SPLIT) {
+                float2 h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    h[e] = make_float2(tf32_round(x[e].x), tf32_round(x[e].y));
+                    l[e] = make_float2(tf32_round(x[e].x - h[e].x), tf32_round(x[e].y - h[e].y));
+                }
+                float4* oh = (float4*)((float2*)p.dst_hi + d);
+                float4* ol = (float4*)((float2*)p.dst_lo + d);
+                oh[0] = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+                oh[1] = make_float4(h[2].x, h[2].y, h[3].x, h[3].y);
+                ol[0] = make_float4(l[0].x, l[0].y, l[1].x, l[1].y);
+                ol[1] = make_float4(l[2].x, l[2].y, l[3].x, l[3].y);
+            } else {                                  // PACK_SPLIT_F16
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float xr = x[e].x * sc, xi = x[e].y * sc;
+                    const __half2 hh = __floats2half2_rn(xr, xi);
+                    h[e] = *(const uint32_t*)&hh;
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(xr - hf.x, xi - hf.y);
+                    l[e] = *(const uint32_t*)&ll;
+                }
+                *(uint4*)((__half2*)p.dst_hi + d) = make_uint4(h[0], h[1], h[2], h[3]);
+                if (p.dst_lo) *(uint4*)((__half2*)p.dst_lo + d) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        if (!more) break;
+        tl = next;
+        buf ^= 1u;
+    }
+}
+
+// GF(2): are the n 4-bit vectors linearly independent?
+bool nibbles_independent(const uint8_t* v, int n) {
+    uint8_t basis[4] = {0, 0, 0, 0};
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+        uint8_t x = v[i] & 15;
+        for (int b = 3; b >= 0 && x; --b) {
+            if (!((x >> b) & 1)) continue;
+            if (basis[b]) {
+                x ^= basis[b];
+            } else {
+                basis[b] = x;
+                ++rank;
+                x = 0;
+            }
+        }
+    }
+    return rank == n;
+}
+
+// tile geometry and slot folds of a bit permutation (everything in Pack2Params that does not
+// depend on pointers, rows or mode); cached per permutation: a plan launches the same few
+// permutations for every slice
+void pack2_geometry(const PackDesc& d, Pack2Params& p);
+
+int launch_pack2(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, cudaStream_t s) {
+    static std::mutex mu;
+    static std::map<std::string, Pack2Params> cache;
+    Pack2Params p{};
+    {
+        std::string key((const char*)d.src_pos, (size_t)d.rank);
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            Pack2Params g{};
+            pack2_geometry(d, g);
+            it = cache.emplace(key, g).first;
+        }
+        p = it->second;
+    }
+    p.src = (const float2*)src;
+    p.dst_hi = dst_hi;
+    p.dst_lo = dst_lo;
+    p.rows = d.rows;
+    p.amax = d.amax;
+    p.rows_mode = d.rows_mode;
+    p.rank = d.rank;
+    p.mode = d.mode;
+    p.n_tiles = (int64_t)d.nb << (d.rank - p.tbits);
+    const size_t smem = 2 * ((size_t)8 << p.tbits);
+    const int64_t grid = std::min<int64_t>(p.n_tiles, (int64_t)sm_count() * 4);
+    pack2_kernel<<<(unsigned)grid, kPack2Threads, smem, s>>>(p);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+void pack2_geometry(const PackDesc& d, Pack2Params& p) {
+    const int r = d.rank;
+    const int lo = 5;                              // contiguous run wanted on both sides: 2^5 amplitudes
+    std::vector<int> in_tile(r, 0);
+    for (int i = 0; i < lo; ++i) in_tile[i] = 1;
+    for (int i = 0; i < r; ++i)
+        if (d.src_pos[i] < lo) in_tile[i] = 1;
+    int have = 0;
+    for (int i = 0; i < r; ++i) have += in_tile[i];
+    for (int i = 0; i < r && have < kPack2TileBits; ++i)
+        if (!in_tile[i]) {
+            in_tile[i] = 1;
+            ++have;
+        }
+    std::vector<int> tdst;                          // destination order
+    for (int i = 0; i < r; ++i)
+        if (in_tile[i]) tdst.push_back(i);
+    const int t = (int)tdst.size();
+    std::vector<int> order(t);                      // source order: tile bits sorted by source position
+    for (int j = 0; j < t; ++j) order[j] = j;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return d.src_pos[tdst[x]] < d.src_pos[tdst[y]]; });
+    p.tbits = t;
+    for (int j = 0; j < t; ++j) {
+        p.tile_dst_pos[j] = (int8_t)tdst[j];
+        p.tile_src_pos[j] = d.src_pos[tdst[order[j]]];
+        p.u2v[j] = (int8_t)order[j];
+    }
+    // bank-conflict-free slots: M(e_j) = e_j for j < 4, fold[j] for j >= 4; the images of the four
+    // bits a half-warp walks on the read side (destination-order bits 2..5) and on the write side
+    // (the destination-order bits of source-order bits 1..4) must each be independent
+    std::vector<int> S, L;
+    for (int j = 2; j <= 5 && j < t; ++j) S.push_back(j);
+    for (int j = 1; j <= 4 && j < t; ++j) L.push_back(order[j]);
+    auto image = [&](int j) -> uint8_t { return j < 4 ? (uint8_t)(1u << j) : p.fold[j]; };
+    auto ok = [&]() {
+        uint8_t a[4], b[4];
+        for (size_t i = 0; i < S.size(); ++i) a[i] = image(S[i]);
+        for (size_t i = 0; i < L.size(); ++i) b[i] = image(L[i]);
+        return nibbles_independent(a, (int)S.size()) && nibbles_independent(b, (int)L.size());
+    };
+    for (int j = 4; j < t; ++j) p.fold[j] = (uint8_t)(1u << (j & 3));
+    if (!ok()) {
+        uint32_t rng = 12345u;
+        bool found = false;
+        for (int trial = 0; trial < 200000 && !found; ++trial) {
+            for (int j = 4; j < t; ++j) {
+                rng = rng * 1664525u + 1013904223u;
+                p.fold[j] = (uint8_t)((rng >> 24) & 15u);
+            }
+            found = ok();
+        }
+        if (!found)
+            for (int j = 4; j < t; ++j) p.fold[j] = (uint8_t)(1u << (j & 3));     // correct, merely conflicted
+    }
+    p.n_outer = 0;
+    for (int i = 0; i < r; ++i)
+        if (!in_tile[i]) {
+            p.outer_dst_pos[p.n_outer] = (int8_t)i;
+            p.outer_src_pos[p.n_outer] = d.src_pos[i];
+            ++p.n_outer;
+        }
+}
+
 }  // namespace
 
 int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, cudaStream_t s) {
@@ -257,6 +548,10 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
         set_error("pack: the fp16 modes need the operand's amax word");
         return TNC_ERR_INVALID;
     }
+    static const bool fast = !(getenv("TNC_PACK_FAST") && atoi(getenv("TNC_PACK_FAST")) == 0);
+    if (fast && d.rank >= 8 && d.rank - 8 < 32 &&
+        (d.mode == PACK_COPY || d.mode == PACK_SPLIT || d.mode == PACK_SPLIT_F16))
+        return launch_pack2(d, src, dst_hi, dst_lo, s);
     PackParams p{};
     p.src = (const float2*)src;
     p.dst_hi = (float2*)dst_hi;
@@ -347,7 +642,8 @@ constexpr int BKB = 128;           // bytes per operand row per stage: one 128B-
 constexpr int kMmaPerKb = BKB / 32;   // every tcgen05.mma consumes 32 bytes of K per row (8 tf32 / 16 fp16)
 constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter, each owning half of the columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-9 epilogue
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 192 * 1024;
+constexpr int kStageBytes = kEpiWarps * 4096;   // per-warp staging buffers of the coalesced epilogue stores
 
 // k-blocks accumulated inside tensor memory before the fp32 register add.  Measured on B200
 // (tools/tc_calibrate.py, 3xTF32): coherent shrink of the result per GEMM of -8.6e-8 at 1,
@@ -369,7 +665,7 @@ struct Cfg {
     static constexpr int STAGES = (kSmemBudget / STAGE) > 8 ? 8 : (kSmemBudget / STAGE);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators (chunk double buffer)
     static constexpr int CPT = BN / 2;                            // columns per epilogue thread
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment*/ + 256 /*barriers*/ + kStageBytes;
     static_assert(STAGES >= 2, "need a double buffer");
 };
 
@@ -484,19 +780,44 @@ __device__ __forceinline__ void drain_chunk(uint32_t taddr, float* acc) {
     }
 }
 
-// Stores a thread's CPT finished columns of one output row; fp16 precisions undo the operand scaling.
+// Stores a warp's 32 finished rows x CPT columns (lane = row); fp16 precisions undo the operand
+// scaling.  Whole tiles go through the warp's shared-memory staging buffer so that every global
+// store instruction covers full 128-byte lines (a thread-per-row store touches 32 lines per
+// instruction and caps a large-C step near 1 TB/s); ragged tiles keep the guarded per-row path.
 template <int CPT, bool F16>
-__device__ __forceinline__ void store_row(const GemmArgs& g, float* crow, int col0, const float* acc) {
-    float sa = 1.f, sb = 1.f;
-    if constexpr (F16) {
-        sa = f16_inv_scale(g.amax[0]);
-        sb = f16_inv_scale(g.amax[1]);
+__device__ __forceinline__ void store_tile_rows(const GemmArgs& g, uint32_t stage, int batch, int row0, int col0, float* acc,
+                                                int lane) {
+    float sab = 1.f;
+    if constexpr (F16) sab = f16_inv_scale(g.amax[0]) * f16_inv_scale(g.amax[1]);
+    const bool whole = row0 + 32 <= g.M && col0 + CPT <= g.N && (g.outer_rj == 0 || g.outer_mb >= 5);
+    if (whole) {
+        float* cbase = g.c + c_row(g, batch, row0) * g.ldc + col0;
+        if constexpr (CPT >= 32) {
+#pragma unroll
+            for (int c = 0; c < CPT; c += 32) {
+                if constexpr (F16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c + j] *= sab;
+                }
+                store_rows_coalesced<8>(stage, acc + c, cbase + c, g.ldc, lane);
+            }
+        } else {
+            if constexpr (F16) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) acc[j] *= sab;
+            }
+            store_rows_coalesced<CPT / 4>(stage, acc, cbase, g.ldc, lane);
+        }
+        return;
     }
+    const int row = row0 + lane;
+    if (row >= g.M) return;
+    float* crow = g.c + c_row(g, batch, row) * g.ldc + col0;
 #pragma unroll
     for (int j = 0; j < CPT; j += 4)
         if (col0 + j < g.N) {
             float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            if constexpr (F16) o = make_float4(o.x * sa * sb, o.y * sa * sb, o.z * sa * sb, o.w * sa * sb);
+            if constexpr (F16) o = make_float4(o.x * sab, o.y * sab, o.z * sab, o.w * sab);
             *(float4*)(crow + j) = o;
         }
 }
@@ -640,9 +961,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar(gc & 1u));
             }
-            const int row = t.m0 + q * 32 + lane;
-            const int col0 = t.n0 + half * CPT;
-            if (row < g.M) store_row<CPT, Prec<PREC>::F16>(g, g.c + c_row(g, t.batch, row) * g.ldc + col0, col0, acc);
+            store_tile_rows<CPT, Prec<PREC>::F16>(g, base + C::STAGES * C::STAGE + 256 + (uint32_t)(warp - 2) * 4096u, t.batch,
+                                                  t.m0 + q * 32, t.n0 + half * CPT, acc, lane);
         }
     }
     tc_fence_before();
@@ -673,7 +993,7 @@ struct Cfg2 {
     static constexpr int STAGES = (kSmemBudget / STAGE) > 6 ? 6 : (kSmemBudget / STAGE);
     static constexpr int TMEM_COLS = 512;
     static constexpr int CPT = BN / 2;
-    static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + kStageBytes;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -857,9 +1177,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive_on_cta(tmem_empty_bar(gc & 1u), 0);
             }
-            const int row = (2 * t.m_tile + (int)rank) * BM + q * 32 + lane;
-            const int col0 = t.n0 + half * CPT;
-            if (row < g.M) store_row<CPT, Prec<PREC>::F16>(g, g.c + c_row(g, t.batch, row) * g.ldc + col0, col0, acc);
+            store_tile_rows<CPT, Prec<PREC>::F16>(g, base + C::STAGES * C::STAGE + 256 + (uint32_t)(warp - 2) * 4096u, t.batch,
+                                                  (2 * t.m_tile + (int)rank) * BM + q * 32, t.n0 + half * CPT, acc, lane);
         }
     }
     tc_fence_before();

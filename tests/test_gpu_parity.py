@@ -149,7 +149,7 @@ def test_permute_bits_kernel(dev):
     from artensor_b200 import _native as N
     lib = N.load()
     rng = np.random.RandomState(1)
-    for rank, rows in [(1, 1), (5, 3), (12, 1), (16, 2), (20, 1)]:
+    for rank, rows in [(1, 1), (5, 3), (8, 3), (9, 1), (11, 2), (12, 1), (13, 5), (16, 2), (20, 1), (24, 1)]:
         for trial in range(3):
             perm = rng.permutation(rank)
             src = torch.randn(rows, 1 << rank, dtype=torch.complex64, device=dev)
