@@ -410,8 +410,18 @@ def main():
             ach = st.bytes_c64 / (best_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "traffic": None, "peak_kind": f"copy bandwidth ({pk['source']})"}
-        roofline["kernel"] = {N.TNC_ALGO_TC: f"gemm_2cta_kernel<{precision}>", N.TNC_ALGO_STEM: "stem_kernel", N.TNC_ALGO_SKINNY: "skinny_kernel",
-                              N.TNC_ALGO_SIMT: "simt_einsum_kernel"}[rec.algo]
+        kname = {N.TNC_ALGO_TC: f"gemm_2cta_kernel<{precision}>", N.TNC_ALGO_STEM: "stem_kernel", N.TNC_ALGO_SKINNY: "skinny_kernel",
+                 N.TNC_ALGO_SIMT: "simt_einsum_kernel"}[rec.algo]
+        roofline["kernel"] = kname
+        try:      # DRAM bytes of this kernel on this very step, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                cap = json.load(f).get(kname)
+            if cap and rec.algo == N.TNC_ALGO_TC and (len(st.m_modes), len(st.n_modes), len(st.k_modes)) == (15, 13, 15):
+                roofline["traffic"] = cap["dram_bytes"]
+                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, "
+                                            "profiles/r01_ncu_full_fat.txt); algorithmic bytes of the step: %d" % st.bytes_c64)
+        except (OSError, ValueError):
+            pass
         roofline["step"] = {"index": st.index, "m_bits": len(st.m_modes), "n_bits": len(st.n_modes),
                             "k_bits": len(st.k_modes), "rows": st.nb, "flops": st.flops, "bytes": st.bytes_c64,
                             "ms": best_ms, "share_of_slice": best_ms / slice_ms}

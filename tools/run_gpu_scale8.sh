@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt
+for N in 8 4 2; do
+  timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) \
+      bench.py --gpus $N --steps 4 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+  echo "N=$N rc=$?"; cat gpurun_out/bench_n$N.json; tail -n 2 gpurun_out/bench_n$N.err
+done
