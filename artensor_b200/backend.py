@@ -108,6 +108,7 @@ class PlanOptions:
     # rows of <= 8 outputs leave the tensor-core kernel latency-bound (measured on n53 m20: 1.4-3.0
     # TB/s against 2.9-4.8 TB/s of the fp32 streaming kernel, whose FMA load is light there)
     skinny_min_n: int = 4
+    swap_operands: bool = True
     hoist: bool = True
     tc_precision: str = field(default_factory=lambda: os.environ.get("TNC_TC_PRECISION", "3xf16"))
 
@@ -146,6 +147,39 @@ def stem_eligible(st: Step):
     """Mirror of stem_supported() in csrc/stem.cu: B[k][n] and the k offsets must fit shared memory."""
     k, n = len(st.k_modes), len(st.n_modes)
     return len(st.h_modes) == 0 and k <= 12 and n <= 12 and (8 << (k + n)) + (4 << k) <= 60 * 1024
+
+
+def operand_elems(st: Step):
+    """Amplitudes the step reads from each operand (gathered rows counted)."""
+    ea = (st.nb if st.ra is not None else 1) << st.a.rank
+    eb = (st.nb if st.rb is not None else 1) << st.b.rank
+    return ea, eb
+
+
+def should_swap(st: Step, min_elems=1 << 12):
+    """C = A.B is lowered as C^T = B^T.A^T when the right operand is the larger one: every kernel
+    streams (or packs without expansion) its LEFT operand and keeps the right one small -- the
+    tensor-core lowering even doubles the right operand (B' expansion).  The output layout is the
+    planner's choice anyway, so exchanging the roles costs nothing.  Outer steps keep their order
+    (their row pairs are A-major by construction, contraction.py:180-185)."""
+    if st.kind == "outer" or len(st.h_modes) != 0:
+        return False
+    ea, eb = operand_elems(st)
+    if max(ea, eb) < min_elems:
+        return False
+    return eb > ea or (eb == ea and len(st.n_modes) > len(st.m_modes))
+
+
+def swapped(st: Step):
+    """The same step with the operand roles exchanged (a <-> b, m <-> n, ra <-> rb)."""
+    import copy
+    s = copy.copy(st)
+    s.a, s.b = st.b, st.a
+    s.m_modes, s.n_modes = st.n_modes, st.m_modes
+    s.k_modes, s.k_modes_b = st.k_modes_b, st.k_modes
+    s.ra, s.rb = st.rb, st.ra
+    s.is_swapped = True
+    return s
 
 
 def skinny_eligible(st: Step, precision, min_n=1):
@@ -228,8 +262,11 @@ class ContractionPlan:
 
         pending = []        # (phase, step, A, B, C, algo) in scheme order
         self.step_phase, self.step_algo = [], []
-        for st in self.steps:
-            A, B = bufs[st.i], bufs[st.j]
+        for orig in self.steps:
+            A, B = bufs[orig.i], bufs[orig.j]
+            st = orig
+            if self.options.swap_operands and self.dtype == N.TNC_C64 and should_swap(orig):
+                st, A, B = swapped(orig), B, A
             phase = N.TNC_PHASE_SLICE if (A.dependent or B.dependent) else N.TNC_PHASE_ONCE
             algo = N.TNC_ALGO_SIMT
             if self.dtype == N.TNC_C64:
@@ -257,8 +294,8 @@ class ContractionPlan:
                 # slice-invariant result consumed inside the slice loop (needed by every slice)
                 if not old.is_leaf and old.region == phase:
                     arenas[phase].release(old.rel_offset, old.size)
-            bufs[st.i] = Cb
-            del bufs[st.j]
+            bufs[orig.i] = Cb
+            del bufs[orig.j]
         base[N.TNC_PHASE_ONCE] = 0
         base[N.TNC_PHASE_SLICE] = arenas[N.TNC_PHASE_ONCE].high
         self.workspace_bytes = max(arenas[N.TNC_PHASE_ONCE].high + arenas[N.TNC_PHASE_SLICE].high, ALIGN)

@@ -51,8 +51,10 @@ __device__ __forceinline__ void cfma(float2& acc, const float2 a, const float2 b
 }
 
 // NCH: outputs (complex) a thread produces per pass over its row; KCH: row amplitudes per chunk.
+// Light variants (few accumulators) are compiled for 4 resident CTAs per SM: their rows are short,
+// and the bytes in flight per SM are what bounds them.
 template <int NCH, int KCH>
-__global__ void __launch_bounds__(kStemThreads, 2) stem_kernel(const StemParams p) {
+__global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4 : 2)) stem_kernel(const StemParams p) {
     extern __shared__ __align__(16) unsigned char stem_smem[];
     const int K = 1 << p.kb, N = 1 << p.nb;
     float2* Bs = (float2*)stem_smem;                    // [K][N]
@@ -230,7 +232,7 @@ int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, cons
     }
     const size_t smem = ((size_t)8 << (e.n_k + e.n_n)) + ((size_t)4 << e.n_k) + 16 + (kStemThreads / 32) * 4096;
     const int64_t tiles = ((((int64_t)1 << e.n_m) + kStemThreads - 1) / kStemThreads) * e.nb;
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 2 * 4);
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 4 * 4);
     switch (e.n_n) {
         case 0: return launch_k<1>(p, smem, grid, s);
         case 1: return launch_k<2>(p, smem, grid, s);

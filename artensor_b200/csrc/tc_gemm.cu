@@ -271,6 +271,7 @@ struct Pack2Params {
     const int32_t* rows;
     const uint32_t* amax;
     int32_t rows_mode, rank, tbits, mode, n_outer;
+    int32_t inner_bits, blocked, bn_log2, kb_log2;   // PACK_EXPAND_SPLIT_F16 (see PackDesc)
     int64_t n_tiles;
     int8_t tile_src_pos[kPack2TileBits];   // source position of tile bit j in SOURCE order
     int8_t u2v[kPack2TileBits];            // destination-order bit that source-order bit j is
@@ -344,6 +345,9 @@ __global__ void __launch_bounds__(kPack2Threads, 4) pack2_kernel(const Pack2Para
         sb = (row << p.rank) + (int64_t)(((uint64_t)shi << 32) | slo);
         db = (blk << p.rank) + (int64_t)(((uint64_t)dhi << 32) | dlo);
     };
+    const bool expand = p.mode == PACK_EXPAND_SPLIT_F16;
+    if (expand) sc = f16_scale(*p.amax);
+    const int64_t blk_mask = ((int64_t)1 << p.rank) - 1;
 
     float4 r[4];
     int64_t sb, db;
@@ -397,6 +401,44 @@ __global__ void __launch_bounds__(kPack2Threads, 4) pack2_kernel(const Pack2Para
                 oh[1] = make_float4(h[2].x, h[2].y, h[3].x, h[3].y);
                 ol[0] = make_float4(l[0].x, l[0].y, l[1].x, l[1].y);
                 ol[1] = make_float4(l[2].x, l[2].y, l[3].x, l[3].y);
+            } else if (expand) {
+                // B'[2n + c'][2k + c], fp16: the four amplitudes are four consecutive k of one n, so
+                // each of the two rows (c' = 0, 1) gets one 16-byte store per part
+                const int64_t blk = d >> p.rank, q = d & blk_mask;
+                const int64_t K = (int64_t)1 << p.inner_bits;
+                const int64_t k = q & (K - 1), n = q >> p.inner_bits;
+                int64_t e, second;
+                if (p.blocked) {
+                    const int hb = p.bn_log2 - 1, kbl = p.kb_log2;
+                    const int64_t row = (n & (((int64_t)1 << hb) - 1)) << 1;
+                    e = (k & (((int64_t)1 << kbl) - 1)) +
+                        ((row + ((int64_t)1 << p.bn_log2) * ((k >> kbl) + (K >> kbl) * (n >> hb))) << kbl);
+                    second = (int64_t)1 << kbl;
+                } else {
+                    e = k | (n << (p.inner_bits + 1));
+                    second = K;
+                }
+                uint32_t h0[4], h1[4], l0[4], l1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xr = x[j].x * sc, xi = x[j].y * sc;
+                    const __half hr = __float2half_rn(xr), hi = __float2half_rn(xi);
+                    const __half2 a0 = __halves2half2(hr, __hneg(hi)), a1 = __halves2half2(hi, hr);
+                    h0[j] = *(const uint32_t*)&a0;
+                    h1[j] = *(const uint32_t*)&a1;
+                    const __half lr = __float2half_rn(xr - __half2float(hr)), li = __float2half_rn(xi - __half2float(hi));
+                    const __half2 b0 = __halves2half2(lr, __hneg(li)), b1 = __halves2half2(li, lr);
+                    l0[j] = *(const uint32_t*)&b0;
+                    l1[j] = *(const uint32_t*)&b1;
+                }
+                __half2* hh = (__half2*)p.dst_hi + (blk << (p.rank + 1)) + e;
+                *(uint4*)hh = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+                *(uint4*)(hh + second) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                if (p.dst_lo) {
+                    __half2* hl = (__half2*)p.dst_lo + (blk << (p.rank + 1)) + e;
+                    *(uint4*)hl = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+                    *(uint4*)(hl + second) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+                }
             } else {                                  // PACK_SPLIT_F16
                 uint32_t h[4], l[4];
 #pragma unroll
@@ -466,6 +508,10 @@ int launch_pack2(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo,
     p.rows_mode = d.rows_mode;
     p.rank = d.rank;
     p.mode = d.mode;
+    p.inner_bits = d.inner_bits;
+    p.blocked = d.blocked;
+    p.bn_log2 = d.bn_log2;
+    p.kb_log2 = d.kb_log2 ? d.kb_log2 : 4;
     p.n_tiles = (int64_t)d.nb << (d.rank - p.tbits);
     const size_t smem = 2 * ((size_t)8 << p.tbits);
     const int64_t grid = std::min<int64_t>(p.n_tiles, (int64_t)sm_count() * 4);
@@ -550,7 +596,8 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
     }
     static const bool fast = !(getenv("TNC_PACK_FAST") && atoi(getenv("TNC_PACK_FAST")) == 0);
     if (fast && d.rank >= 8 && d.rank - 8 < 32 &&
-        (d.mode == PACK_COPY || d.mode == PACK_SPLIT || d.mode == PACK_SPLIT_F16))
+        (d.mode == PACK_COPY || d.mode == PACK_SPLIT || d.mode == PACK_SPLIT_F16 ||
+         (d.mode == PACK_EXPAND_SPLIT_F16 && d.inner_bits >= 2)))
         return launch_pack2(d, src, dst_hi, dst_lo, s);
     PackParams p{};
     p.src = (const float2*)src;

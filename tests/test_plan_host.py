@@ -229,3 +229,38 @@ def test_default_options_pick_algorithms_by_intensity():
         assert 2 <= len(s.k_modes) <= 5 and 4 <= len(s.n_modes) <= 7 and s.a.numel >= 1 << 20 and (s.rb is None or s.nb == 1)
     assert sum(s.flops for s in by[N.TNC_ALGO_SKINNY]) > 2 * sum(s.flops for s in by[N.TNC_ALGO_STEM])
     assert len(by[N.TNC_ALGO_SIMT]) > 100 and max(s.c.numel for s in by[N.TNC_ALGO_SIMT]) < 1 << 12
+
+
+def test_operand_swap_keeps_results():
+    """Steps whose right operand is the larger one are lowered with the roles exchanged
+    (C^T = B^T A^T); the emitted records must still compute the reference's einsum, with and
+    without rows on either operand."""
+    from artensor_b200.backend import should_swap
+    rng = np.random.RandomState(4)
+
+    def rnd(*shape):
+        return torch.from_numpy((rng.randn(*shape) + 1j * rng.randn(*shape)).astype(np.complex64))
+
+    # plain, no rows: A rank 5, B rank 13
+    eq = "abcxy,xydefghijklmn->dabecfghijklmn"
+    leaves = {0: rnd(*[2] * 5), 1: rnd(*[2] * 13)}
+    plan = ContractionPlan([((0, 1), eq)], {k: tuple(v.shape) for k, v in leaves.items()}, False, build_native=False)
+    assert should_swap(plan.steps[0])
+    rec = plan.ops[N.TNC_PHASE_ONCE][-1][1] if plan.ops[N.TNC_PHASE_ONCE][-1][0] == "einsum" else plan.ops[N.TNC_PHASE_SLICE][0][1]
+    assert rec.a.rank == 13 and rec.b.rank == 5 and rec.n_m == 11 and rec.n_n == 3     # roles exchanged
+    got = emulate.run_plan(plan, plan.pack_leaves(leaves).numpy(), [0]).reshape(plan.out_shape)
+    want = np.einsum(eq, leaves[0].numpy().astype(np.complex128), leaves[1].numpy().astype(np.complex128))
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+    no_swap = ContractionPlan([((0, 1), eq)], {k: tuple(v.shape) for k, v in leaves.items()}, False, build_native=False,
+                              options=PlanOptions(swap_operands=False))
+    got2 = emulate.run_plan(no_swap, no_swap.pack_leaves(leaves).numpy(), [0]).reshape(no_swap.out_shape)
+    assert np.abs(got2 - want).max() / np.abs(want).max() < 2e-6
+    # sparse, rows on the (larger) right operand only: 6 bitstring rows
+    eq = "abx,Zxcdefghijkl->Zabcdefghijkl"
+    leaves = {0: rnd(2, 2, 2), 1: rnd(6, *[2] * 11)}
+    step = ((0, 1), eq, [[torch.tensor([0])], [torch.arange(6)]])      # contraction.py:249-254
+    plan = ContractionPlan([step], {k: tuple(v.shape) for k, v in leaves.items()}, True, build_native=False)
+    assert should_swap(plan.steps[0])
+    got = emulate.run_plan(plan, plan.pack_leaves(leaves).numpy(), [0]).reshape(plan.out_shape)
+    want = np.einsum(eq, leaves[0].numpy().astype(np.complex128), leaves[1].numpy().astype(np.complex128))
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
