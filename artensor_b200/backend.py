@@ -188,7 +188,9 @@ def skinny_eligible(st: Step, precision, min_n=1):
     k, n, m = len(st.k_modes), len(st.n_modes), len(st.m_modes)
     if precision == "3xtf32" or len(st.h_modes) != 0:
         return False
-    if not (2 <= k <= 5 and max(1, min_n) <= n <= 7 and m >= 7):
+    # rows of K >= 32 carry enough bytes on the A side to run one output bit shorter
+    low = max(1, min_n - 1) if k >= 5 else max(1, min_n)
+    if not (2 <= k <= 6 and low <= n <= 7 and m >= 7) or (k == 6 and n > 6):
         return False
     if st.rb is not None and st.nb != 1:
         return False

@@ -1,6 +1,6 @@
 // Streaming tensor-core kernel for the "stem" steps of a contraction tree
 // (artensor/contraction.py:70, :147-190 call sites): a huge left operand meets a small right
-// operand (K <= 32, N <= 128 complex), 4..32 flop per byte.  Such a step is bound by HBM bandwidth
+// operand (K <= 64, N <= 128 complex), 4..32 flop per byte.  Such a step is bound by HBM bandwidth
 // as long as the math is cheap: on the CUDA cores it is not (stem.cu turns FMA-bound above
 // ~8 flop/byte), on the tensor cores it is.  So this kernel streams A and C exactly once, like
 // stem.cu, but multiplies on tcgen05:
@@ -35,7 +35,6 @@ namespace tnc {
 namespace {
 
 constexpr int kProducerWarps = 8;      // two groups of 4 warps, alternating tiles
-constexpr int kEpilogueWarp0 = 8;      // warps 8..11: TMEM lane quarter = warp & 3
 constexpr int kMmaWarp = 12;
 constexpr int kSkinnyThreads = 13 * 32;
 constexpr int kTileRows = 128;
@@ -63,6 +62,7 @@ struct SkinnyParams {
     uint32_t run_mask[TNC_MAX_BITS];
     int8_t run_src[TNC_MAX_BITS], run_dst[TNC_MAX_BITS];
     int8_t k_a[8], k_b[8], n_b[8];
+    int32_t k_blocks;              // 1, or 2 for K = 64
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -73,9 +73,14 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     return *(const uint32_t*)&h;
 }
 
-// KC = complex k per row (1 << kb), R = 128-row sub-tiles per slot, PANELS = 2 (hi + lo) or 1 (hi only)
-template <int KC, int R, int PANELS>
+// KC = complex k per row and k-block, KB = k-blocks (K = KC * KB; KB == 2 only with KC == 32: the
+// two producer groups then convert the two k-blocks of the SAME tile, each with its own row scale,
+// into two accumulators that the epilogue adds in fp32 registers, round-to-nearest), R = 128-row
+// sub-tiles per slot, PANELS = 2 (hi + lo) or 1 (hi only)
+template <int KC, int KB, int R, int PANELS>
 __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyParams p) {
+    static_assert(KB == 1 || (KB == 2 && KC == 32 && R == 1), "two k-blocks: full rows, one sub-tile");
+    constexpr int SUBS = KB * R;                          // accumulators (and row-scale vectors) per slot
     constexpr int PREC = PANELS == 2 ? TNC_TC_3XF16 : TNC_TC_F16;
     constexpr int KSUB = KC * 4 < 32 ? 32 : KC * 4;       // bytes of one sub-tile's K run inside a 128-byte row
     constexpr int CHUNKS = (KC + 3) / 4;                  // 16-byte chunks a row really carries
@@ -85,13 +90,13 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* aligned = skinny_smem_raw + (base - raw);
     // layout: B' hi | B' lo | slots x (A hi | A lo) | slots x row scales | 4 staging buffers | barriers | misc
-    const uint32_t b_bytes = (uint32_t)p.n_mma * 128u;                    // multiple of 2048
-    const uint32_t b_hi = base, b_lo = base + b_bytes;
-    const uint32_t a0 = base + 2u * b_bytes;
-    const uint32_t slot_bytes = PANELS * kTileBytes;
-    const uint32_t scales_off = 2u * b_bytes + (uint32_t)p.slots * slot_bytes;
-    float* row_scale = (float*)(aligned + scales_off);                    // [slots][R][128]
-    const uint32_t stage0 = base + scales_off + (uint32_t)p.slots * (R * 512u); // 4 x 4 KB
+    const uint32_t b_bytes = (uint32_t)p.n_mma * 128u;                    // one part of one k-block; multiple of 2048
+    const uint32_t b_hi = base, b_lo = base + b_bytes;                    // k-block kb: + kb * 2 * b_bytes
+    const uint32_t a0 = base + KB * 2u * b_bytes;
+    const uint32_t slot_bytes = KB * PANELS * kTileBytes;                 // k-block kb: + kb * PANELS * kTileBytes
+    const uint32_t scales_off = KB * 2u * b_bytes + (uint32_t)p.slots * slot_bytes;
+    float* row_scale = (float*)(aligned + scales_off);                    // [slots][SUBS][128]
+    const uint32_t stage0 = base + scales_off + (uint32_t)p.slots * (SUBS * 512u); // 4 x 4 KB
     const uint32_t bars = stage0 + 4u * 4096u;
     uint32_t* misc = (uint32_t*)(aligned + (bars - base) + 3 * kMaxSlots * 8);   // [0] TMEM base, [1] amax(B) bits
     uint32_t* koff = misc + 4;                                            // [KC] A offset of contracted index k
@@ -100,12 +105,12 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     auto free_bar = [&](int s) { return bars + 8u * (2 * kMaxSlots + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int K = KC, N = 1 << p.nb;
+    const int K = KC * KB, N = 1 << p.nb;
 
     // ---------------------------------------------------------------- set-up (all threads)
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.slots; ++s) {
-            mbar_init(full_bar(s), 128);
+            mbar_init(full_bar(s), 128 * KB);
             mbar_init(done_bar(s), 1);
             mbar_init(free_bar(s), 4);
         }
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
-        uint32_t cols = (uint32_t)(p.slots * R * p.n_mma);
+        uint32_t cols = (uint32_t)(p.slots * SUBS * p.n_mma);
         cols = cols < 32u ? 32u : cols;                                   // power of two by construction
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(misc)), "r"(cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     }
     // zero B' and every A slot once: the padding (rows >= 2N, columns >= 2K) is never written again
     {
-        const uint32_t total16 = (2u * b_bytes + (uint32_t)p.slots * slot_bytes) >> 4;
+        const uint32_t total16 = (KB * 2u * b_bytes + (uint32_t)p.slots * slot_bytes) >> 4;
         for (uint32_t i = threadIdx.x; i < total16; i += kSkinnyThreads) sts128(base + (i << 4), 0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -157,17 +162,18 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             const __half hr = __float2half_rn(xr), hi = __float2half_rn(xi);
             // B'[2n][2k] = Br, B'[2n][2k+1] = -Bi, B'[2n+1][2k] = Bi, B'[2n+1][2k+1] = Br
             // element (row, col) lives at row * 128 + ((col >> 3) ^ (row & 7)) * 16 + (col & 7) * 2
-            const uint32_t col = 2u * k, r0 = 2u * n, r1 = 2u * n + 1u;
+            const uint32_t col = 2u * (k & (KC - 1)), r0 = 2u * n, r1 = 2u * n + 1u;
+            const uint32_t kbo = (uint32_t)(k / KC) * 2u * b_bytes;       // this k's k-block
             const uint32_t off0 = r0 * 128u + ((((col >> 3) ^ (r0 & 7u)) << 4) | ((col & 7u) << 1));
             const uint32_t off1 = r1 * 128u + ((((col >> 3) ^ (r1 & 7u)) << 4) | ((col & 7u) << 1));
             const __half2 v0 = __halves2half2(hr, __hneg(hi)), v1 = __halves2half2(hi, hr);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_hi + off0), "r"(*(const uint32_t*)&v0) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_hi + off1), "r"(*(const uint32_t*)&v1) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_hi + kbo + off0), "r"(*(const uint32_t*)&v0) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_hi + kbo + off1), "r"(*(const uint32_t*)&v1) : "memory");
             if constexpr (PANELS == 2) {
                 const __half lr = __float2half_rn(xr - __half2float(hr)), li = __float2half_rn(xi - __half2float(hi));
                 const __half2 w0 = __halves2half2(lr, __hneg(li)), w1 = __halves2half2(li, lr);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_lo + off0), "r"(*(const uint32_t*)&w0) : "memory");
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_lo + off1), "r"(*(const uint32_t*)&w1) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_lo + kbo + off0), "r"(*(const uint32_t*)&w0) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(b_lo + kbo + off1), "r"(*(const uint32_t*)&w1) : "memory");
             }
         }
     }
@@ -184,7 +190,9 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
         // ------------------------------------------------------------ producers
         const int group = warp >> 2;
         const int row = ((warp & 3) << 5) | lane;                         // row inside the tile = TMEM lane
-        for (int64_t j = group;; j += 2) {
+        // KB == 1: the groups alternate tiles; KB == 2: group g converts k-block g of every tile
+        const int kb_mine = KB == 2 ? group : 0;
+        for (int64_t j = (KB == 2 ? 0 : group);; j += (KB == 2 ? 1 : 2)) {
             const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
             if (tile >= p.tiles) break;
             const int slot = (int)(j % p.slots);
@@ -203,19 +211,19 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                 if (KC >= 2 && p.a_vec) {
 #pragma unroll
                     for (int k = 0; k < KC; k += 2) {
-                        const float4 x = __ldg((const float4*)(ap + koff[k]));
+                        const float4 x = __ldg((const float4*)(ap + koff[kb_mine * KC + k]));
                         av[i][k] = make_float2(x.x, x.y);
                         av[i][k + 1] = make_float2(x.z, x.w);
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) av[i][k] = __ldg(ap + koff[k]);
+                    for (int k = 0; k < KC; ++k) av[i][k] = __ldg(ap + koff[kb_mine * KC + k]);
                 }
             }
             // the slot (shared memory tile, scales, TMEM accumulators) is free once the epilogue of
             // its previous tile is done
             mbar_wait(free_bar(slot), (use & 1u) ^ 1u);
-            const uint32_t ahi = a0 + (uint32_t)slot * slot_bytes + (uint32_t)row * 128u;
+            const uint32_t ahi = a0 + (uint32_t)slot * slot_bytes + (uint32_t)kb_mine * (PANELS * kTileBytes) + (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
             for (int i = 0; i < R; ++i) {
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                     sts128(ahi + off, h[0], h[1], h[2], h[3]);
                     if constexpr (PANELS == 2) sts128(ahi + kTileBytes + off, l[0], l[1], l[2], l[3]);
                 }
-                row_scale[(slot * R + i) * 128 + row] = f16_inv_scale(mbits);
+                row_scale[(slot * SUBS + kb_mine * R + i) * 128 + row] = f16_inv_scale(mbits);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full_bar(slot));
@@ -264,23 +272,27 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                 const uint32_t use = (uint32_t)(j / p.slots);
                 mbar_wait(full_bar(slot), use & 1u);
                 tc_fence_after();
-                const uint64_t da_hi = umma_desc(a0 + (uint32_t)slot * slot_bytes);
-                const uint64_t da_lo = umma_desc(a0 + (uint32_t)slot * slot_bytes + kTileBytes);
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    const uint32_t tacc = tmem + (uint32_t)((slot * R + i) * p.n_mma);
-                    const uint64_t ah = da_hi + i * (KSUB / 16), al = da_lo + i * (KSUB / 16);   // K offset of sub-tile i
-                    uint32_t acc = 0;
-                    if constexpr (PANELS == 2) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint32_t abase = a0 + (uint32_t)slot * slot_bytes + (uint32_t)kb * (PANELS * kTileBytes);
+                    const uint64_t da_hi = umma_desc(abase), da_lo = umma_desc(abase + kTileBytes);
+                    const uint64_t bh = db_hi + kb * ((2u * b_bytes) >> 4), bl = db_lo + kb * ((2u * b_bytes) >> 4);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const uint32_t tacc = tmem + (uint32_t)((slot * SUBS + kb * R + i) * p.n_mma);
+                        const uint64_t ah = da_hi + i * (KSUB / 16), al = da_lo + i * (KSUB / 16);   // K offset of sub-tile i
+                        uint32_t acc = 0;
+                        if constexpr (PANELS == 2) {
+                            for (int s = 0; s < p.k_steps; ++s) {
+                                umma<PREC, 1>(tacc, al + 2 * s, bh + 2 * s, idesc, acc);
+                                acc = 1;
+                            }
+                            for (int s = 0; s < p.k_steps; ++s) umma<PREC, 1>(tacc, ah + 2 * s, bl + 2 * s, idesc, 1);
+                        }
                         for (int s = 0; s < p.k_steps; ++s) {
-                            umma<PREC, 1>(tacc, al + 2 * s, db_hi + 2 * s, idesc, acc);
+                            umma<PREC, 1>(tacc, ah + 2 * s, bh + 2 * s, idesc, acc);
                             acc = 1;
                         }
-                        for (int s = 0; s < p.k_steps; ++s) umma<PREC, 1>(tacc, ah + 2 * s, db_lo + 2 * s, idesc, 1);
-                    }
-                    for (int s = 0; s < p.k_steps; ++s) {
-                        umma<PREC, 1>(tacc, ah + 2 * s, db_hi + 2 * s, idesc, acc);
-                        acc = 1;
                     }
                 }
                 umma_commit(done_bar(slot));
@@ -303,16 +315,22 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             tc_fence_after();
 #pragma unroll 1
             for (int i = 0; i < R; ++i) {
-                const float s = row_scale[(slot * R + i) * 128 + q * 32 + lane] * b_inv;
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((slot * R + i) * p.n_mma);
+                const float s = row_scale[(slot * SUBS + i) * 128 + q * 32 + lane] * b_inv;
+                float s1 = 0.f;                                           // second k-block's scale (KB == 2)
+                if constexpr (KB == 2) s1 = row_scale[(slot * SUBS + 1) * 128 + q * 32 + lane] * b_inv;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((slot * SUBS + i) * p.n_mma);
                 // C[rows][m][n]: the sub-tile's rows are consecutive, n_real floats each
                 float* cwarp = (float*)p.c + (((tile * R + i) << 7) + q * 32) * (int64_t)n_real;
                 const bool last_sub = i == R - 1;
                 if (n_real >= 32) {
                     for (int c0 = 0; c0 < n_real; c0 += 32) {
-                        uint32_t v[32];
+                        uint32_t v[32], w[KB == 2 ? 32 : 1];
                         tmem_ld16(taddr + c0, v);
                         tmem_ld16(taddr + c0 + 16, v + 16);
+                        if constexpr (KB == 2) {
+                            tmem_ld16(taddr + p.n_mma + c0, w);
+                            tmem_ld16(taddr + p.n_mma + c0 + 16, w + 16);
+                        }
                         tmem_ld_wait();
                         if (last_sub && c0 + 32 >= n_real) {              // last read of the slot's accumulators: release it
                             tc_fence_before();
@@ -322,14 +340,16 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                         float o[32];
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
-                            const float y = __uint_as_float(v[x]) * s;
+                            float y = __uint_as_float(v[x]) * s;
+                            if constexpr (KB == 2) y = fmaf(__uint_as_float(w[x]), s1, y);
                             o[x] = fmaf(y, p.debias, y);
                         }
                         store_rows_coalesced<8>(stage, o, cwarp + c0, n_real, lane);
                     }
                 } else {
-                    uint32_t v[16];
+                    uint32_t v[16], w[KB == 2 ? 16 : 1];
                     tmem_ld16(taddr, v);
+                    if constexpr (KB == 2) tmem_ld16(taddr + p.n_mma, w);
                     tmem_ld_wait();
                     if (last_sub) {
                         tc_fence_before();
@@ -339,7 +359,8 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                     float o[16];
 #pragma unroll
                     for (int x = 0; x < 16; ++x) {
-                        const float y = __uint_as_float(v[x]) * s;
+                        float y = __uint_as_float(v[x]) * s;
+                        if constexpr (KB == 2) y = fmaf(__uint_as_float(w[x]), s1, y);
                         o[x] = fmaf(y, p.debias, y);
                     }
                     if (n_real == 16) store_rows_coalesced<4>(stage, o, cwarp, n_real, lane);
@@ -352,7 +373,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {
-        uint32_t cols = (uint32_t)(p.slots * R * p.n_mma);
+        uint32_t cols = (uint32_t)(p.slots * SUBS * p.n_mma);
         cols = cols < 32u ? 32u : cols;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
     }
@@ -369,14 +390,15 @@ int sm_count() {
     return n;
 }
 
-template <int KC, int R, int PANELS>
+template <int KC, int KB, int R, int PANELS>
 int launch(const SkinnyParams& p, size_t smem, int grid, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[kMaxDevices] = {};       // the attribute is per device
+    bool& configured = configured_on[current_device()];
     if (!configured) {
-        TNC_CUDA(cudaFuncSetAttribute(skinny_kernel<KC, R, PANELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TNC_CUDA(cudaFuncSetAttribute(skinny_kernel<KC, KB, R, PANELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    skinny_kernel<KC, R, PANELS><<<grid, kSkinnyThreads, smem, s>>>(p);
+    skinny_kernel<KC, KB, R, PANELS><<<grid, kSkinnyThreads, smem, s>>>(p);
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }
@@ -384,12 +406,12 @@ int launch(const SkinnyParams& p, size_t smem, int grid, cudaStream_t s) {
 template <int KC, int PANELS>
 int launch_r(const SkinnyParams& p, size_t smem, int grid, cudaStream_t s) {
     if constexpr (KC <= 8) {
-        if (p.sub == 4) return launch<KC, 4, PANELS>(p, smem, grid, s);
+        if (p.sub == 4) return launch<KC, 1, 4, PANELS>(p, smem, grid, s);
     }
     if constexpr (KC <= 16) {
-        if (p.sub == 2) return launch<KC, 2, PANELS>(p, smem, grid, s);
+        if (p.sub == 2) return launch<KC, 1, 2, PANELS>(p, smem, grid, s);
     }
-    return launch<KC, 1, PANELS>(p, smem, grid, s);
+    return launch<KC, 1, 1, PANELS>(p, smem, grid, s);
 }
 
 template <int PANELS>
@@ -398,7 +420,8 @@ int launch_k(const SkinnyParams& p, size_t smem, int grid, cudaStream_t s) {
         case 2: return launch_r<4, PANELS>(p, smem, grid, s);
         case 3: return launch_r<8, PANELS>(p, smem, grid, s);
         case 4: return launch_r<16, PANELS>(p, smem, grid, s);
-        default: return launch_r<32, PANELS>(p, smem, grid, s);
+        case 5: return launch_r<32, PANELS>(p, smem, grid, s);
+        default: return launch<32, 2, 1, PANELS>(p, smem, grid, s);
     }
 }
 
@@ -407,7 +430,8 @@ int launch_k(const SkinnyParams& p, size_t smem, int grid, cudaStream_t s) {
 bool skinny_supported(const tnc_einsum& e, int dtype, int precision) {
     if (dtype != TNC_C64 || e.n_h != 0) return false;
     if (precision != TNC_TC_3XF16 && precision != TNC_TC_F16) return false;
-    if (e.n_k < 2 || e.n_k > 5 || e.n_n < 1 || e.n_n > 7 || e.n_m < 7) return false;
+    if (e.n_k < 2 || e.n_k > 6 || e.n_n < 1 || e.n_n > 7 || e.n_m < 7) return false;
+    if (e.n_k == 6 && e.n_n > 6) return false;                           // two k-blocks of B' and two slots must fit shared memory
     if (e.rows_b != TNC_ROWS_NONE && e.nb != 1) return false;            // one right operand for the whole launch
     if (e.rows_a == TNC_ROWS_NONE && e.nb != 1) return false;
     for (int i = 0; i < e.n_n; ++i)
@@ -456,18 +480,21 @@ int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void*
     }
     const int n_real = 2 << e.n_n, k_real = 2 << e.n_k;
     p.n_mma = std::max(16, n_real);
-    p.k_steps = std::max(1, k_real / 16);
+    p.k_blocks = e.n_k == 6 ? 2 : 1;
+    p.k_steps = std::max(1, (k_real / p.k_blocks) / 16);
     // rows per producer thread: ~256 bytes of loads in flight, and >= 2 slots of accumulators in TMEM
     p.sub = std::min(e.n_k <= 3 ? 4 : e.n_k == 4 ? 2 : 1, 256 / p.n_mma);
     while (p.sub > 1 && e.n_m < 7 + (p.sub == 4 ? 2 : 1)) p.sub >>= 1;
-    p.slots = std::min(kMaxSlots, 512 / (p.sub * p.n_mma));
+    p.slots = std::min(kMaxSlots, 512 / (p.sub * p.k_blocks * p.n_mma));
+    if (p.k_blocks == 2) p.slots = 2;                                    // 64 KB of A per slot
     // mean of the accumulator's round-toward-zero bias, by MMAs per product (tools/tc_calibrate.py)
     p.debias = p.k_steps >= 4 ? 8.6e-8f : p.k_steps == 2 ? 5.4e-8f : 3.6e-8f;
     if (precision == TNC_TC_F16) p.debias = 0.f;
     p.tiles = (((int64_t)e.nb << e.n_m) >> 7) / p.sub;
     const int panels = precision == TNC_TC_F16 ? 1 : 2;
-    const size_t smem = 1024 + 2 * (size_t)p.n_mma * 128 + (size_t)p.slots * panels * kTileBytes + (size_t)p.slots * p.sub * 512 +
-                        4 * 4096 + 3 * kMaxSlots * 8 + 16 + 32 * 4 + 64;
+    const size_t smem = 1024 + p.k_blocks * 2 * (size_t)p.n_mma * 128 + (size_t)p.slots * p.k_blocks * panels * kTileBytes +
+                        (size_t)p.slots * p.sub * p.k_blocks * 512 +
+                        4 * 4096 + 3 * kMaxSlots * 8 + 16 + 64 * 4 + 64;
     const int grid = (int)std::min<int64_t>(p.tiles, sm_count());
     return panels == 2 ? launch_k<2>(p, smem, grid, s) : launch_k<1>(p, smem, grid, s);
 }

@@ -160,7 +160,8 @@ int sm_count() {
 
 template <int NCH, int KCH>
 int launch(const StemParams& p, size_t smem, int grid, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[kMaxDevices] = {};       // the attribute is per device
+    bool& configured = configured_on[current_device()];
     if (!configured) {
         TNC_CUDA(cudaFuncSetAttribute(stem_kernel<NCH, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;

@@ -388,6 +388,13 @@ __global__ void __launch_bounds__(kPack2Threads, 4) pack2_kernel(const Pack2Para
                 float4* o = (float4*)((float2*)p.dst_hi + d);
                 o[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
                 o[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+            } else if (p.mode == PACK_ACCUM) {
+                float4* o = (float4*)((float2*)p.dst_hi + d);
+                float4 c0 = o[0], c1 = o[1];
+                c0.x += x[0].x, c0.y += x[0].y, c0.z += x[1].x, c0.w += x[1].y;
+                c1.x += x[2].x, c1.y += x[2].y, c1.z += x[3].x, c1.w += x[3].y;
+                o[0] = c0;
+                o[1] = c1;
             } else if (p.mode == PACK_SPLIT) {
                 float2 h[4], l[4];
 #pragma unroll
@@ -596,9 +603,13 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
     }
     static const bool fast = !(getenv("TNC_PACK_FAST") && atoi(getenv("TNC_PACK_FAST")) == 0);
     if (fast && d.rank >= 8 && d.rank - 8 < 32 &&
-        (d.mode == PACK_COPY || d.mode == PACK_SPLIT || d.mode == PACK_SPLIT_F16 ||
+        (d.mode == PACK_COPY || d.mode == PACK_SPLIT || d.mode == PACK_SPLIT_F16 || d.mode == PACK_ACCUM ||
          (d.mode == PACK_EXPAND_SPLIT_F16 && d.inner_bits >= 2)))
         return launch_pack2(d, src, dst_hi, dst_lo, s);
+    if (d.mode == PACK_ACCUM) {
+        set_error("pack: the accumulate mode needs rank >= 8 (got %d)", d.rank);
+        return TNC_ERR_UNSUPPORTED;
+    }
     PackParams p{};
     p.src = (const float2*)src;
     p.dst_hi = (float2*)dst_hi;
@@ -1277,7 +1288,8 @@ int make_map(CUtensorMap* map, void* addr, int elem, int64_t d0, int64_t d1, int
 
 template <int BN, int PREC>
 int launch_gemm(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[kMaxDevices] = {};       // the attribute is per device
+    bool& configured = configured_on[current_device()];
     if (!configured) {
         TNC_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, PREC>::SMEM));
         configured = true;
@@ -1300,7 +1312,8 @@ int launch_gemm_bn(int bn, const CUtensorMap* maps, const GemmArgs& g, int64_t g
 
 template <int PREC>
 int launch_gemm_2cta(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_on[kMaxDevices] = {};       // the attribute is per device
+    bool& configured = configured_on[current_device()];
     if (!configured) {
         TNC_CUDA(cudaFuncSetAttribute(gemm_2cta_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<PREC>::SMEM));
         configured = true;

@@ -26,7 +26,8 @@ void tc_gemm_destroy(TcGemmOp* op);
 // ---------------------------------------------------------------- pack (bit-permutation) kernel
 // dst[b][q] = f(src[row(b)][p]) where bit i of q is bit src_pos[i] of p; tiled through shared
 // memory so that both the global reads and the global writes are contiguous runs.
-enum PackMode { PACK_COPY = 0, PACK_SPLIT = 1, PACK_EXPAND_SPLIT = 2, PACK_SPLIT_F16 = 3, PACK_EXPAND_SPLIT_F16 = 4 };
+enum PackMode { PACK_COPY = 0, PACK_SPLIT = 1, PACK_EXPAND_SPLIT = 2, PACK_SPLIT_F16 = 3, PACK_EXPAND_SPLIT_F16 = 4,
+                PACK_ACCUM = 5 /* dst += permuted src (fast kernel only: rank >= 8) */ };
 struct PackDesc {
     int32_t rank;                 // bits per block (source and destination)
     int32_t nb;                   // destination blocks

@@ -467,13 +467,23 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
             return launch_permute(p, plan->elem_bytes(), st);
         }
         case OP_ACCUM: {
+            plan->last_launches += 1;
+            if (plan->dtype == TNC_C64 && op.a.src.rank >= 8 && op.a.src.rank < 40) {
+                // large results: the tiled permutation kernel in read-add-write mode
+                PackDesc d{};
+                d.rank = op.a.src.rank;
+                d.nb = op.a.src.rows;
+                d.rows_mode = TNC_ROWS_IDENTITY;
+                d.mode = PACK_ACCUM;
+                for (int i = 0; i < d.rank; ++i) d.src_pos[op.a.out_pos[i]] = (int8_t)i;
+                return launch_pack(d, ws + op.a.src.offset, accum_out, nullptr, st);
+            }
             AccumParams p{};
             p.src = ws + op.a.src.offset;
             p.out = accum_out;
             p.rank = op.a.src.rank;
             p.rows = op.a.src.rows;
             memcpy(p.out_pos, op.a.out_pos, sizeof(p.out_pos));
-            plan->last_launches += 1;
             return launch_accum(p, plan->dtype, st);
         }
     }

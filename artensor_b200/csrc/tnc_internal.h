@@ -10,6 +10,13 @@
 namespace tnc {
 
 void set_error(const char* fmt, ...);
+
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 int cuda_fail(cudaError_t e, const char* what);
 
 #define TNC_CUDA(call)                                              \

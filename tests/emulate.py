@@ -53,7 +53,7 @@ def run_plan(plan, leaf_blob, slice_ids):
                 assert E.n_k >= 1 and E.n_n >= 1 and E.n_h == 0
             if E.algo == N.TNC_ALGO_SKINNY:
                 assert sorted(E.n_c[i] for i in range(E.n_n)) == list(range(E.n_n)) and E.n_h == 0
-                assert 2 <= E.n_k <= 5 and 1 <= E.n_n <= 7 and E.n_m >= 7
+                assert 2 <= E.n_k <= 6 and 1 <= E.n_n <= 7 and E.n_m >= 7 and not (E.n_k == 6 and E.n_n > 6)
                 assert E.rows_b == N.TNC_ROWS_NONE or E.nb == 1
             if E.algo == N.TNC_ALGO_STEM:
                 assert sorted(E.n_c[i] for i in range(E.n_n)) == list(range(E.n_n)) and E.n_h == 0

@@ -292,9 +292,9 @@ def test_stem_single_step_matches_fp64_einsum(dev, shape):
     assert np.abs(got - want).max() / rms < 2e-6, f"m={m} n={n} k={k}"
 
 
-# streaming tensor-core kernel: 2 <= k <= 5, 1 <= n <= 7, m >= 7
+# streaming tensor-core kernel: 2 <= k <= 6, 1 <= n <= 7 (<= 6 for k = 6), m >= 7
 SKINNY_SHAPES = [(7, 1, 2), (8, 3, 3), (9, 5, 5), (10, 7, 4), (12, 2, 5), (13, 6, 2), (9, 4, 3), (14, 7, 5), (16, 5, 4),
-                 (11, 7, 2), (15, 1, 5)]
+                 (11, 7, 2), (15, 1, 5), (9, 5, 6), (12, 3, 6), (14, 6, 6), (8, 1, 6)]
 
 
 @pytest.mark.parametrize("precision,tol", [("3xf16", 2e-6), ("f16", 2e-3)])
