@@ -16,7 +16,7 @@
 //     For short rows (K < 32) a thread owns R rows 128 apart, so that it always has ~256 bytes of
 //     loads in flight: the R sub-tiles sit side by side along the K axis of the same 128-byte
 //     swizzled rows, and the MMA of sub-tile i simply starts its A descriptor i * K bytes in;
-//   * one thread issues the 3 x K/16 MMAs of every 128-row sub-tile (lo*hi + hi*lo + hi*hi, or hi*hi
+//   * one thread of the producer group issues the 3 x K/16 MMAs of every 128-row sub-tile (lo*hi + hi*lo + hi*hi, or hi*hi
 //     alone in the complex-half mode) into the slot's accumulator in tensor memory;
 //   * epilogue warps read the accumulator (tcgen05.ld), undo the row and operand scales, and write
 //     C[rows][m][n] through a shared-memory staging buffer so that every global store instruction
@@ -34,9 +34,10 @@ namespace tnc {
 
 namespace {
 
-constexpr int kProducerWarps = 8;      // two groups of 4 warps, alternating tiles
-constexpr int kMmaWarp = 12;
-constexpr int kSkinnyThreads = 13 * 32;
+constexpr int kGroups = 3;             // producer groups of 4 warps, taking tiles round-robin
+constexpr int kProducerWarps = 4 * kGroups;
+constexpr int kSkinnyThreads = (kProducerWarps + 4) * 32;   // + 4 epilogue warps (TMEM lane quarter = warp & 3); 16 warps: 128 registers each
+constexpr int kAllocWarp = 0;          // owns the TMEM allocation
 constexpr int kTileRows = 128;
 constexpr int kTileBytes = kTileRows * 128;      // one K-major tile: 128 rows x 128 bytes
 constexpr int kMaxSlots = 4;
@@ -63,6 +64,7 @@ struct SkinnyParams {
     int8_t run_src[TNC_MAX_BITS], run_dst[TNC_MAX_BITS];
     int8_t k_a[8], k_b[8], n_b[8];
     int32_t k_blocks;              // 1, or 2 for K = 64
+    int32_t groups;                // active producer groups (<= kGroups, <= slots)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
         misc[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kMmaWarp) {
+    if (warp == kAllocWarp) {
         uint32_t cols = (uint32_t)(p.slots * SUBS * p.n_mma);
         cols = cols < 32u ? 32u : cols;                                   // power of two by construction
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(misc)), "r"(cols) : "memory");
@@ -186,15 +188,60 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     // a tile = R sub-tiles of 128 consecutive rows; mb >= 7 + log2(R) (checked by the launcher)
     const int64_t tiles_per_batch = ((int64_t)1 << (p.mb - 7)) / R;
 
+    // the MMAs of one tile: every sub-tile / k-block into its own accumulator of the slot
+    const uint32_t idesc = umma_idesc<PREC>(kTileRows, p.n_mma);
+    const uint64_t db_hi = umma_desc(b_hi), db_lo = umma_desc(b_lo);
+    auto issue_mma = [&](int slot, uint32_t use) {
+        mbar_wait(full_bar(slot), use & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t abase = a0 + (uint32_t)slot * slot_bytes + (uint32_t)kb * (PANELS * kTileBytes);
+            const uint64_t da_hi = umma_desc(abase), da_lo = umma_desc(abase + kTileBytes);
+            const uint64_t bh = db_hi + kb * ((2u * b_bytes) >> 4), bl = db_lo + kb * ((2u * b_bytes) >> 4);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const uint32_t tacc = tmem + (uint32_t)((slot * SUBS + kb * R + i) * p.n_mma);
+                const uint64_t ah = da_hi + i * (KSUB / 16), al = da_lo + i * (KSUB / 16);   // K offset of sub-tile i
+                uint32_t acc = 0;
+                if constexpr (PANELS == 2) {
+                    for (int s = 0; s < p.k_steps; ++s) {
+                        umma<PREC, 1>(tacc, al + 2 * s, bh + 2 * s, idesc, acc);
+                        acc = 1;
+                    }
+                    for (int s = 0; s < p.k_steps; ++s) umma<PREC, 1>(tacc, ah + 2 * s, bl + 2 * s, idesc, 1);
+                }
+                for (int s = 0; s < p.k_steps; ++s) {
+                    umma<PREC, 1>(tacc, ah + 2 * s, bh + 2 * s, idesc, acc);
+                    acc = 1;
+                }
+            }
+        }
+        umma_commit(done_bar(slot));
+    };
+
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------ producers
         const int group = warp >> 2;
         const int row = ((warp & 3) << 5) | lane;                         // row inside the tile = TMEM lane
-        // KB == 1: the groups alternate tiles; KB == 2: group g converts k-block g of every tile
+        // KB == 1: the groups take tiles round-robin; KB == 2: groups 0 and 1 convert k-blocks 0 and 1
+        // of every tile (a third group has nothing to do)
         const int kb_mine = KB == 2 ? group : 0;
-        for (int64_t j = (KB == 2 ? 0 : group);; j += (KB == 2 ? 1 : 2)) {
+        // a group must never run two phases ahead of a slot's `free` barrier (parity waits alias):
+        // with the epilogue retiring tiles in order that holds iff groups <= slots
+        const bool idle = group >= p.groups;
+        if (KB == 2 && group == 2) {
+            // two k-blocks: groups 0 and 1 convert, the first warp of group 2 issues the MMAs
+            if ((warp & 3) == 0 && lane == 0)
+                for (int64_t j = 0;; ++j) {
+                    if ((int64_t)blockIdx.x + j * gridDim.x >= p.tiles) break;
+                    issue_mma((int)(j % p.slots), (uint32_t)(j / p.slots));
+                }
+            __syncwarp();
+        }
+        for (int64_t j = (KB == 2 ? 0 : group);; j += (KB == 2 ? 1 : p.groups)) {
             const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
-            if (tile >= p.tiles) break;
+            if (idle || tile >= p.tiles) break;
             const int slot = (int)(j % p.slots);
             const uint32_t use = (uint32_t)(j / p.slots);
             const int64_t bidx = tile / tiles_per_batch;
@@ -259,46 +306,11 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full_bar(slot));
+            // KB == 1: one thread of the group issues the tile's MMAs once every producer of the tile
+            // has arrived (KB == 2: the idle third group does, see below)
+            if (KB == 1 && (warp & 3) == 0 && lane == 0) issue_mma(slot, use);
+            __syncwarp();
         }
-    } else if (warp == kMmaWarp) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc<PREC>(kTileRows, p.n_mma);
-            const uint64_t db_hi = umma_desc(b_hi), db_lo = umma_desc(b_lo);
-            for (int64_t j = 0;; ++j) {
-                const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
-                if (tile >= p.tiles) break;
-                const int slot = (int)(j % p.slots);
-                const uint32_t use = (uint32_t)(j / p.slots);
-                mbar_wait(full_bar(slot), use & 1u);
-                tc_fence_after();
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint32_t abase = a0 + (uint32_t)slot * slot_bytes + (uint32_t)kb * (PANELS * kTileBytes);
-                    const uint64_t da_hi = umma_desc(abase), da_lo = umma_desc(abase + kTileBytes);
-                    const uint64_t bh = db_hi + kb * ((2u * b_bytes) >> 4), bl = db_lo + kb * ((2u * b_bytes) >> 4);
-#pragma unroll
-                    for (int i = 0; i < R; ++i) {
-                        const uint32_t tacc = tmem + (uint32_t)((slot * SUBS + kb * R + i) * p.n_mma);
-                        const uint64_t ah = da_hi + i * (KSUB / 16), al = da_lo + i * (KSUB / 16);   // K offset of sub-tile i
-                        uint32_t acc = 0;
-                        if constexpr (PANELS == 2) {
-                            for (int s = 0; s < p.k_steps; ++s) {
-                                umma<PREC, 1>(tacc, al + 2 * s, bh + 2 * s, idesc, acc);
-                                acc = 1;
-                            }
-                            for (int s = 0; s < p.k_steps; ++s) umma<PREC, 1>(tacc, ah + 2 * s, bl + 2 * s, idesc, 1);
-                        }
-                        for (int s = 0; s < p.k_steps; ++s) {
-                            umma<PREC, 1>(tacc, ah + 2 * s, bh + 2 * s, idesc, acc);
-                            acc = 1;
-                        }
-                    }
-                }
-                umma_commit(done_bar(slot));
-            }
-        }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;
@@ -372,7 +384,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kMmaWarp) {
+    if (warp == kAllocWarp) {
         uint32_t cols = (uint32_t)(p.slots * SUBS * p.n_mma);
         cols = cols < 32u ? 32u : cols;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
@@ -483,10 +495,11 @@ int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void*
     p.k_blocks = e.n_k == 6 ? 2 : 1;
     p.k_steps = std::max(1, (k_real / p.k_blocks) / 16);
     // rows per producer thread: ~256 bytes of loads in flight, and >= 2 slots of accumulators in TMEM
-    p.sub = std::min(e.n_k <= 3 ? 4 : e.n_k == 4 ? 2 : 1, 256 / p.n_mma);
+    p.sub = std::max(1, std::min(e.n_k <= 3 ? 4 : e.n_k == 4 ? 2 : 1, 128 / p.n_mma));   // 4 slots of accumulators in TMEM when possible
     while (p.sub > 1 && e.n_m < 7 + (p.sub == 4 ? 2 : 1)) p.sub >>= 1;
     p.slots = std::min(kMaxSlots, 512 / (p.sub * p.k_blocks * p.n_mma));
     if (p.k_blocks == 2) p.slots = 2;                                    // 64 KB of A per slot
+    p.groups = p.k_blocks == 2 ? 2 : std::min(kGroups, p.slots);
     // mean of the accumulator's round-toward-zero bias, by MMAs per product (tools/tc_calibrate.py)
     p.debias = p.k_steps >= 4 ? 8.6e-8f : p.k_steps == 2 ? 5.4e-8f : 3.6e-8f;
     if (precision == TNC_TC_F16) p.debias = 0.f;
