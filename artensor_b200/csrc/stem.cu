@@ -33,7 +33,8 @@ struct StemParams {
     const int32_t* rows_a;
     const int32_t* rows_b;
     int32_t rows_mode_a, rows_mode_b;
-    int32_t nbatch;
+    int32_t nbatch;                // outer batches (each reloads the right operand(s))
+    int32_t fold;                  // right-operand rows handled per row of A read (1 = none), see launch_stem
     int32_t rank_a, rank_b;
     int32_t mb, kb, nb;
     int32_t a_vec;                 // k bit 0 sits at A position 0: two k neighbours form one 16-byte load
@@ -57,8 +58,8 @@ template <int NCH, int KCH>
 __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4 : 2)) stem_kernel(const StemParams p) {
     extern __shared__ __align__(16) unsigned char stem_smem[];
     const int K = 1 << p.kb, N = 1 << p.nb;
-    float2* Bs = (float2*)stem_smem;                    // [K][N]
-    uint32_t* koff = (uint32_t*)(Bs + (size_t)K * N);   // A offset of contracted index k
+    float2* Bs = (float2*)stem_smem;                    // [fold][K][N]
+    uint32_t* koff = (uint32_t*)(Bs + (size_t)p.fold * K * N);   // A offset of contracted index k
     const uint32_t stage = ((smem_u32(koff + K) + 15u) & ~15u) + (threadIdx.x >> 5) * 4096u;   // this warp's staging buffer
     const bool staged = NCH >= 2 && p.mb >= 5;           // whole warps only
     const int lane = threadIdx.x & 31;
@@ -71,20 +72,27 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
     const int64_t tiles_per_batch = (rows + kStemThreads - 1) / kStemThreads;
     const int64_t tiles = tiles_per_batch * p.nbatch;
     int cur_batch = -1;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    // Each CTA walks a contiguous range of tiles: with many small batches (outer steps: thousands of
+    // row pairs of a few hundred tiles each) a strided walk would change batch -- reload B, two
+    // barriers -- on every tile.
+    const int64_t t_begin = tiles * blockIdx.x / gridDim.x, t_end = tiles * (blockIdx.x + 1) / gridDim.x;
+    for (int64_t t = t_begin; t < t_end; ++t) {
         const int b = (int)(t / tiles_per_batch);
         if (b != cur_batch) {
             __syncthreads();
-            int64_t rb = 0;
-            if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = b;
-            else if (p.rows_mode_b >= 0) rb = p.rows_b[b];
-            const float2* __restrict__ bsrc = p.b + (rb << p.rank_b);
-            for (int e = threadIdx.x; e < K * N; e += kStemThreads) {
-                const int k = e >> p.nb, n = e & (N - 1);
-                uint32_t o = 0;
-                for (int i = 0; i < p.kb; ++i) o |= ((uint32_t)(k >> i) & 1u) << p.k_b[i];
-                for (int i = 0; i < p.nb; ++i) o |= ((uint32_t)(n >> i) & 1u) << p.n_b[i];
-                Bs[e] = bsrc[o];
+            for (int f = 0; f < p.fold; ++f) {
+                int64_t rb = 0;
+                if (p.fold > 1) rb = f;                                   // folded: rows 0 .. fold-1 of B
+                else if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = b;
+                else if (p.rows_mode_b >= 0) rb = p.rows_b[b];
+                const float2* __restrict__ bsrc = p.b + (rb << p.rank_b);
+                for (int e = threadIdx.x; e < K * N; e += kStemThreads) {
+                    const int k = e >> p.nb, n = e & (N - 1);
+                    uint32_t o = 0;
+                    for (int i = 0; i < p.kb; ++i) o |= ((uint32_t)(k >> i) & 1u) << p.k_b[i];
+                    for (int i = 0; i < p.nb; ++i) o |= ((uint32_t)(n >> i) & 1u) << p.n_b[i];
+                    Bs[(size_t)f * K * N + e] = bsrc[o];
+                }
             }
             __syncthreads();
             cur_batch = b;
@@ -97,7 +105,11 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
         int64_t aoff = ra << p.rank_a;
         for (int i = 0; i < p.n_runs; ++i) aoff |= ((r >> p.run_src[i]) & (int64_t)p.run_mask[i]) << p.run_dst[i];
         const float2* __restrict__ ap = p.a + aoff;
-        float2* __restrict__ cp = p.c + (((int64_t)b << p.mb) + r) * N;
+        // folded: the row of A is read from HBM once and meets every row of B (the repeats hit L1/L2)
+#pragma unroll 1
+        for (int f = 0; f < p.fold; ++f) {
+        const float2* __restrict__ Bf = Bs + (size_t)f * K * N;
+        float2* __restrict__ cp = p.c + ((((int64_t)b * p.fold + f) << p.mb) + r) * N;
 #pragma unroll 1
         for (int n0 = 0; n0 < N; n0 += NCH) {
             float2 acc[NCH];
@@ -119,7 +131,7 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
                 }
 #pragma unroll
                 for (int j = 0; j < KCH; ++j) {
-                    const float2* brow = Bs + (size_t)(k0 + j) * N + n0;
+                    const float2* brow = Bf + (size_t)(k0 + j) * N + n0;
                     if constexpr (NCH == 1) {
                         cfma(acc[0], av[j], brow[0]);
                     } else {
@@ -143,6 +155,7 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
                         *(float4*)(cp + n0 + i) = make_float4(acc[i].x, acc[i].y, acc[i + 1].x, acc[i + 1].y);
                 }
             }
+        }
         }
     }
 }
@@ -207,6 +220,19 @@ int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, cons
     p.rows_mode_a = e.rows_a;
     p.rows_mode_b = e.rows_b;
     p.nbatch = e.nb;
+    p.fold = 1;
+    // Right-operand rows folded into the row loop (A is then read from HBM once, not once per row
+    // of B): a plain step whose rows come from B alone, or a full outer step (all row pairs,
+    // A-major: validated when the operation was added).
+    const size_t b_bytes = (size_t)8 << (e.n_k + e.n_n);
+    if (e.nb > 1 && e.rows_a == TNC_ROWS_NONE && e.rows_b == TNC_ROWS_IDENTITY && e.nb * b_bytes <= 32 * 1024) {
+        p.fold = e.nb;
+        p.nbatch = 1;
+    } else if ((e.flags & TNC_EINSUM_OUTER_ROWS) && e.b.rows > 1 && e.b.rows * b_bytes <= 32 * 1024) {
+        p.fold = e.b.rows;
+        p.nbatch = e.a.rows;
+        p.rows_mode_a = TNC_ROWS_IDENTITY;                                // outer batch = row of A
+    }
     p.rank_a = e.a.rank;
     p.rank_b = e.b.rank;
     p.mb = e.n_m;
@@ -231,8 +257,8 @@ int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, cons
         ++p.n_runs;
         j += len;
     }
-    const size_t smem = ((size_t)8 << (e.n_k + e.n_n)) + ((size_t)4 << e.n_k) + 16 + (kStemThreads / 32) * 4096;
-    const int64_t tiles = ((((int64_t)1 << e.n_m) + kStemThreads - 1) / kStemThreads) * e.nb;
+    const size_t smem = p.fold * b_bytes + ((size_t)4 << e.n_k) + 16 + (kStemThreads / 32) * 4096;
+    const int64_t tiles = ((((int64_t)1 << e.n_m) + kStemThreads - 1) / kStemThreads) * p.nbatch;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 4 * 4);
     switch (e.n_n) {
         case 0: return launch_k<1>(p, smem, grid, s);

@@ -736,7 +736,9 @@ struct GemmArgs {
     int32_t a_batched, b_batched;
     int32_t kc;               // k-blocks per TMEM accumulation chunk
     int32_t tiles, rounds;    // persistent grid: CTA c runs tiles c, c + grid, ... (rounds of them)
-    int32_t blocked;          // panels are tile-contiguous: [tile][k-block][rows][128 bytes]
+    int32_t blocked;          // A panel is tile-contiguous: [tile][k-block][rows][128 bytes]
+    int32_t blocked_b;        // B' panel likewise
+    int32_t n_inner;          // outer-rows step with B's rows folded into N: real columns per row of B (0 = not folded)
     int32_t outer_rj, outer_mb;   // outer-rows step: batch = row of B, GEMM row = (row of A, m): see c_row()
     int32_t sync_every;       // k-blocks between grid-wide lockstep barriers (0 = none)
     uint32_t* sync_counter;   // zeroed before the launch
@@ -847,9 +849,16 @@ __device__ __forceinline__ void store_tile_rows(const GemmArgs& g, uint32_t stag
                                                 int lane) {
     float sab = 1.f;
     if constexpr (F16) sab = f16_inv_scale(g.amax[0]) * f16_inv_scale(g.amax[1]);
+    // Output address of GEMM element (row, col).  Folded outer-rows steps (n_inner != 0): the GEMM
+    // columns are (row of B, n), and C wants the row pair outermost, so every n_inner columns
+    // belong to another row block of C; n_inner >= 32, so a 32-column slab never straddles two.
+    auto cptr = [&](int row, int col) -> float* {
+        if (g.n_inner == 0) return g.c + c_row(g, batch, row) * g.ldc + col;
+        const int rb = col / g.n_inner;
+        return g.c + c_row(g, rb, row) * g.ldc + (col - rb * g.n_inner);
+    };
     const bool whole = row0 + 32 <= g.M && col0 + CPT <= g.N && (g.outer_rj == 0 || g.outer_mb >= 5);
     if (whole) {
-        float* cbase = g.c + c_row(g, batch, row0) * g.ldc + col0;
         if constexpr (CPT >= 32) {
 #pragma unroll
             for (int c = 0; c < CPT; c += 32) {
@@ -857,26 +866,25 @@ __device__ __forceinline__ void store_tile_rows(const GemmArgs& g, uint32_t stag
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[c + j] *= sab;
                 }
-                store_rows_coalesced<8>(stage, acc + c, cbase + c, g.ldc, lane);
+                store_rows_coalesced<8>(stage, acc + c, cptr(row0, col0 + c), g.ldc, lane);
             }
         } else {
             if constexpr (F16) {
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) acc[j] *= sab;
             }
-            store_rows_coalesced<CPT / 4>(stage, acc, cbase, g.ldc, lane);
+            store_rows_coalesced<CPT / 4>(stage, acc, cptr(row0, col0), g.ldc, lane);
         }
         return;
     }
     const int row = row0 + lane;
     if (row >= g.M) return;
-    float* crow = g.c + c_row(g, batch, row) * g.ldc + col0;
 #pragma unroll
     for (int j = 0; j < CPT; j += 4)
         if (col0 + j < g.N) {
             float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
             if constexpr (F16) o = make_float4(o.x * sab, o.y * sab, o.z * sab, o.w * sab);
-            *(float4*)(crow + j) = o;
+            *(float4*)cptr(row, col0 + j) = o;
         }
 }
 
@@ -944,23 +952,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     mbar_expect_tx(full_bar(s), C::STAGE);
                     const uint32_t st = base + s * C::STAGE;
-                    if (g.blocked) {
-                        // one contiguous [rows][128 bytes] block per (tile, k-block)
-                        const int blk_a = kb + nkb * (t.m_tile + g.m_tiles * ba);
-                        const int blk_b = kb + nkb * (t.n_tile + g.n_tiles * bb);
-                        tma_load_3d(st, &map_a_hi, full_bar(s), 0, 0, blk_a);
-                        tma_load_3d(st + C::B_HI, &map_b_hi, full_bar(s), 0, 0, blk_b);
-                        if constexpr (C::PANELS == 2) {
-                            tma_load_3d(st + C::A_LO, &map_a_lo, full_bar(s), 0, 0, blk_a);
-                            tma_load_3d(st + C::B_LO, &map_b_lo, full_bar(s), 0, 0, blk_b);
-                        }
-                    } else {
-                        tma_load_3d(st, &map_a_hi, full_bar(s), kb * BK, t.m0, ba);
-                        tma_load_3d(st + C::B_HI, &map_b_hi, full_bar(s), kb * BK, t.n0, bb);
-                        if constexpr (C::PANELS == 2) {
-                            tma_load_3d(st + C::A_LO, &map_a_lo, full_bar(s), kb * BK, t.m0, ba);
-                            tma_load_3d(st + C::B_LO, &map_b_lo, full_bar(s), kb * BK, t.n0, bb);
-                        }
+                    // blocked panels: one contiguous [rows][128 bytes] block per (tile, k-block)
+                    const int a0 = g.blocked ? 0 : kb * BK, a1 = g.blocked ? 0 : t.m0;
+                    const int a2 = g.blocked ? kb + nkb * (t.m_tile + g.m_tiles * ba) : ba;
+                    const int b0 = g.blocked_b ? 0 : kb * BK, b1 = g.blocked_b ? 0 : t.n0;
+                    const int b2 = g.blocked_b ? kb + nkb * (t.n_tile + g.n_tiles * bb) : bb;
+                    tma_load_3d(st, &map_a_hi, full_bar(s), a0, a1, a2);
+                    tma_load_3d(st + C::B_HI, &map_b_hi, full_bar(s), b0, b1, b2);
+                    if constexpr (C::PANELS == 2) {
+                        tma_load_3d(st + C::A_LO, &map_a_lo, full_bar(s), a0, a1, a2);
+                        tma_load_3d(st + C::B_LO, &map_b_lo, full_bar(s), b0, b1, b2);
                     }
                 }
             }
@@ -1159,23 +1160,15 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     if (rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE);     // both CTAs' bytes land on rank 0's barrier
                     const uint32_t st = base + s * C::STAGE;
-                    if (g.blocked) {
-                        const int blk_a = kb + nkb * (m_tile128 + g.m_tiles * ba);
-                        const int blk_b = kb + nkb * (t.n_tile + g.n_tiles * bb);
-                        tma_load_3d_2sm(st, &map_a_hi, full_bar(s), 0, 0, blk_a);
-                        tma_load_3d_2sm(st + C::B_HI, &map_b_hi, full_bar(s), 0, 128 * (int)rank, blk_b);
-                        if constexpr (C::PANELS == 2) {
-                            tma_load_3d_2sm(st + C::A_LO, &map_a_lo, full_bar(s), 0, 0, blk_a);
-                            tma_load_3d_2sm(st + C::B_LO, &map_b_lo, full_bar(s), 0, 128 * (int)rank, blk_b);
-                        }
-                    } else {
-                        const int mrow = m_tile128 * BM, nrow = t.n0 + 128 * (int)rank;
-                        tma_load_3d_2sm(st, &map_a_hi, full_bar(s), kb * BK, mrow, ba);
-                        tma_load_3d_2sm(st + C::B_HI, &map_b_hi, full_bar(s), kb * BK, nrow, bb);
-                        if constexpr (C::PANELS == 2) {
-                            tma_load_3d_2sm(st + C::A_LO, &map_a_lo, full_bar(s), kb * BK, mrow, ba);
-                            tma_load_3d_2sm(st + C::B_LO, &map_b_lo, full_bar(s), kb * BK, nrow, bb);
-                        }
+                    const int a0 = g.blocked ? 0 : kb * BK, a1 = g.blocked ? 0 : m_tile128 * BM;
+                    const int a2 = g.blocked ? kb + nkb * (m_tile128 + g.m_tiles * ba) : ba;
+                    const int b0 = g.blocked_b ? 0 : kb * BK, b1 = (g.blocked_b ? 0 : t.n0) + 128 * (int)rank;
+                    const int b2 = g.blocked_b ? kb + nkb * (t.n_tile + g.n_tiles * bb) : bb;
+                    tma_load_3d_2sm(st, &map_a_hi, full_bar(s), a0, a1, a2);
+                    tma_load_3d_2sm(st + C::B_HI, &map_b_hi, full_bar(s), b0, b1, b2);
+                    if constexpr (C::PANELS == 2) {
+                        tma_load_3d_2sm(st + C::A_LO, &map_a_lo, full_bar(s), a0, a1, a2);
+                        tma_load_3d_2sm(st + C::B_LO, &map_b_lo, full_bar(s), b0, b1, b2);
                     }
                 }
             }
@@ -1347,12 +1340,13 @@ struct TcGemmOp {
     int64_t M = 0, N = 0, K = 0;                      // real GEMM sizes
     int64_t batch = 1;
     int a_batched = 0, b_batched = 0;
+    int n_inner = 0;
     int bn = 256;
     GemmArgs args{};
     int64_t tiles = 0;
     char* maps_for = nullptr;                         // workspace base the tensor maps were encoded for
     CUtensorMap maps[4];
-    int blocked = 0;                                  // tile-contiguous panels
+    int blocked = 0, blocked_b = 0;                   // tile-contiguous panels (A, B')
     int two_cta = 0;                                  // CTA pairs (cta_group::2) on 256 x 256 tiles
     int grid = 1;
     uint32_t* dev_words = nullptr;                    // [0], [1]: amax bits of A, B; [32]: lockstep barrier counter
@@ -1364,6 +1358,7 @@ struct Shape {
     int64_t nb_a, nb_b, batch, M, N, K;
     int fold_rows;   // A's identity rows folded into M
     int outer;       // TNC_EINSUM_OUTER_ROWS lowering
+    int n_inner;     // outer lowering with B's rows folded into N: real columns per row of B (0: B's rows are the batch)
 };
 
 int shape_of(const tnc_einsum& e, Shape* sh) {
@@ -1390,13 +1385,20 @@ int shape_of(const tnc_einsum& e, Shape* sh) {
     }
     sh->batch = sh->fold_rows ? 1 : e.nb;
     sh->outer = (e.flags & TNC_EINSUM_OUTER_ROWS) && e.nb > 1 && !sh->fold_rows;
+    sh->n_inner = 0;
     if (sh->outer) {          // A's rows extend M, B's rows are the batch: nothing is gathered twice
         sh->nb_a = e.a.rows;
         sh->nb_b = e.b.rows;
         sh->batch = e.b.rows;
+        // ... or, when a row of B spans whole 32-column slabs, B's rows extend N instead: ONE GEMM
+        // that reads the (large) left panel once per 256 columns instead of once per row of B
+        if (((int64_t)2 << e.n_n) >= 32 && !(getenv("TNC_TC_FOLDN") && atoi(getenv("TNC_TC_FOLDN")) == 0)) {
+            sh->n_inner = 2 << e.n_n;
+            sh->batch = 1;
+        }
     }
     sh->M = ((int64_t)1 << e.n_m) * ((sh->fold_rows || sh->outer) ? sh->nb_a : 1);
-    sh->N = (int64_t)2 << e.n_n;
+    sh->N = ((int64_t)2 << e.n_n) * (sh->n_inner ? sh->nb_b : 1);
     sh->K = (int64_t)2 << e.n_k;
     if (sh->M >= ((int64_t)1 << 31) || sh->N >= ((int64_t)1 << 31) || sh->K >= ((int64_t)1 << 31) ||
         sh->batch >= ((int64_t)1 << 31)) {
@@ -1461,10 +1463,12 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     op->pa.kb_log2 = kbl;
     const int bn = sh.N >= 256 ? 256 : sh.N >= 128 ? 128 : sh.N >= 64 ? 64 : sh.N >= 32 ? 32 : 16;
     // tile-contiguous panels need whole tiles: K a multiple of one k-block, every row block a
-    // multiple of 128 rows, N a multiple of the tile width
+    // multiple of 128 rows, N a multiple of the tile width (a folded B' panel keeps the plain
+    // [row of B][n][k] order: its row count need not be a multiple of the tile)
     op->blocked = e.n_k >= kbl && e.n_m >= 7 && sh.N >= bn;
     if (const char* env = getenv("TNC_TC_BLOCKED"))
         if (atoi(env) == 0) op->blocked = 0;
+    op->blocked_b = op->blocked && sh.n_inner == 0;
     {
         int8_t pm[TNC_MAX_BITS];                       // A position of row bit j (output order)
         for (int i = 0; i < e.n_m; ++i) pm[e.m_c[i] - e.n_n] = e.m_a[i];
@@ -1488,7 +1492,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     op->pb.mode = f16 ? PACK_EXPAND_SPLIT_F16 : PACK_EXPAND_SPLIT;
     op->pb.inner_bits = e.n_k;
     op->pb.kb_log2 = kbl;
-    op->pb.blocked = op->blocked;
+    op->pb.blocked = op->blocked_b;
     for (int l = 0; (1 << l) <= bn; ++l) op->pb.bn_log2 = l;
     for (int i = 0; i < e.n_k; ++i) op->pb.src_pos[i] = e.k_b[i];
     for (int i = 0; i < e.n_n; ++i) op->pb.src_pos[e.n_k + e.n_c[i]] = e.n_b[i];
@@ -1509,12 +1513,14 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     op->batch = sh.batch;
     op->a_batched = sh.batch > 1 && e.rows_a != TNC_ROWS_NONE && !sh.outer;
     op->b_batched = sh.batch > 1 && e.rows_b != TNC_ROWS_NONE;
+    op->n_inner = sh.n_inner;
     op->bn = bn;
     GemmArgs& g = op->args;
     g.c_batch_stride = sh.M * sh.N;
     g.outer_rj = sh.outer ? (int32_t)sh.nb_b : 0;
     g.outer_mb = e.n_m;
-    g.ldc = (int32_t)sh.N;
+    g.ldc = (int32_t)(sh.n_inner ? sh.n_inner : sh.N);
+    g.n_inner = sh.n_inner;
     g.M = (int32_t)sh.M;
     g.N = (int32_t)sh.N;
     g.K = (int32_t)sh.K;
@@ -1536,6 +1542,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     }
     g.tiles = (int32_t)op->tiles;
     g.blocked = op->blocked;
+    g.blocked_b = op->blocked_b;
     op->two_cta = bn == 256 && sh.M % 256 == 0 && g.m_tiles >= 2;
     if (const char* env = getenv("TNC_TC_2CTA"))
         if (atoi(env) == 0) op->two_cta = 0;
@@ -1587,18 +1594,23 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
         const int bk = bk_of(op->precision);
         char* lo_a = ws + (lo ? op->alo_off : op->ahi_off);
         char* lo_b = ws + (lo ? op->blo_off : op->bhi_off);
+        const int64_t nkb = op->K / bk;
         if (op->blocked) {
             // `blocks` blocks of [rows][128 bytes], one per (tile, k-block)
-            const int64_t nkb = op->K / bk;
-            const int64_t blocks_a = nkb * op->args.m_tiles * batch_a, blocks_b = nkb * op->args.n_tiles * batch_b;
+            const int64_t blocks_a = nkb * op->args.m_tiles * batch_a;
             if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
             if ((rc = make_map(&op->maps[1], lo_a, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
+        } else {
+            // K-major panel [batch][rows][K]; folded rows are part of M
+            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[1], lo_a, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
+        }
+        if (op->blocked_b) {
+            const int64_t blocks_b = nkb * op->args.n_tiles * batch_b;
             if ((rc = make_map(&op->maps[2], ws + op->bhi_off, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
             if ((rc = make_map(&op->maps[3], lo_b, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
         } else {
-            // K-major panels [batch][rows][K]; folded rows are part of M
-            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
-            if ((rc = make_map(&op->maps[1], lo_a, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
+            // [batch][rows][K]; a folded panel ([row of B][n][k], no batch) is one matrix of N rows
             if ((rc = make_map(&op->maps[2], ws + op->bhi_off, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
             if ((rc = make_map(&op->maps[3], lo_b, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
         }
