@@ -182,19 +182,36 @@ def swapped(st: Step):
     return s
 
 
+def skinny_fold(st: Step):
+    """Mirror of skinny_fold() in csrc/skinny.cu: rows of the right operand one launch handles
+    (1: a single right operand; > 1: its rows are folded into N; 0: not supported)."""
+    if st.rb is None or st.nb == 1:
+        return 0 if (st.ra is None and st.nb != 1) else 1
+    fold = 0
+    if st.ra is None and st.kind == "plain":
+        fold = st.nb
+    elif full_outer(st):
+        fold = st.b.rows
+    k, n = len(st.k_modes), len(st.n_modes)
+    if fold < 1 or k > 5 or n < 2 or (fold << (n + 1)) > 256:
+        return 0
+    return fold
+
+
 def skinny_eligible(st: Step, precision, min_n=1):
     """Mirror of skinny_supported() in csrc/skinny.cu; `min_n` is the planner's own cut-off
-    (PlanOptions.skinny_min_n)."""
+    (PlanOptions.skinny_min_n) on the outputs per row of A read (folded rows count)."""
     k, n, m = len(st.k_modes), len(st.n_modes), len(st.m_modes)
     if precision == "3xtf32" or len(st.h_modes) != 0:
         return False
+    fold = skinny_fold(st)
+    if fold == 0:
+        return False
     # rows of K >= 32 carry enough bytes on the A side to run one output bit shorter
     low = max(1, min_n - 1) if k >= 5 else max(1, min_n)
-    if not (2 <= k <= 6 and low <= n <= 7 and m >= 7) or (k == 6 and n > 6):
+    if not (2 <= k <= 6 and 1 <= n <= 7 and m >= 7) or (k == 6 and n > 6):
         return False
-    if st.rb is not None and st.nb != 1:
-        return False
-    return not (st.ra is None and st.nb != 1)
+    return (fold << n) >= (1 << low)
 
 
 class ContractionPlan:

@@ -65,6 +65,8 @@ struct SkinnyParams {
     int8_t k_a[8], k_b[8], n_b[8];
     int32_t k_blocks;              // 1, or 2 for K = 64
     int32_t groups;                // active producer groups (<= kGroups, <= slots)
+    int32_t fold;                  // rows of B folded into N (1 = none): accumulator columns [f * n_real, (f+1) * n_real)
+                                   // of a tile are the outputs against row f of B and go to row block (batch * fold + f) of C
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -136,15 +138,15 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
         for (uint32_t i = threadIdx.x; i < total16; i += kSkinnyThreads) sts128(base + (i << 4), 0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    // the right operand (one block: B has no rows, or a single output row block)
-    int64_t rb = 0;
-    if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = 0;
-    else if (p.rows_mode_b >= 0) rb = p.rows_b[0];
-    const float2* __restrict__ bsrc = p.b + (rb << p.rank_b);
+    // the right operand: one block (B has no rows, or a single output row block), or -- folded -- rows
+    // 0 .. fold-1 of B stacked along N
+    int64_t rb0 = 0;
+    if (p.fold == 1 && p.rows_mode_b >= 0) rb0 = p.rows_b[0];
     {
         float m = 0.f;
-        for (int e = threadIdx.x; e < K * N; e += kSkinnyThreads) {
-            const float2 x = bsrc[e];                                     // amax does not care about the order
+        const float2* __restrict__ ball = p.b + (rb0 << p.rank_b);
+        for (int e = threadIdx.x; e < p.fold * K * N; e += kSkinnyThreads) {
+            const float2 x = ball[e];                                     // amax does not care about the order
             m = fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y)));
         }
         uint32_t bits = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
@@ -154,7 +156,9 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     const uint32_t b_amax = misc[1];
     {
         const float sc = f16_scale(b_amax);
-        for (int e = threadIdx.x; e < K * N; e += kSkinnyThreads) {
+        for (int ef = threadIdx.x; ef < p.fold * K * N; ef += kSkinnyThreads) {
+            const int f = ef / (K * N), e = ef - f * (K * N);
+            const float2* __restrict__ bsrc = p.b + ((rb0 + f) << p.rank_b);
             const int k = e & (K - 1), n = e >> p.kb;
             uint32_t o = 0;
             for (int i = 0; i < p.kb; ++i) o |= ((uint32_t)(k >> i) & 1u) << p.k_b[i];
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             const __half hr = __float2half_rn(xr), hi = __float2half_rn(xi);
             // B'[2n][2k] = Br, B'[2n][2k+1] = -Bi, B'[2n+1][2k] = Bi, B'[2n+1][2k+1] = Br
             // element (row, col) lives at row * 128 + ((col >> 3) ^ (row & 7)) * 16 + (col & 7) * 2
-            const uint32_t col = 2u * (k & (KC - 1)), r0 = 2u * n, r1 = 2u * n + 1u;
+            const uint32_t col = 2u * (k & (KC - 1)), r0 = 2u * (f * N + n), r1 = r0 + 1u;
             const uint32_t kbo = (uint32_t)(k / KC) * 2u * b_bytes;       // this k's k-block
             const uint32_t off0 = r0 * 128u + ((((col >> 3) ^ (r0 & 7u)) << 4) | ((col & 7u) << 1));
             const uint32_t off1 = r1 * 128u + ((((col >> 3) ^ (r1 & 7u)) << 4) | ((col & 7u) << 1));
@@ -325,26 +329,20 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             mbar_wait(full_bar(slot), use & 1u);                          // acquires the producers' row scales
             mbar_wait(done_bar(slot), use & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (int i = 0; i < R; ++i) {
-                const float s = row_scale[(slot * SUBS + i) * 128 + q * 32 + lane] * b_inv;
-                float s1 = 0.f;                                           // second k-block's scale (KB == 2)
-                if constexpr (KB == 2) s1 = row_scale[(slot * SUBS + 1) * 128 + q * 32 + lane] * b_inv;
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((slot * SUBS + i) * p.n_mma);
-                // C[rows][m][n]: the sub-tile's rows are consecutive, n_real floats each
-                float* cwarp = (float*)p.c + (((tile * R + i) << 7) + q * 32) * (int64_t)n_real;
-                const bool last_sub = i == R - 1;
+            // one accumulator (n_real columns from TMEM column `tcol`) -> n_real floats per row at `cptr`;
+            // `release`: this is the last read of the slot's accumulators
+            auto emit = [&](uint32_t tcol, float* cptr, float s, float s1, bool release) {
                 if (n_real >= 32) {
                     for (int c0 = 0; c0 < n_real; c0 += 32) {
                         uint32_t v[32], w[KB == 2 ? 32 : 1];
-                        tmem_ld16(taddr + c0, v);
-                        tmem_ld16(taddr + c0 + 16, v + 16);
+                        tmem_ld16(tcol + c0, v);
+                        tmem_ld16(tcol + c0 + 16, v + 16);
                         if constexpr (KB == 2) {
-                            tmem_ld16(taddr + p.n_mma + c0, w);
-                            tmem_ld16(taddr + p.n_mma + c0 + 16, w + 16);
+                            tmem_ld16(tcol + p.n_mma + c0, w);
+                            tmem_ld16(tcol + p.n_mma + c0 + 16, w + 16);
                         }
                         tmem_ld_wait();
-                        if (last_sub && c0 + 32 >= n_real) {              // last read of the slot's accumulators: release it
+                        if (release && c0 + 32 >= n_real) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(free_bar(slot));
@@ -356,14 +354,18 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                             if constexpr (KB == 2) y = fmaf(__uint_as_float(w[x]), s1, y);
                             o[x] = fmaf(y, p.debias, y);
                         }
-                        store_rows_coalesced<8>(stage, o, cwarp + c0, n_real, lane);
+                        store_rows_coalesced<8>(stage, o, cptr + c0, n_real, lane);
                     }
                 } else {
-                    uint32_t v[16], w[KB == 2 ? 16 : 1];
-                    tmem_ld16(taddr, v);
-                    if constexpr (KB == 2) tmem_ld16(taddr + p.n_mma, w);
+                    uint32_t v[16] = {}, w[KB == 2 ? 16 : 1] = {};
+                    if (n_real == 16) tmem_ld16(tcol, v);
+                    else tmem_ld8(tcol, v);
+                    if constexpr (KB == 2) {
+                        if (n_real == 16) tmem_ld16(tcol + p.n_mma, w);
+                        else tmem_ld8(tcol + p.n_mma, w);
+                    }
                     tmem_ld_wait();
-                    if (last_sub) {
+                    if (release) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(free_bar(slot));
@@ -375,9 +377,25 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                         if constexpr (KB == 2) y = fmaf(__uint_as_float(w[x]), s1, y);
                         o[x] = fmaf(y, p.debias, y);
                     }
-                    if (n_real == 16) store_rows_coalesced<4>(stage, o, cwarp, n_real, lane);
-                    else if (n_real == 8) store_rows_coalesced<2>(stage, o, cwarp, n_real, lane);
-                    else store_rows_coalesced<1>(stage, o, cwarp, n_real, lane);
+                    if (n_real == 16) store_rows_coalesced<4>(stage, o, cptr, n_real, lane);
+                    else if (n_real == 8) store_rows_coalesced<2>(stage, o, cptr, n_real, lane);
+                    else store_rows_coalesced<1>(stage, o, cptr, n_real, lane);
+                }
+            };
+            const int64_t bidx = tile / tiles_per_batch;
+#pragma unroll 1
+            for (int i = 0; i < R; ++i) {
+                const float s = row_scale[(slot * SUBS + i) * 128 + q * 32 + lane] * b_inv;
+                float s1 = 0.f;                                           // second k-block's scale (KB == 2)
+                if constexpr (KB == 2) s1 = row_scale[(slot * SUBS + 1) * 128 + q * 32 + lane] * b_inv;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((slot * SUBS + i) * p.n_mma);
+                // C[rows][m][n]: the sub-tile's rows are consecutive, n_real floats each
+                const int64_t row_in_batch = ((((tile - bidx * tiles_per_batch) * R + i) << 7) + q * 32);
+                const bool last_sub = i == R - 1;
+#pragma unroll 1
+                for (int f = 0; f < p.fold; ++f) {
+                    float* cptr = (float*)p.c + ((((bidx * p.fold + f) << p.mb) + row_in_batch) * (int64_t)n_real);
+                    emit(taddr + (uint32_t)(f * n_real), cptr, s, s1, last_sub && f == p.fold - 1);
                 }
             }
         }
@@ -439,13 +457,24 @@ int launch_k(const SkinnyParams& p, size_t smem, int grid, cudaStream_t s) {
 
 }  // namespace
 
+// Rows of B handled by one launch: 1 (B has no rows / a single row block), the row count when they
+// can be folded into N -- a plain step whose rows come from B alone, or a full outer step (all row
+// pairs, A-major) --, 0 when the step needs a different right operand per row block.
+int skinny_fold(const tnc_einsum& e) {
+    if (e.rows_b == TNC_ROWS_NONE || e.nb == 1) return (e.rows_a == TNC_ROWS_NONE && e.nb != 1) ? 0 : 1;
+    int fold = 0;
+    if (e.rows_a == TNC_ROWS_NONE && e.rows_b == TNC_ROWS_IDENTITY) fold = e.nb;
+    else if (e.flags & TNC_EINSUM_OUTER_ROWS) fold = e.b.rows;
+    if (fold < 1 || e.n_k > 5 || e.n_n < 2 || ((int64_t)fold << (e.n_n + 1)) > 256) return 0;
+    return fold;
+}
+
 bool skinny_supported(const tnc_einsum& e, int dtype, int precision) {
     if (dtype != TNC_C64 || e.n_h != 0) return false;
     if (precision != TNC_TC_3XF16 && precision != TNC_TC_F16) return false;
     if (e.n_k < 2 || e.n_k > 6 || e.n_n < 1 || e.n_n > 7 || e.n_m < 7) return false;
     if (e.n_k == 6 && e.n_n > 6) return false;                           // two k-blocks of B' and two slots must fit shared memory
-    if (e.rows_b != TNC_ROWS_NONE && e.nb != 1) return false;            // one right operand for the whole launch
-    if (e.rows_a == TNC_ROWS_NONE && e.nb != 1) return false;
+    if (skinny_fold(e) == 0) return false;                               // one right operand (possibly folded) per launch
     for (int i = 0; i < e.n_n; ++i)
         if (e.n_c[i] >= e.n_n) return false;                             // output must be C[rows][m][n]
     return true;
@@ -491,7 +520,9 @@ int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void*
         j += len;
     }
     const int n_real = 2 << e.n_n, k_real = 2 << e.n_k;
-    p.n_mma = std::max(16, n_real);
+    p.fold = skinny_fold(e);
+    p.n_mma = 16;
+    while (p.n_mma < p.fold * n_real) p.n_mma <<= 1;                     // power of two: TMEM allocations are
     p.k_blocks = e.n_k == 6 ? 2 : 1;
     p.k_steps = std::max(1, (k_real / p.k_blocks) / 16);
     // rows per producer thread: ~256 bytes of loads in flight, and >= 2 slots of accumulators in TMEM
@@ -503,7 +534,11 @@ int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void*
     // mean of the accumulator's round-toward-zero bias, by MMAs per product (tools/tc_calibrate.py)
     p.debias = p.k_steps >= 4 ? 8.6e-8f : p.k_steps == 2 ? 5.4e-8f : 3.6e-8f;
     if (precision == TNC_TC_F16) p.debias = 0.f;
-    p.tiles = (((int64_t)e.nb << e.n_m) >> 7) / p.sub;
+    if (p.fold > 1) {
+        p.nbatch = (e.flags & TNC_EINSUM_OUTER_ROWS) ? e.a.rows : 1;     // outer batch = row of A
+        if (e.flags & TNC_EINSUM_OUTER_ROWS) p.rows_mode_a = TNC_ROWS_IDENTITY;
+    }
+    p.tiles = (((int64_t)p.nbatch << e.n_m) >> 7) / p.sub;
     const int panels = precision == TNC_TC_F16 ? 1 : 2;
     const size_t smem = 1024 + p.k_blocks * 2 * (size_t)p.n_mma * 128 + (size_t)p.slots * p.k_blocks * panels * kTileBytes +
                         (size_t)p.slots * p.sub * p.k_blocks * 512 +

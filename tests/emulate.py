@@ -54,7 +54,8 @@ def run_plan(plan, leaf_blob, slice_ids):
             if E.algo == N.TNC_ALGO_SKINNY:
                 assert sorted(E.n_c[i] for i in range(E.n_n)) == list(range(E.n_n)) and E.n_h == 0
                 assert 2 <= E.n_k <= 6 and 1 <= E.n_n <= 7 and E.n_m >= 7 and not (E.n_k == 6 and E.n_n > 6)
-                assert E.rows_b == N.TNC_ROWS_NONE or E.nb == 1
+                assert (E.rows_b == N.TNC_ROWS_NONE or E.nb == 1 or (E.rows_a == N.TNC_ROWS_NONE and E.rows_b == N.TNC_ROWS_IDENTITY)
+                        or (E.flags & N.TNC_EINSUM_OUTER_ROWS))
             if E.algo == N.TNC_ALGO_STEM:
                 assert sorted(E.n_c[i] for i in range(E.n_n)) == list(range(E.n_n)) and E.n_h == 0
                 assert (8 << (E.n_k + E.n_n)) + (4 << E.n_k) <= 60 * 1024

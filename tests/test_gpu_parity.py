@@ -338,6 +338,46 @@ def test_skinny_row_scaling(dev):
     assert np.all(run_single_step(dev, scheme, leaves, "skinny", "3xf16") == 0)
 
 
+def _rnd(rng, *shape):
+    return torch.from_numpy((rng.randn(*shape) + 1j * rng.randn(*shape)).astype(np.complex64))
+
+
+@pytest.mark.parametrize("algo", ["skinny", "stem", "tc"])
+def test_right_operand_rows_folded(dev, algo):
+    """Sparse steps whose bitstring rows sit on the RIGHT operand: a plain step (rows on B alone)
+    and a full outer step (all row pairs).  The streaming kernels fold B's rows into the row loop /
+    into N so that A is read once; the GEMM lowering folds them into N.  Checked against einsum."""
+    from artensor_b200 import ContractionPlan
+    rng = np.random.RandomState(8)
+    m, k, n, F, RA = 9, 4, 4, 6, 3
+    la, lk, ln = LETTERS[:m], LETTERS[m:m + k], LETTERS[m + k:m + k + n]
+    # plain: A = [m k], B = [Z k n] -> [Z m n]            (contraction.py:189-191, rows from B)
+    eq = f"{la}{lk},Z{lk}{ln}->Z{la}{ln}"
+    leaves = {0: _rnd(rng, *[2] * (m + k)), 1: _rnd(rng, F, *[2] * (k + n))}
+    step = ((0, 1), eq, [[torch.tensor([0])], [torch.arange(F)]])
+    plan = ContractionPlan([step], {i: tuple(v.shape) for i, v in leaves.items()}, True, options=force_options(algo))
+    got = _execute(dev, plan, leaves)
+    want = np.einsum(eq, leaves[0].numpy().astype(np.complex128), leaves[1].numpy().astype(np.complex128))
+    assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 1e-5
+    # outer: A = [Y m k], B = [Z k n] -> [(Y Z) m n]     (contraction.py:180-188)
+    eq = f"Y{la}{lk},Z{lk}{ln}->YZ{la}{ln}"
+    leaves = {0: _rnd(rng, RA, *[2] * (m + k)), 1: _rnd(rng, F, *[2] * (k + n))}
+    step = ((0, 1), eq, [[], []], tuple([-1] + [2] * (m + n)), tuple([RA * F] + [2] * (m + n)))
+    plan = ContractionPlan([step], {i: tuple(v.shape) for i, v in leaves.items()}, True, options=force_options(algo))
+    got = _execute(dev, plan, leaves)
+    want = np.einsum(eq, leaves[0].numpy().astype(np.complex128), leaves[1].numpy().astype(np.complex128)).reshape(got.shape)
+    assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 1e-5
+
+
+def _execute(dev, plan, leaves):
+    blob = plan.pack_leaves({i: v.to(dev) for i, v in leaves.items()})
+    out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
+    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
+    plan.execute(blob, out, 0, 1, ws, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
 @pytest.mark.parametrize("precision", ["3xtf32", "3xf16"])
 def test_tc_long_contraction_keeps_fp32_accuracy(dev, precision):
     """K = 16384 complex (32768 real) accumulated in tensor memory: the split product must stay
