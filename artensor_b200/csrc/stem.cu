@@ -17,6 +17,7 @@
 // (~70 TFLOP/s) becomes the limit above ~11 flop/byte; steps above ~24 flop/byte go to the
 // tcgen05 path instead.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -160,6 +161,199 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
     }
 }
 
+// -------------------------------------------------------------------------------------
+// Bulk-copy variant for K <= 16 (the n <= 4, k <= 4 steps with 2..8 flop/byte, where bytes in flight
+// per SM are what bounds the kernel above).  A tile is 256 consecutive rows; because the row index is
+// numbered by A's address bits in ascending order, the tile's amplitudes are the 2^T lowest
+// address bits of A (8 row bits + the kl contracted bits that sit below them) times the 2^(kb-kl)
+// combinations of the higher contracted bits: 2^(kb-kl) contiguous chunks of 2^T amplitudes.
+//   * a producer warp moves whole chunks HBM -> shared memory with cp.async.bulk into a ring of
+//     stages (mbarrier full / empty), so 48-96 KB per CTA are in flight whatever the consumers do;
+//   * 256 consumer threads (one per row) copy their K amplitudes from the stage into registers,
+//     release the stage at once, and keep them for every row of the right operand that meets this
+//     row of A ("segment": the batches of the step that share the A row -- all of them for a
+//     plain step with rows on B, b.rows for a full outer step, a run of the A-row table for an
+//     outer step with a row subset).  A is therefore read from HBM once;
+//   * every row of the right operand stays resident in shared memory as B[row][k][n].
+struct BulkParams {
+    const float2* a;
+    const float2* b;
+    float2* c;
+    const int32_t* rows_a;
+    const int32_t* rows_b;
+    const int32_t* seg_begin;      // n_seg + 1 batch indices, or nullptr (see launch_stem)
+    int32_t rows_mode_a, rows_mode_b;
+    int32_t n_seg, nbatch, b_rows;
+    int32_t rank_a, rank_b, mb, kb, nb;
+    int32_t T;                     // address bits of one chunk
+    int32_t stages;
+    uint32_t off_b, off_koff, off_bars, off_staging;   // shared-memory byte offsets
+    int32_t n_runs;                // tile index -> A offset: runs of consecutive bits
+    uint32_t run_mask[TNC_MAX_BITS];
+    int8_t run_src[TNC_MAX_BITS], run_dst[TNC_MAX_BITS];
+    int8_t row_lo[8];              // A position (< T) of the tile's row bit j
+    int8_t k_a[TNC_MAX_BITS], k_b[TNC_MAX_BITS], n_b[TNC_MAX_BITS];
+};
+
+constexpr int kBulkConsumers = 256;
+constexpr int kBulkThreads = kBulkConsumers + 32;
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int NCH, int KB, int PER_SM>
+__global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const BulkParams p) {
+    constexpr int K = 1 << KB;
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    const int N = NCH < 16 ? NCH : (1 << p.nb);        // the launcher picks NCH = min(N, 16)
+    const uint32_t stage_bytes = (uint32_t)(K << 8) * 8u;
+    float2* Bs = (float2*)(bulk_smem + p.off_b);                 // [b_rows][K][N]
+    uint32_t* koff_s = (uint32_t*)(bulk_smem + p.off_koff);      // stage offset (amplitudes) of contracted index k
+    const uint32_t bar_full = smem_u32(bulk_smem + p.off_bars), bar_empty = bar_full + 8u * (uint32_t)p.stages;
+    const uint32_t stage0 = smem_u32(bulk_smem);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < p.b_rows * K * N; e += kBulkThreads) {
+        const int row = e / (K * N), rem = e - row * (K * N);
+        const int k = rem >> p.nb, n = rem & (N - 1);
+        uint32_t o = 0;
+        for (int i = 0; i < KB; ++i) o |= ((uint32_t)(k >> i) & 1u) << p.k_b[i];
+        for (int i = 0; i < p.nb; ++i) o |= ((uint32_t)(n >> i) & 1u) << p.n_b[i];
+        Bs[e] = p.b[((int64_t)row << p.rank_b) + o];
+    }
+    if (tid < K) {
+        uint32_t lo = 0, c = 0;
+        int ci = 0;
+        for (int i = 0; i < KB; ++i) {
+            const uint32_t bit = ((uint32_t)tid >> i) & 1u;
+            if (p.k_a[i] < p.T) lo |= bit << p.k_a[i];
+            else c |= bit << ci++;
+        }
+        koff_s[tid] = (c << p.T) | lo;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full + 8u * s, 1);
+            mbar_init(bar_empty + 8u * s, kBulkConsumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tile_bits = p.mb - 8;
+    const int64_t items = (int64_t)p.n_seg << tile_bits;
+    const int64_t i_begin = items * blockIdx.x / gridDim.x, i_end = items * (blockIdx.x + 1) / gridDim.x;
+    const int64_t tile_mask = ((int64_t)1 << tile_bits) - 1;
+    int s = 0;
+    uint32_t ph = 0;
+    if (tid >= kBulkConsumers) {
+        if (tid != kBulkConsumers) return;
+        // ---- producer: one thread issues the bulk copies of each tile
+        int n_hi = 0;
+        int8_t hi_pos[4];
+        for (int i = 0; i < KB; ++i)
+            if (p.k_a[i] >= p.T) hi_pos[n_hi++] = p.k_a[i];
+        const uint32_t chunk_bytes = 8u << p.T;
+        int64_t cur_seg = -1, ra = 0;
+        for (int64_t it = i_begin; it < i_end; ++it) {
+            const int64_t seg = it >> tile_bits, tile = it & tile_mask;
+            if (seg != cur_seg) {
+                cur_seg = seg;
+                if (p.rows_mode_a == TNC_ROWS_NONE) ra = 0;
+                else if (p.seg_begin) {
+                    const int32_t b0 = p.seg_begin[seg];
+                    ra = p.rows_mode_a >= 0 ? p.rows_a[b0] : b0;
+                } else ra = seg;
+            }
+            int64_t aoff = ra << p.rank_a;
+            for (int i = 0; i < p.n_runs; ++i) aoff |= ((tile >> p.run_src[i]) & (int64_t)p.run_mask[i]) << p.run_dst[i];
+            mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+            mbar_expect_tx(bar_full + 8u * s, stage_bytes);
+            const uint32_t dst = stage0 + (uint32_t)s * stage_bytes;
+            for (int c = 0; c < (1 << n_hi); ++c) {
+                int64_t o = aoff;
+                for (int i = 0; i < n_hi; ++i) o |= (int64_t)((c >> i) & 1) << hi_pos[i];
+                bulk_load(dst + (uint32_t)c * chunk_bytes, p.a + o, chunk_bytes, bar_full + 8u * s);
+            }
+            if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+        return;
+    }
+    // ---- consumers: one thread per row of the tile
+    const int lane = tid & 31;
+    const uint32_t stage_w = smem_u32(bulk_smem + p.off_staging) + (uint32_t)(tid >> 5) * (256u * NCH);
+    uint32_t roff = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) roff |= (((uint32_t)tid >> j) & 1u) << p.row_lo[j];
+    int64_t cur_seg = -1;
+    int32_t b0 = 0, b1 = 0;
+    for (int64_t it = i_begin; it < i_end; ++it) {
+        const int64_t seg = it >> tile_bits, tile = it & tile_mask;
+        if (seg != cur_seg) {
+            cur_seg = seg;
+            if (p.seg_begin) {
+                b0 = p.seg_begin[seg];
+                b1 = p.seg_begin[seg + 1];
+            } else if (p.rows_mode_a == TNC_ROWS_NONE) {
+                b0 = 0;
+                b1 = p.nbatch;
+            } else {
+                b0 = (int32_t)seg;
+                b1 = b0 + 1;
+            }
+        }
+        mbar_wait(bar_full + 8u * s, ph);
+        const float2* st = (const float2*)(bulk_smem + (size_t)s * stage_bytes) + roff;
+        float2 av[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) av[k] = st[koff_s[k]];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8u * s);
+        if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+        }
+        const int64_t r = (tile << 8) + tid;
+#pragma unroll 1
+        for (int32_t b = b0; b < b1; ++b) {
+            int32_t rb = 0;
+            if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = b;
+            else if (p.rows_mode_b >= 0) rb = p.rows_b[b];
+            const float2* __restrict__ Bf = Bs + (size_t)rb * K * N;
+            float2* __restrict__ cp = p.c + ((((int64_t)b) << p.mb) + r) * N;
+#pragma unroll 1
+            for (int n0 = 0; n0 < N; n0 += NCH) {
+                float2 acc[NCH];
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float2* brow = Bf + (size_t)k * N + n0;
+                    if constexpr (NCH == 1) {
+                        cfma(acc[0], av[k], brow[0]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NCH; i += 2) {
+                            const float4 bb = *(const float4*)(brow + i);      // warp-uniform: broadcast
+                            cfma(acc[i], av[k], make_float2(bb.x, bb.y));
+                            cfma(acc[i + 1], av[k], make_float2(bb.z, bb.w));
+                        }
+                    }
+                }
+                if constexpr (NCH == 1) {
+                    cp[n0] = acc[0];
+                } else {
+                    store_rows_coalesced<NCH / 2>(stage_w, (const float*)acc, (float*)(cp - (int64_t)lane * N + n0), 2 * (int64_t)N, lane);
+                }
+            }
+        }
+    }
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -194,6 +388,132 @@ int launch_k(const StemParams& p, size_t smem, int grid, cudaStream_t s) {
     }
 }
 
+template <int NCH, int KB, int PER_SM>
+int launch_bulk(const BulkParams& p, size_t smem, int grid, cudaStream_t s) {
+    static bool configured_on[kMaxDevices] = {};
+    bool& configured = configured_on[current_device()];
+    if (!configured) {
+        TNC_CUDA(cudaFuncSetAttribute(stem_bulk_kernel<NCH, KB, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        configured = true;
+    }
+    stem_bulk_kernel<NCH, KB, PER_SM><<<grid, kBulkThreads, smem, s>>>(p);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+template <int NCH>
+int launch_bulk_k(const BulkParams& p, size_t smem, int grid, int per_sm, cudaStream_t s) {
+    if (per_sm >= 3) {
+        switch (p.kb) {
+            case 0: return launch_bulk<NCH, 0, 3>(p, smem, grid, s);
+            case 1: return launch_bulk<NCH, 1, 3>(p, smem, grid, s);
+            case 2: return launch_bulk<NCH, 2, 3>(p, smem, grid, s);
+            case 3: return launch_bulk<NCH, 3, 3>(p, smem, grid, s);
+            default: return launch_bulk<NCH, 4, 3>(p, smem, grid, s);
+        }
+    }
+    switch (p.kb) {
+        case 0: return launch_bulk<NCH, 0, 2>(p, smem, grid, s);
+        case 1: return launch_bulk<NCH, 1, 2>(p, smem, grid, s);
+        case 2: return launch_bulk<NCH, 2, 2>(p, smem, grid, s);
+        case 3: return launch_bulk<NCH, 3, 2>(p, smem, grid, s);
+        default: return launch_bulk<NCH, 4, 2>(p, smem, grid, s);
+    }
+}
+
+// The bulk-copy variant applies when a row's K <= 16 amplitudes fit registers, tiles are whole
+// (>= 256 rows) and every row of the right operand fits shared memory together.
+bool bulk_applies(const tnc_einsum& e) {
+    const size_t b_bytes = ((size_t)8 << (e.n_k + e.n_n)) * (size_t)e.b.rows;
+    return e.n_k <= 4 && e.n_m >= 8 && b_bytes <= 32 * 1024;
+}
+
+int launch_stem_bulk(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
+                     const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s) {
+    BulkParams p{};
+    p.a = (const float2*)a;
+    p.b = (const float2*)b;
+    p.c = (float2*)c;
+    p.rows_a = dev_rows_a;
+    p.rows_b = dev_rows_b;
+    p.seg_begin = dev_seg_begin;
+    p.rows_mode_a = e.rows_a;
+    p.rows_mode_b = e.rows_b;
+    p.nbatch = e.nb;
+    p.n_seg = dev_seg_begin ? n_seg : (e.rows_a == TNC_ROWS_NONE ? 1 : e.nb);
+    p.b_rows = e.b.rows;
+    p.rank_a = e.a.rank;
+    p.rank_b = e.b.rank;
+    p.mb = e.n_m;
+    p.kb = e.n_k;
+    p.nb = e.n_n;
+    for (int i = 0; i < e.n_k; ++i) {
+        p.k_a[i] = e.k_a[i];
+        p.k_b[i] = e.k_b[i];
+    }
+    for (int i = 0; i < e.n_n; ++i) p.n_b[e.n_c[i]] = e.n_b[i];
+    // row bit j (output position n_n + j) -> A position, ascending (the planner numbers the rows by
+    // A's address bits); a layout that does not is left to the per-thread kernel
+    int8_t pa[TNC_MAX_BITS];
+    for (int i = 0; i < e.n_m; ++i) pa[e.m_c[i] - e.n_n] = e.m_a[i];
+    for (int j = 1; j < e.n_m; ++j)
+        if (pa[j] < pa[j - 1]) return TNC_ERR_UNSUPPORTED;
+    p.T = pa[7] + 1;
+    for (int j = 0; j < 8; ++j) p.row_lo[j] = pa[j];
+    p.n_runs = 0;
+    for (int j = 8; j < e.n_m;) {
+        int len = 1;
+        while (j + len < e.n_m && pa[j + len] == pa[j] + len) ++len;
+        p.run_src[p.n_runs] = (int8_t)(j - 8);
+        p.run_dst[p.n_runs] = pa[j];
+        p.run_mask[p.n_runs] = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
+        ++p.n_runs;
+        j += len;
+    }
+    const int nch = std::min(1 << e.n_n, 16);
+    const size_t stage_bytes = (size_t)8 << (8 + e.n_k);
+    const size_t b_bytes = ((size_t)8 << (e.n_k + e.n_n)) * (size_t)e.b.rows;
+    const size_t warp_staging = nch >= 2 ? (size_t)256 * nch : 0;      // 32 rows x nch outputs
+    const size_t staging = (size_t)(kBulkConsumers / 32) * warp_staging;
+    const size_t fixed = ((b_bytes + 15) & ~(size_t)15) + 64 + 16 * 8 + staging + 128;
+    // Three resident CTAs hide the consumers' latencies better at the power-capped clock of a
+    // long run, but the variants with >= 8 outputs x >= 8 amplitudes per row need more than the 72
+    // registers that leaves them (measured inside n53 / n30 slices: 1.18 vs 1.38 ms for n = k = 3
+    // at two CTAs, 2.15 vs 3.2 ms for n = 2, k = 4 at three).
+    static const int forced_per_sm = getenv("TNC_STEM_BULK_CTAS") ? atoi(getenv("TNC_STEM_BULK_CTAS")) : 0;
+    int per_sm = forced_per_sm ? (forced_per_sm >= 3 ? 3 : 2) : ((nch >= 8 && e.n_k >= 3) || nch >= 16 ? 2 : 3);
+    int stages = (int)(((per_sm == 3 ? 74 : 112) * 1024 - fixed) / stage_bytes);
+    if (stages < 2 && per_sm == 3) {
+        per_sm = 2;
+        stages = (int)((112 * 1024 - fixed) / stage_bytes);
+    }
+    if (stages < 2) {
+        per_sm = 1;
+        stages = (int)((220 * 1024 - fixed) / stage_bytes);
+    }
+    stages = std::min(stages, 8);
+    if (stages < 2) return TNC_ERR_UNSUPPORTED;
+    p.stages = stages;
+    size_t off = (size_t)stages * stage_bytes;
+    p.off_b = (uint32_t)off;
+    off += (b_bytes + 15) & ~(size_t)15;
+    p.off_koff = (uint32_t)off;
+    off += 64;
+    p.off_bars = (uint32_t)off;
+    off += 16 * 8;
+    p.off_staging = (uint32_t)off;
+    off += staging;
+    const int64_t items = (int64_t)p.n_seg << (e.n_m - 8);
+    const int grid = (int)std::min<int64_t>(items, (int64_t)sm_count() * per_sm);
+    switch (e.n_n) {
+        case 0: return launch_bulk_k<1>(p, off, grid, per_sm, s);
+        case 1: return launch_bulk_k<2>(p, off, grid, per_sm, s);
+        case 2: return launch_bulk_k<4>(p, off, grid, per_sm, s);
+        case 3: return launch_bulk_k<8>(p, off, grid, per_sm, s);
+        default: return launch_bulk_k<16>(p, off, grid, per_sm, s);
+    }
+}
+
 }  // namespace
 
 bool stem_supported(const tnc_einsum& e, int dtype) {
@@ -206,10 +526,15 @@ bool stem_supported(const tnc_einsum& e, int dtype) {
 }
 
 int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
-                const int32_t* dev_rows_b, cudaStream_t s) {
+                const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s) {
     if (!stem_supported(e, TNC_C64)) {
         set_error("stem einsum: unsupported shape or output layout (k=%d n=%d h=%d)", e.n_k, e.n_n, e.n_h);
         return TNC_ERR_UNSUPPORTED;
+    }
+    static const bool no_bulk = getenv("TNC_STEM_NO_BULK") != nullptr;      // measurement aid
+    if (!no_bulk && bulk_applies(e)) {
+        const int rc = launch_stem_bulk(e, a, b, c, dev_rows_a, dev_rows_b, dev_seg_begin, n_seg, s);
+        if (rc != TNC_ERR_UNSUPPORTED) return rc;
     }
     StemParams p{};
     p.a = (const float2*)a;

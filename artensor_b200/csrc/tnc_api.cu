@@ -35,6 +35,8 @@ struct Op {
     tnc_accum a{};
     int leaf_begin = 0, leaf_count = 0;
     int64_t koff_a = -1, koff_b = -1;     // byte offsets into the device blob
+    int64_t seg_off = -1;                 // streaming kernel: runs of batches sharing their row of A
+    int n_seg = 0;
     std::shared_ptr<TcGemmOp> tc;         // tensor-core lowering, when algo == TNC_ALGO_TC
 };
 
@@ -364,6 +366,15 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
             }
             op.koff_a = append(ka.data(), nk * sizeof(uint32_t));
             op.koff_b = append(kb.data(), nk * sizeof(uint32_t));
+            if (e.algo == TNC_ALGO_STEM && e.rows_a >= 0) {
+                const std::vector<int32_t>& ra = plan->tables[e.rows_a];
+                std::vector<int32_t> seg;
+                for (int32_t i = 0; i < e.nb; ++i)
+                    if (i == 0 || ra[i] != ra[i - 1]) seg.push_back(i);
+                op.n_seg = (int)seg.size();
+                seg.push_back(e.nb);
+                op.seg_off = append(seg.data(), seg.size() * sizeof(int32_t));
+            }
         }
     plan->leaves_off = append(plan->leaves.data(), plan->leaves.size() * sizeof(LeafDev));
     if (blob.empty()) blob.resize(256);
@@ -420,7 +431,8 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
                 plan->last_launches += 1;
                 if (e.algo == TNC_ALGO_SKINNY)
                     return launch_skinny(e, plan->tc_precision, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st);
-                return launch_stem(e, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st);
+                const int32_t* seg = op.seg_off >= 0 ? (const int32_t*)(plan->dev_blob + op.seg_off) : nullptr;
+                return launch_stem(e, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, seg, op.n_seg, st);
             }
             SimtEinsumParams p{};
             p.a = ws + e.a.offset;

@@ -47,8 +47,11 @@ int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s);
 // ---------------------------------------------------------------- streaming ("stem") einsum
 // HBM-bound steps: huge left operand, tiny right operand; output written as C[rows][m][n].
 bool stem_supported(const tnc_einsum& e, int dtype);
+// `dev_seg_begin` (n_seg + 1 batch indices, device) splits the batches into runs that share their
+// row of A (built by tnc_plan_finalize from the A-row table); nullptr: one run per batch, or a
+// single run when A has no rows.
 int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
-                const int32_t* dev_rows_b, cudaStream_t s);
+                const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s);
 
 // ---------------------------------------------------------------- streaming tensor-core ("skinny") einsum
 // Same operand shapes and output layout as the streaming kernel, multiplied on tcgen05 (skinny.cu).

@@ -369,6 +369,43 @@ def test_right_operand_rows_folded(dev, algo):
     assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(10, 3, 3), (9, 0, 2), (11, 2, 4), (8, 4, 1)])
+def test_stem_bulk_row_segments(dev, shape):
+    """Bulk-copy streaming kernel (m >= 8, k <= 4) on steps whose batches share rows of A: an
+    outer step that keeps a subset of the (A row, B row) pairs (contraction.py:265-268) and a
+    chunked batched step with gathered row pairs (:272-300).  The kernel reads each row of A once
+    per run of equal A-row indices; checked against einsum on the gathered operands."""
+    from artensor_b200 import ContractionPlan
+    from artensor_b200 import _native as N
+    m, n, k = shape
+    rng = np.random.RandomState(31 + m)
+    RA, RB = 5, 7
+    la, lk, ln = LETTERS[:m], LETTERS[m:m + k], LETTERS[m + k:m + k + n]
+    leaves = {0: _rnd(rng, RA, *[2] * (m + k)), 1: _rnd(rng, RB, *[2] * (k + n))}
+    a128, b128 = leaves[0].numpy().astype(np.complex128), leaves[1].numpy().astype(np.complex128)
+    shapes = {i: tuple(v.shape) for i, v in leaves.items()}
+    # outer step, 17 of the 35 row pairs kept (sorted, A-major)
+    keep = np.sort(rng.choice(RA * RB, 17, replace=False))
+    eq = f"Y{la}{lk},Z{lk}{ln}->YZ{la}{ln}"
+    step = ((0, 1), eq, [[torch.from_numpy(keep)], []], tuple([-1] + [2] * (m + n)), tuple([len(keep)] + [2] * (m + n)))
+    plan = ContractionPlan([step], shapes, True, options=force_options("stem"))
+    assert plan.step_algo == [N.TNC_ALGO_STEM]
+    got = _execute(dev, plan, leaves)
+    full = np.einsum(eq, a128, b128).reshape((RA * RB,) + (2,) * (m + n))
+    want = full[keep]
+    assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 2e-6
+    # batched step: 12 gathered row pairs in two chunks, A rows repeated and unsorted
+    ia = torch.tensor([0, 0, 0, 3, 3, 1, 4, 4, 4, 4, 2, 0])
+    ib = torch.tensor([6, 1, 2, 2, 5, 0, 3, 4, 6, 0, 1, 5])
+    eq = f"X{la}{lk},X{lk}{ln}->X{la}{ln}"
+    step = ((0, 1), eq, [[ia[:6], ia[6:]], [ib[:6], ib[6:]]], None, tuple([12] + [2] * (m + n)))
+    plan = ContractionPlan([step], shapes, True, options=force_options("stem"))
+    assert plan.step_algo == [N.TNC_ALGO_STEM]
+    got = _execute(dev, plan, leaves)
+    want = np.einsum(eq, a128[ia.numpy()], b128[ib.numpy()])
+    assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 2e-6
+
+
 def _execute(dev, plan, leaves):
     blob = plan.pack_leaves({i: v.to(dev) for i, v in leaves.items()})
     out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)

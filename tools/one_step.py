@@ -32,12 +32,22 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--shuffle", action="store_true", help="shuffled mode order (default: A = [m][k], B = [k][n])")
+    ap.add_argument("--ka", default=None, help="comma-separated address-bit positions of the contracted bonds in A")
     a = ap.parse_args()
     rng = np.random.RandomState(a.seed)
     lm, ln, lk = LETTERS[:a.m], LETTERS[a.m:a.m + a.n], LETTERS[a.m + a.n:a.m + a.n + a.k]
     la, lb, lo = list(lm + lk), list(lk + ln), list(lm + ln)
     if a.shuffle:
         rng.shuffle(la), rng.shuffle(lb), rng.shuffle(lo)
+    if a.ka is not None:
+        pos = [int(x) for x in a.ka.split(",")]
+        assert len(pos) == a.k and len(set(pos)) == a.k and all(0 <= q < a.m + a.k for q in pos)
+        r = a.m + a.k
+        slots = [None] * r                          # slots[i] = mode at dim i; address bit = r - 1 - i
+        for ch, q in zip(lk, pos):
+            slots[r - 1 - q] = ch
+        rest = iter(lm)
+        la = [ch if ch is not None else next(rest) for ch in slots]
     eq = "".join(la) + "," + "".join(lb) + "->" + "".join(lo)
     extra = {} if a.precision is None else {"tc_precision": a.precision}
     opts = {"tc": PlanOptions(tc_min_flops=0, tc_min_intensity=0, skinny_min_elems=1 << 62, **extra),
