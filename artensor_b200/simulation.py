@@ -2,10 +2,12 @@
 
 `TensorNetworkSimulation.contraction` (simulation.py:90-117) and the copy of the slice loop in
 `tensor_network_contraction` (simulation.py:198-213) are replaced by one call into the native
-executor that walks the slice range on the GPU.  Everything symbolic -- circuit parsing,
-`_simplify`, the order search, the scheme compilers -- is the reference's own code, imported
-lazily from the `artensor` package and used unchanged (`prepare_contraction`, `update_scheme`).
-A simulation can also be rebuilt from a frozen case file (`from_case`), which needs no reference.
+executor that walks the slice range on the GPU.  Circuit parsing, `_simplify` and the order
+search are the reference's own code, imported lazily from the `artensor` package and used
+unchanged (`prepare_contraction`); the scheme is compiled from the reference's contraction tree by
+this package's own compilers (`scheme.py`, same tuple format; `scheme_compiler = "reference"`
+selects the reference's).  A simulation can also be rebuilt from a frozen case file
+(`from_case`), which needs no reference.
 
 Differences from the reference, all deliberate:
   * leaf slicing fixes every sliced bond of a tensor at once (the packaged loop mis-indexes
@@ -20,6 +22,7 @@ import numpy as np
 import torch
 
 from . import contraction as _c
+from . import scheme as _scheme
 from .backend import PlanOptions
 from .plan import SchemeError
 
@@ -83,9 +86,10 @@ class TensorNetworkSimulation:
         self.pattern = pattern
         self.max_bitstrings = max_bitstrings
         self.plan_options = PlanOptions()
+        self.scheme_compiler = "b200"      # or "reference": contraction.py:23-59 / :208-342 unchanged
         self._plan_cache = {}
 
-    # ---- planning: the reference's code, unchanged (simulation.py:47-88) ----
+    # ---- planning: the reference's order search, unchanged (simulation.py:47-88) ----
     def prepare_contraction(self, sc_target=30, trials=6, iters=20, betas=np.linspace(0.1, 10, 100),
                             slicing_repeat=4, start_seed=0, alpha=32.0):
         ref = _reference()
@@ -111,12 +115,17 @@ class TensorNetworkSimulation:
                 self.permute_dims = [0] + [dim + 1 for dim in self.permute_dims]
 
     def update_scheme(self, sc_target=30, bitstrings=[]):
-        ref = _reference()
+        """simulation.py:79-88.  The tree is compiled by artensor_b200.scheme (layout-friendly mode
+        orders, reproducible strings, chunking that covers every row: SURVEY.md 4.3-B2/B5) unless
+        `scheme_compiler == "reference"`."""
+        if self.scheme_compiler not in ("b200", "reference"):
+            raise ValueError(f"scheme_compiler {self.scheme_compiler!r}: expected 'b200' or 'reference'")
+        comp = _scheme if self.scheme_compiler == "b200" else _reference()
         if self.pattern == 'normal':
-            self.scheme, self.output_bonds = ref.contraction_scheme(deepcopy(self.ctree))
+            self.scheme, self.output_bonds = comp.contraction_scheme(deepcopy(self.ctree))
             self.tensor_contraction_func = _c.tensor_contraction
         else:
-            self.scheme, self.output_bonds, self.bitstrings_sorted = ref.contraction_scheme_sparse(
+            self.scheme, self.output_bonds, self.bitstrings_sorted = comp.contraction_scheme_sparse(
                 deepcopy(self.ctree), bitstrings, sc_target=sc_target)
             self.tensor_contraction_func = _c.tensor_contraction_sparse
             assert len(self.bitstrings_sorted) <= self.max_bitstrings

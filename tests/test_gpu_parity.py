@@ -46,7 +46,8 @@ def sim_from(name):
     return case, exp, TensorNetworkSimulation.from_case(case)
 
 
-SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10"]
+SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10",
+         "n12_full_own", "n12_sparse100_sc8_own"]   # _own: scheme compiled by artensor_b200/scheme.py
 
 
 @pytest.mark.parametrize("name", SMALL)

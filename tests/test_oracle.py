@@ -7,7 +7,8 @@ import pytest
 from conftest import load_golden
 from oracle import tn_oracle as O
 
-SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10"]
+SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10",
+         "n12_full_own", "n12_sparse100_sc8_own"]   # _own: scheme compiled by artensor_b200/scheme.py
 
 # tests/test_circuits.py:25-31 of the reference
 KAT_N12 = {

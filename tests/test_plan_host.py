@@ -15,7 +15,8 @@ from artensor_b200.plan import SchemeParser, parse_eq
 from oracle import tn_oracle as O
 import emulate
 
-SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10"]
+SMALL = ["n12_full", "n12_sparse5", "n12_sparse64_sc9", "n12_sparse100_sc8", "n12_sparse256c_sc10",
+         "n12_full_own", "n12_sparse100_sc8_own"]   # _own: scheme compiled by artensor_b200/scheme.py
 
 
 def make_plan(case, **kw):

@@ -141,6 +141,10 @@ CONFIGS = {
     "n12_sparse64_sc9": (n12_qsim, lambda: random_bitstrings(12, 64, 1), dict(sc_target=9, trials=4, iters=10), None, True),
     "n12_sparse100_sc8": (n12_qsim, lambda: random_bitstrings(12, 100, 2), dict(sc_target=8, trials=4, iters=10), None, True),
     "n12_sparse256c_sc10": (n12_qsim, lambda: correlated_bitstrings(12, 8, 3), dict(sc_target=10, trials=4, iters=10), None, True),
+    # "_own": the scheme is compiled from the reference's contraction tree by artensor_b200/scheme.py
+    # (SURVEY.md 8-f1); the expected outputs are still the REFERENCE executor's, run on that scheme
+    "n12_full_own": (n12_qsim, lambda: [], dict(sc_target=30, trials=4, iters=10), None, True),
+    "n12_sparse100_sc8_own": (n12_qsim, lambda: random_bitstrings(12, 100, 2), dict(sc_target=8, trials=4, iters=10), None, True),
     "n30_sparse64_sc26": (n30_qsim, lambda: google_amplitudes(64)[0], dict(sc_target=26, trials=4, iters=5), None, False),
     "n30_full": (n30_qsim, lambda: [], dict(sc_target=30, trials=4, iters=5), [0], False),
     "n30_sparse10000": (n30_qsim, lambda: google_amplitudes(10000)[0], dict(sc_target=30, trials=4, iters=5), [0], False),
@@ -176,7 +180,12 @@ def build(name):
     bitstrings = bits_fn()
     if not os.path.exists(case_path):
         t0 = time.time()
-        sim = TensorNetworkSimulation.from_circuit_file(circ_fn(), bitstrings)
+        if name.endswith("_own"):
+            from artensor_b200 import TensorNetworkSimulation as OwnSimulation
+            sim = OwnSimulation.from_circuit_file(circ_fn(), bitstrings)
+            assert sim.scheme_compiler == "b200"
+        else:
+            sim = TensorNetworkSimulation.from_circuit_file(circ_fn(), bitstrings)
         sim.prepare_contraction(slicing_repeat=1, start_seed=0, **prep)
         validate_scheme(sim.scheme, sim.pattern)
         print(f"[{name}] order search {time.time() - t0:.1f}s; steps={len(sim.scheme)} "
