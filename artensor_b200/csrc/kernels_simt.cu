@@ -83,6 +83,62 @@ __global__ void __launch_bounds__(kThreads) simt_einsum_kernel(SimtEinsumParams 
     }
 }
 
+// ------------------------------------------------------------------ chain of tiny einsums
+// The same arithmetic as simt_einsum_kernel for a run of consecutive tiny steps, in one launch:
+// one CTA of 1024 threads walks the run, `__syncthreads()` between steps makes a step's outputs
+// (global memory, written by this CTA) visible to the next one.  Operands are read with ld.cg:
+// a step may read what an earlier step of the same launch wrote, so the non-coherent path is out.
+constexpr int kChainThreads = 1024;
+__global__ void __launch_bounds__(kChainThreads) simt_chain_kernel(const ChainStep* __restrict__ steps, int n, char* ws,
+                                                                   const char* __restrict__ blob) {
+    __shared__ ChainStep p;
+    static_assert(sizeof(ChainStep) % 4 == 0, "copied word by word");
+    for (int s = 0; s < n; ++s) {
+        __syncthreads();                       // the previous step is complete and nobody reads `p` any more
+        for (int w = threadIdx.x; w < (int)(sizeof(ChainStep) / 4); w += kChainThreads)
+            ((uint32_t*)&p)[w] = ((const uint32_t*)(steps + s))[w];
+        __syncthreads();
+        const float2* A = (const float2*)(ws + p.a_off);
+        const float2* B = (const float2*)(ws + p.b_off);
+        float2* C = (float2*)(ws + p.c_off);
+        const int32_t* rows_a = (const int32_t*)(blob + p.rows_a_off);
+        const int32_t* rows_b = (const int32_t*)(blob + p.rows_b_off);
+        const uint32_t* koff_a = (const uint32_t*)(blob + p.koff_a_off);
+        const uint32_t* koff_b = (const uint32_t*)(blob + p.koff_b_off);
+        const uint32_t cmask = p.rank_c >= 32 ? 0xffffffffu : ((1u << p.rank_c) - 1u);
+        const uint32_t nk = 1u << p.kb;
+        for (int64_t e = threadIdx.x; e < p.total; e += kChainThreads) {
+            const int64_t row = e >> p.rank_c;
+            const uint32_t cb = (uint32_t)e & cmask;
+            uint32_t oa = 0, ob = 0;
+            for (int q = 0; q < p.rank_c; ++q) {
+                const uint32_t bit = (cb >> q) & 1u;
+                const int pa = p.c2a[q], pb = p.c2b[q];
+                if (pa >= 0) oa |= bit << pa;
+                if (pb >= 0) ob |= bit << pb;
+            }
+            int64_t ra = 0, rb = 0;
+            if (p.rows_mode_a == TNC_ROWS_IDENTITY) ra = row;
+            else if (p.rows_mode_a >= 0) ra = __ldg(rows_a + row);          // the plan's tables never change: cached path
+            if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = row;
+            else if (p.rows_mode_b >= 0) rb = __ldg(rows_b + row);
+            const float2* a = A + (ra << p.rank_a) + oa;
+            const float2* b = B + (rb << p.rank_b) + ob;
+            float cr = 0.f, ci = 0.f;
+#pragma unroll 4
+            for (uint32_t k = 0; k < nk; ++k) {
+                const float2 x = __ldcg(a + __ldg(koff_a + k));
+                const float2 y = __ldcg(b + __ldg(koff_b + k));
+                cr = fmaf(x.x, y.x, cr);
+                cr = fmaf(-x.y, y.y, cr);
+                ci = fmaf(x.x, y.y, ci);
+                ci = fmaf(x.y, y.x, ci);
+            }
+            C[e] = make_float2(cr, ci);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ leaf slicing
 // One block per leaf; leaves are tiny (rank <= ~6).  dst[r][e] = src[r][deposit(e) | fixed].
 template <typename T>
@@ -151,6 +207,13 @@ int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
     const int grid = grid_for(p.total);
     if (dtype == TNC_C64) simt_einsum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
     else simt_einsum_kernel<__half2><<<grid, kThreads, 0, s>>>(p);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
+int launch_simt_chain(const ChainStep* dev_steps, int n, void* workspace, const void* dev_blob, cudaStream_t s) {
+    if (n <= 0) return TNC_OK;
+    simt_chain_kernel<<<1, kChainThreads, 0, s>>>(dev_steps, n, (char*)workspace, (const char*)dev_blob);
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cstdlib>
 #include <memory>
 
 #include "tnc_internal.h"
@@ -37,6 +38,8 @@ struct Op {
     int64_t koff_a = -1, koff_b = -1;     // byte offsets into the device blob
     int64_t seg_off = -1;                 // streaming kernel: runs of batches sharing their row of A
     int n_seg = 0;
+    int chain_len = 0;                    // > 1: head of a run of tiny generic steps executed by one launch; -1: member
+    int64_t chain_off = -1;               // the run's ChainStep records in the device blob
     std::shared_ptr<TcGemmOp> tc;         // tensor-core lowering, when algo == TNC_ALGO_TC
 };
 
@@ -376,6 +379,53 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
                 op.seg_off = append(seg.data(), seg.size() * sizeof(int32_t));
             }
         }
+    // runs of consecutive tiny generic steps -> one chain launch each
+    static const bool no_chain = getenv("TNC_NO_CHAIN") != nullptr;       // measurement aid
+    auto chainable = [&](const Op& op) {
+        if (no_chain || plan->dtype != TNC_C64 || op.kind != OP_EINSUM || op.e.algo != TNC_ALGO_SIMT) return false;
+        const int64_t total = (int64_t)op.e.nb << op.e.c.rank;
+        return total <= kChainMaxOutputs && (total << op.e.n_k) <= kChainMaxMacs;
+    };
+    for (int ph = 0; ph < 2; ++ph) {
+        auto& ops = plan->ops[ph];
+        for (size_t i = 0; i < ops.size();) {
+            size_t j = i;
+            while (j < ops.size() && chainable(ops[j])) ++j;
+            if (j - i >= 2) {
+                std::vector<ChainStep> recs;
+                for (size_t t = i; t < j; ++t) {
+                    const tnc_einsum& e = ops[t].e;
+                    ChainStep c{};
+                    c.a_off = e.a.offset;
+                    c.b_off = e.b.offset;
+                    c.c_off = e.c.offset;
+                    c.rows_mode_a = e.rows_a;
+                    c.rows_mode_b = e.rows_b;
+                    c.rows_a_off = e.rows_a >= 0 ? plan->table_off[e.rows_a] : 0;
+                    c.rows_b_off = e.rows_b >= 0 ? plan->table_off[e.rows_b] : 0;
+                    c.koff_a_off = ops[t].koff_a;
+                    c.koff_b_off = ops[t].koff_b;
+                    c.total = (int64_t)e.nb << e.c.rank;
+                    c.rank_a = e.a.rank;
+                    c.rank_b = e.b.rank;
+                    c.rank_c = e.c.rank;
+                    c.kb = e.n_k;
+                    for (int q = 0; q < TNC_MAX_BITS; ++q) c.c2a[q] = c.c2b[q] = -1;
+                    for (int q = 0; q < e.n_m; ++q) c.c2a[e.m_c[q]] = e.m_a[q];
+                    for (int q = 0; q < e.n_n; ++q) c.c2b[e.n_c[q]] = e.n_b[q];
+                    for (int q = 0; q < e.n_h; ++q) {
+                        c.c2a[e.h_c[q]] = e.h_a[q];
+                        c.c2b[e.h_c[q]] = e.h_b[q];
+                    }
+                    recs.push_back(c);
+                    ops[t].chain_len = -1;
+                }
+                ops[i].chain_len = (int)(j - i);
+                ops[i].chain_off = append(recs.data(), recs.size() * sizeof(ChainStep));
+            }
+            i = j > i ? j : i + 1;
+        }
+    }
     plan->leaves_off = append(plan->leaves.data(), plan->leaves.size() * sizeof(LeafDev));
     if (blob.empty()) blob.resize(256);
     TNC_CUDA(cudaMalloc((void**)&plan->dev_blob, blob.size()));
@@ -419,6 +469,11 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
         }
         case OP_EINSUM: {
             const tnc_einsum& e = op.e;
+            if (op.chain_len < 0) return TNC_OK;                 // ran with the head of its chain
+            if (op.chain_len > 1) {
+                plan->last_launches += 1;
+                return launch_simt_chain((const ChainStep*)(plan->dev_blob + op.chain_off), op.chain_len, ws, plan->dev_blob, st);
+            }
             if (op.tc) {
                 int launches = 0;
                 int rc = tc_gemm_run(op.tc.get(), ws, st, hook, hook_ctx, &launches);

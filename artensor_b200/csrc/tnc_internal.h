@@ -44,6 +44,23 @@ struct SimtEinsumParams {
 };
 int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s);
 
+// A run of consecutive tiny generic steps executed by ONE launch (one CTA walks the run, a block
+// barrier between steps) instead of one ~6 us launch per step.  Records live in the plan's device
+// blob; operand addresses are offsets into the workspace given at execute time.
+struct ChainStep {
+    int64_t a_off, b_off, c_off;               // bytes into the workspace
+    int64_t rows_a_off, rows_b_off;            // bytes into the device blob (unused for NONE / IDENTITY)
+    int64_t koff_a_off, koff_b_off;            // bytes into the device blob
+    int64_t total;                             // nb << rank_c
+    int32_t rows_mode_a, rows_mode_b;
+    int32_t rank_a, rank_b, rank_c, kb;
+    int8_t c2a[TNC_MAX_BITS];
+    int8_t c2b[TNC_MAX_BITS];
+};
+constexpr int64_t kChainMaxOutputs = 1 << 13;  // per step
+constexpr int64_t kChainMaxMacs = 1 << 19;     // per step (outputs << contracted bits)
+int launch_simt_chain(const ChainStep* dev_steps, int n, void* workspace, const void* dev_blob, cudaStream_t s);
+
 // ---------------------------------------------------------------- streaming ("stem") einsum
 // HBM-bound steps: huge left operand, tiny right operand; output written as C[rows][m][n].
 bool stem_supported(const tnc_einsum& e, int dtype);
