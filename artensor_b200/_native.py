@@ -9,7 +9,7 @@ import os
 
 TNC_MAX_BITS = 40
 TNC_MAX_SLICED = 8
-TNC_ABI_VERSION = 4
+TNC_ABI_VERSION = 5
 TNC_PROFILE_SLOTS = 4
 
 TNC_C64, TNC_C32 = 0, 1
@@ -17,6 +17,7 @@ TNC_PHASE_ONCE, TNC_PHASE_SLICE = 0, 1
 TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM, TNC_ALGO_SKINNY = 0, 1, 2, 3
 TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
 TNC_EINSUM_OUTER_ROWS = 1
+TNC_EINSUM_OUTER_PAIRS = 2
 TNC_TC_3XTF32, TNC_TC_3XF16, TNC_TC_F16 = 0, 1, 2
 TNC_OPT_TC_PRECISION = 0
 TC_PRECISIONS = {"3xtf32": TNC_TC_3XTF32, "3xf16": TNC_TC_3XF16, "f16": TNC_TC_F16}

@@ -122,7 +122,7 @@ def tc_scratch_bytes(st: Step):
     al = lambda x: (x + 1023) // 1024 * 1024
     nb_a = st.nb if st.ra is not None else 1
     nb_b = st.nb if st.rb is not None else 1
-    if full_outer(st):
+    if full_outer(st) or outer_pairs(st):
         nb_a, nb_b = st.a.rows, st.b.rows
     a_panel = al((nb_a << (len(st.m_modes) + len(st.k_modes))) * 8)
     b_panel = al((nb_b << (len(st.n_modes) + len(st.k_modes))) * 16)
@@ -134,6 +134,19 @@ def full_outer(st: Step):
     return (st.kind == "outer" and st.a.rows is not None and st.b.rows is not None and
             st.nb == st.a.rows * st.b.rows and np.array_equal(st.ra, np.arange(st.nb) // st.b.rows) and
             np.array_equal(st.rb, np.arange(st.nb) % st.b.rows))
+
+
+def outer_pairs(st: Step):
+    """A step whose output rows are every (row of A, row of B) pair exactly once, in an order other
+    than A-major: the reference's batched ("cat") steps when the wanted bitstrings are the full
+    product of the operands' rows (contraction.py:272-300 sorts the pairs by the row of the larger
+    operand).  TNC_EINSUM_OUTER_PAIRS lets the tensor-core path pack each operand row once."""
+    if st.ra is None or st.rb is None or st.a.rows is None or st.b.rows is None or st.nb < 2:
+        return False
+    if st.nb != st.a.rows * st.b.rows or full_outer(st):
+        return False
+    pair = np.asarray(st.ra, dtype=np.int64) * st.b.rows + np.asarray(st.rb, dtype=np.int64)
+    return len(np.unique(pair)) == st.nb
 
 
 def tc_eligible(st: Step, precision="3xtf32"):
@@ -430,7 +443,7 @@ class ContractionPlan:
         e.h_b = N.bits(B.pos[m] for m in st.h_modes_b)
         e.h_c = N.bits(Cb.pos[m] for m in st.h_modes)
         e.algo = algo
-        e.flags = N.TNC_EINSUM_OUTER_ROWS if full_outer(st) else 0
+        e.flags = N.TNC_EINSUM_OUTER_ROWS if full_outer(st) else (N.TNC_EINSUM_OUTER_PAIRS if outer_pairs(st) else 0)
         return e
 
     def _build_native(self, ops):

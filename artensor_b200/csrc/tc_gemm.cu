@@ -740,6 +740,7 @@ struct GemmArgs {
     int32_t blocked_b;        // B' panel likewise
     int32_t n_inner;          // outer-rows step with B's rows folded into N: real columns per row of B (0 = not folded)
     int32_t outer_rj, outer_mb;   // outer-rows step: batch = row of B, GEMM row = (row of A, m): see c_row()
+    const int32_t* pair_rows;     // OUTER_PAIRS: C row block of the pair (ra * outer_rj + rb); nullptr: the pair index itself
     int32_t sync_every;       // k-blocks between grid-wide lockstep barriers (0 = none)
     uint32_t* sync_counter;   // zeroed before the launch
     const uint32_t* amax;     // fp16 precisions: amax words of A and B (the epilogue undoes their scaling)
@@ -766,7 +767,9 @@ __device__ __forceinline__ bool lockstep_barrier(uint32_t* counter, uint32_t tar
 __device__ __forceinline__ int64_t c_row(const GemmArgs& g, int batch, int row) {
     if (g.outer_rj == 0) return (int64_t)batch * g.M + row;
     const int64_t ra = row >> g.outer_mb;
-    return ((ra * g.outer_rj + batch) << g.outer_mb) + (row & ((1 << g.outer_mb) - 1));
+    int64_t pair = ra * g.outer_rj + batch;
+    if (g.pair_rows) pair = g.pair_rows[pair];
+    return (pair << g.outer_mb) + (row & ((1 << g.outer_mb) - 1));
 }
 
 struct TileCoord {
@@ -1384,7 +1387,7 @@ int shape_of(const tnc_einsum& e, Shape* sh) {
         return TNC_ERR_INVALID;
     }
     sh->batch = sh->fold_rows ? 1 : e.nb;
-    sh->outer = (e.flags & TNC_EINSUM_OUTER_ROWS) && e.nb > 1 && !sh->fold_rows;
+    sh->outer = (e.flags & (TNC_EINSUM_OUTER_ROWS | TNC_EINSUM_OUTER_PAIRS)) && e.nb > 1 && !sh->fold_rows;
     sh->n_inner = 0;
     if (sh->outer) {          // A's rows extend M, B's rows are the batch: nothing is gathered twice
         sh->nb_a = e.a.rows;
@@ -1425,7 +1428,7 @@ int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype) {
 }
 
 int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
-                   TcGemmOp** out) {
+                   const int32_t* dev_pair_rows, TcGemmOp** out) {
     const int64_t need = tc_gemm_scratch_bytes(e, dtype);
     if (need < 0) return TNC_ERR_UNSUPPORTED;
     if (e.scratch_bytes < need || (e.scratch_offset & 1023)) {
@@ -1518,6 +1521,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     GemmArgs& g = op->args;
     g.c_batch_stride = sh.M * sh.N;
     g.outer_rj = sh.outer ? (int32_t)sh.nb_b : 0;
+    g.pair_rows = (sh.outer && (e.flags & TNC_EINSUM_OUTER_PAIRS)) ? dev_pair_rows : nullptr;
     g.outer_mb = e.n_m;
     g.ldc = (int32_t)(sh.n_inner ? sh.n_inner : sh.N);
     g.n_inner = sh.n_inner;

@@ -18,7 +18,9 @@ int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype);
 
 // `dev_rows_a` / `dev_rows_b`: device copies of the row tables (nullptr unless rows_* >= 0).
 // `precision` is a tnc_tc_precision.
+// `dev_pair_rows` (TNC_EINSUM_OUTER_PAIRS only): device table, C row block of the pair (ra * b.rows + rb)
 int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
+                   const int32_t* dev_pair_rows,
                    TcGemmOp** out);
 int tc_gemm_run(TcGemmOp* op, char* workspace, cudaStream_t s, LaunchHook hook, void* ctx, int* launches);
 void tc_gemm_destroy(TcGemmOp* op);

@@ -38,6 +38,7 @@ struct Op {
     int64_t koff_a = -1, koff_b = -1;     // byte offsets into the device blob
     int64_t seg_off = -1;                 // streaming kernel: runs of batches sharing their row of A
     int n_seg = 0;
+    int pair_table = -1;                  // OUTER_PAIRS: plan table with the C row block of every (A row, B row) pair
     int chain_len = 0;                    // > 1: head of a run of tiny generic steps executed by one launch; -1: member
     int64_t chain_off = -1;               // the run's ChainStep records in the device blob
     std::shared_ptr<TcGemmOp> tc;         // tensor-core lowering, when algo == TNC_ALGO_TC
@@ -261,6 +262,22 @@ int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* e) {
             return TNC_ERR_INVALID;
         }
     }
+    std::vector<int32_t> pair_rows;
+    if (e->flags & TNC_EINSUM_OUTER_PAIRS) {
+        bool ok = (int64_t)e->a.rows * e->b.rows == e->nb && e->rows_a != TNC_ROWS_NONE && e->rows_b != TNC_ROWS_NONE &&
+                  !(e->flags & TNC_EINSUM_OUTER_ROWS);
+        if (ok) pair_rows.assign((size_t)e->nb, -1);
+        for (int i = 0; ok && i < e->nb; ++i) {
+            const int ra = e->rows_a >= 0 ? plan->tables[e->rows_a][i] : i;
+            const int rb = e->rows_b >= 0 ? plan->tables[e->rows_b][i] : i;
+            ok = ra < e->a.rows && rb < e->b.rows && pair_rows[(size_t)ra * e->b.rows + rb] < 0;
+            if (ok) pair_rows[(size_t)ra * e->b.rows + rb] = i;
+        }
+        if (!ok) {
+            set_error("einsum: TNC_EINSUM_OUTER_PAIRS set but the rows are not every (A row, B row) pair exactly once");
+            return TNC_ERR_INVALID;
+        }
+    }
     if (e->algo != TNC_ALGO_SIMT && e->algo != TNC_ALGO_TC && e->algo != TNC_ALGO_STEM && e->algo != TNC_ALGO_SKINNY) {
         set_error("einsum: unknown algo %d", e->algo);
         return TNC_ERR_INVALID;
@@ -279,6 +296,10 @@ int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* e) {
     Op op;
     op.kind = OP_EINSUM;
     op.e = *e;
+    if (!pair_rows.empty()) {
+        plan->tables.push_back(pair_rows);
+        op.pair_table = (int)plan->tables.size() - 1;
+    }
     plan->ops[phase].push_back(op);
     return TNC_OK;
 }
@@ -441,7 +462,8 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
                 return TNC_ERR_NOMEM;
             }
             TcGemmOp* tc = nullptr;
-            int rc = tc_gemm_create(op.e, plan->dtype, plan->tc_precision, ra, rb, &tc);
+            const int32_t* pairs = op.pair_table >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[op.pair_table]) : nullptr;
+            int rc = tc_gemm_create(op.e, plan->dtype, plan->tc_precision, ra, rb, pairs, &tc);
             if (rc != TNC_OK) return rc;
             op.tc.reset(tc, tc_gemm_destroy);
         }

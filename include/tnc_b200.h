@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TNC_ABI_VERSION 4
+#define TNC_ABI_VERSION 5
 #define TNC_MAX_BITS 40          /* max bit modes per group / per tensor */
 #define TNC_MAX_SLICED 8         /* max sliced bonds on one leaf */
 
@@ -80,6 +80,13 @@ typedef enum tnc_algo {
  * artensor/contraction.py:180-185).  The row tables must say the same; the flag lets the
  * tensor-core path fold A's rows into M and loop over B's rows instead of gathering copies. */
 #define TNC_EINSUM_OUTER_ROWS 1
+/* OUTER_PAIRS: the output rows enumerate ALL pairs of operand rows exactly once, in the order the
+ * row tables give (the reference's chunked batched steps whose wanted bitstrings are the full
+ * product of the operands' rows, artensor/contraction.py:272-300: sorted by the row of the larger
+ * operand, not A-major).  The tensor-core path then packs every operand row ONCE, folds A's rows
+ * into M and B's rows into N, and scatters the row blocks of C through the inverse of the tables;
+ * without the flag the same step gathers a.rows * b.rows copies of the operand rows. */
+#define TNC_EINSUM_OUTER_PAIRS 2
 
 /* Row table ids: a plan-owned int32 table (tnc_plan_add_table) or one of these. */
 #define TNC_ROWS_NONE (-1)       /* operand has no row mode: always block 0 */

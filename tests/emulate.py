@@ -83,6 +83,10 @@ def run_plan(plan, leaf_blob, slice_ids):
                 return plan.tables[mode].astype(np.int64)[row]
             if E.flags & N.TNC_EINSUM_OUTER_ROWS:
                 assert np.array_equal(rows(E.rows_a), row // E.b.rows) and np.array_equal(rows(E.rows_b), row % E.b.rows)
+            if E.flags & N.TNC_EINSUM_OUTER_PAIRS:      # every (A row, B row) pair exactly once, any order
+                assert E.nb == E.a.rows * E.b.rows and not (E.flags & N.TNC_EINSUM_OUTER_ROWS)
+                pairs = (rows(E.rows_a) * E.b.rows + rows(E.rows_b))[::1 << E.c.rank]
+                assert len(np.unique(pairs)) == E.nb
             oa += rows(E.rows_a) << E.a.rank
             ob += rows(E.rows_b) << E.b.rank
             k = np.arange(1 << E.n_k, dtype=np.int64)

@@ -407,6 +407,31 @@ def test_stem_bulk_row_segments(dev, shape):
     assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 2e-6
 
 
+@pytest.mark.parametrize("algo", ["tc", "tc:3xtf32", "stem", "skinny", "simt"])
+def test_batched_step_over_all_row_pairs(dev, algo):
+    """A chunked batched step whose gathered pairs are every (row of A, row of B) pair exactly
+    once, in a scrambled order (contraction.py:272-300 when the wanted bitstrings are the full
+    product): TNC_EINSUM_OUTER_PAIRS.  The tensor-core path packs each operand row once and
+    scatters the row blocks of C through the inverse table; the other kernels use the tables."""
+    from artensor_b200 import ContractionPlan
+    from artensor_b200 import _native as N
+    from artensor_b200.backend import outer_pairs
+    rng = np.random.RandomState(19)
+    m, k, n, RA, RB = 9, 4, 5, 6, 4
+    la, lk, ln = LETTERS[:m], LETTERS[m:m + k], LETTERS[m + k:m + k + n]
+    leaves = {0: _rnd(rng, RA, *[2] * (m + k)), 1: _rnd(rng, RB, *[2] * (k + n))}
+    order = rng.permutation(RA * RB)
+    ia, ib = torch.from_numpy(order // RB), torch.from_numpy(order % RB)
+    eq = f"X{la}{lk},X{lk}{ln}->X{la}{ln}"
+    step = ((0, 1), eq, [[ia[:10], ia[10:]], [ib[:10], ib[10:]]], None, tuple([RA * RB] + [2] * (m + n)))
+    opts = force_options(*algo.split(":"))
+    plan = ContractionPlan([step], {i: tuple(v.shape) for i, v in leaves.items()}, True, options=opts)
+    assert outer_pairs(plan.steps[0]) and plan.ops[N.TNC_PHASE_ONCE][-1][1].flags == N.TNC_EINSUM_OUTER_PAIRS
+    got = _execute(dev, plan, leaves)
+    want = np.einsum(eq, leaves[0].numpy().astype(np.complex128)[ia.numpy()], leaves[1].numpy().astype(np.complex128)[ib.numpy()])
+    assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 1e-5
+
+
 def _execute(dev, plan, leaves):
     blob = plan.pack_leaves({i: v.to(dev) for i, v in leaves.items()})
     out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)

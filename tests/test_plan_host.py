@@ -265,3 +265,28 @@ def test_operand_swap_keeps_results():
     got = emulate.run_plan(plan, plan.pack_leaves(leaves).numpy(), [0]).reshape(plan.out_shape)
     want = np.einsum(eq, leaves[0].numpy().astype(np.complex128), leaves[1].numpy().astype(np.complex128))
     assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+
+
+def test_outer_pairs_detection_and_native_validation():
+    """backend.outer_pairs: every (A row, B row) pair exactly once in any order but A-major."""
+    from artensor_b200.backend import outer_pairs, full_outer
+    rng = np.random.RandomState(2)
+    RA, RB, m, k, n = 3, 4, 3, 2, 2
+    L = "abcdefghijkl"
+    la, lk, ln = L[:m], L[m:m + k], L[m + k:m + k + n]
+    shapes = {0: (RA,) + (2,) * (m + k), 1: (RB,) + (2,) * (k + n)}
+    eq = f"X{la}{lk},X{lk}{ln}->X{la}{ln}"
+
+    def plan_for(ia, ib):
+        step = ((0, 1), eq, [[torch.as_tensor(ia)], [torch.as_tensor(ib)]], None, tuple([len(ia)] + [2] * (m + n)))
+        return ContractionPlan([step], shapes, True, build_native=False)
+    order = rng.permutation(RA * RB)
+    p = plan_for(order // RB, order % RB)
+    assert outer_pairs(p.steps[0]) and not full_outer(p.steps[0])
+    assert p.ops[N.TNC_PHASE_ONCE][-1][1].flags == N.TNC_EINSUM_OUTER_PAIRS
+    got = emulate.run_plan(p, np.arange(p.leaf_blob_elems).astype(np.complex64), [0])   # the emulator checks the flag's contract
+    assert got.shape[0] == RA * RB
+    sub = order[:-1]
+    assert not outer_pairs(plan_for(sub // RB, sub % RB).steps[0])                      # a pair missing
+    dup = np.concatenate([order[:-1], order[:1]])
+    assert not outer_pairs(plan_for(dup // RB, dup % RB).steps[0])                      # a pair twice
