@@ -36,9 +36,18 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when the
-# environment sets NCCL_DEBUG) goes to stderr
+# stdout carries exactly one JSON line.  NCCL prints its banner ("NCCL version ...") with a plain
+# printf to file descriptor 1 whatever NCCL_DEBUG_FILE says, so descriptor 1 is pointed at stderr
+# for the whole run and the JSON line is written to a saved copy of the real stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -223,7 +232,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def plan_of(case, tc_min_flops, build_native=True):
@@ -491,7 +500,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "breakdown": breakdown,
             "cpu_baseline": cpu, "half_mode": half,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
