@@ -62,13 +62,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp is descheduled until the phase completes or the hint
+// (nanoseconds) runs out, instead of re-issuing the poll back to back.
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
 // A wait that cannot complete is a protocol bug: trap after ~2 s instead of hanging the GPU.
+// Waiting warps must not eat issue slots (the streaming kernels are issue-bound: ncu showed 20 % of
+// the executed instructions in this loop when it polled back to back and read the clock on every
+// iteration) nor power (the GEMM's epilogue warps wait most of the time, under a power cap).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
     uint32_t polls = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    long long t0 = 0;
+    while (!mbar_try_wait_suspend(bar, parity, 2000u)) {
+        if ((++polls & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
