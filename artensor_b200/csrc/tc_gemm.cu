@@ -1531,6 +1531,10 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     g.m_tiles = (int32_t)((sh.M + BM - 1) / BM);
     g.n_tiles = (int32_t)((sh.N + op->bn - 1) / op->bn);
     g.group_m = 16;
+    if (const char* env = getenv("TNC_TC_GROUP_M")) {  // experiment knob: row tiles per sweep group
+        const int v = atoi(env);
+        if (v >= 1 && v <= 1024) g.group_m = v;
+    }
     g.a_batched = op->a_batched;
     g.b_batched = op->b_batched;
     g.kc = kDefaultKC[precision];
