@@ -67,6 +67,10 @@ struct SkinnyParams {
     int32_t groups;                // active producer groups (<= kGroups, <= slots)
     int32_t fold;                  // rows of B folded into N (1 = none): accumulator columns [f * n_real, (f+1) * n_real)
                                    // of a tile are the outputs against row f of B and go to row block (batch * fold + f) of C
+    uint32_t koff_c[32];           // A offset of contracted index k inside one k-block: kernel parameters live in the
+                                   // constant bank, so with k unrolled the offset is an instruction operand (the shared-
+                                   // memory table cost an LDS + a 64-bit IMAD per 8-byte load: 6 instructions per load)
+    int64_t kblock_off;            // A offset of the second k-block (K = 64)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -243,32 +247,44 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                 }
             __syncwarp();
         }
-        for (int64_t j = (KB == 2 ? 0 : group);; j += (KB == 2 ? 1 : p.groups)) {
+        int64_t row_off[R];                                               // A offset of this thread's row bits (sub-tile i)
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int64_t rl = (int64_t)(i << 7) | row;
+            int64_t o = 0;
+            for (int t = 0; t < p.n_runs; ++t) o |= ((rl >> p.run_src[t]) & (int64_t)p.run_mask[t]) << p.run_dst[t];
+            row_off[i] = o;
+        }
+        // slot / use of tile number j without a division per tile: j advances by `step`
+        const int step = KB == 2 ? 1 : p.groups;
+        int slot = (KB == 2 ? 0 : group) % p.slots;
+        uint32_t use = (uint32_t)((KB == 2 ? 0 : group) / p.slots);
+        for (int64_t j = (KB == 2 ? 0 : group);; j += step) {
             const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
             if (idle || tile >= p.tiles) break;
-            const int slot = (int)(j % p.slots);
-            const uint32_t use = (uint32_t)(j / p.slots);
             const int64_t bidx = tile / tiles_per_batch;
             int64_t ra = 0;
             if (p.rows_mode_a == TNC_ROWS_IDENTITY) ra = bidx;
             else if (p.rows_mode_a >= 0) ra = p.rows_a[bidx];
             float2 av[R][KC];
+            // the tile's part of the A offset is the same for the R rows of a thread; the thread's own
+            // row bits (row_off) never change
+            const int64_t r0 = ((tile - bidx * tiles_per_batch) * R) << 7;
+            int64_t toff = (ra << p.rank_a) + (KB == 2 ? kb_mine * p.kblock_off : 0);
+            for (int t = 0; t < p.n_runs; ++t) toff |= ((r0 >> p.run_src[t]) & (int64_t)p.run_mask[t]) << p.run_dst[t];
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                const int64_t r = (((tile - bidx * tiles_per_batch) * R + i) << 7) | row;
-                int64_t aoff = ra << p.rank_a;
-                for (int t = 0; t < p.n_runs; ++t) aoff |= ((r >> p.run_src[t]) & (int64_t)p.run_mask[t]) << p.run_dst[t];
-                const float2* __restrict__ ap = p.a + aoff;
+                const float2* __restrict__ ap = p.a + (toff | row_off[i]);
                 if (KC >= 2 && p.a_vec) {
 #pragma unroll
                     for (int k = 0; k < KC; k += 2) {
-                        const float4 x = __ldg((const float4*)(ap + koff[kb_mine * KC + k]));
+                        const float4 x = __ldg((const float4*)(ap + p.koff_c[k]));
                         av[i][k] = make_float2(x.x, x.y);
                         av[i][k + 1] = make_float2(x.z, x.w);
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) av[i][k] = __ldg(ap + koff[kb_mine * KC + k]);
+                    for (int k = 0; k < KC; ++k) av[i][k] = __ldg(ap + p.koff_c[k]);
                 }
             }
             // the slot (shared memory tile, scales, TMEM accumulators) is free once the epilogue of
@@ -314,6 +330,11 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             // has arrived (KB == 2: the idle third group does, see below)
             if (KB == 1 && (warp & 3) == 0 && lane == 0) issue_mma(slot, use);
             __syncwarp();
+            slot += step;                                                 // step <= slots (groups <= slots)
+            if (slot >= p.slots) {
+                slot -= p.slots;
+                ++use;
+            }
         }
     } else {
         // ------------------------------------------------------------ epilogue
@@ -321,11 +342,15 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
         const uint32_t stage = stage0 + (uint32_t)q * 4096u;
         const float b_inv = f16_inv_scale(b_amax);
         const int n_real = 2 << p.nb;                                     // floats per output row
-        for (int64_t j = 0;; ++j) {
+        int slot = 0;
+        uint32_t use = 0;
+        for (int64_t j = 0;; ++j, ++slot) {
             const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
             if (tile >= p.tiles) break;
-            const int slot = (int)(j % p.slots);
-            const uint32_t use = (uint32_t)(j / p.slots);
+            if (slot == p.slots) {                                        // slot = j % slots, use = j / slots
+                slot = 0;
+                ++use;
+            }
             mbar_wait(full_bar(slot), use & 1u);                          // acquires the producers' row scales
             mbar_wait(done_bar(slot), use & 1u);
             tc_fence_after();
@@ -506,6 +531,12 @@ int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void*
     }
     for (int i = 0; i < e.n_n; ++i) p.n_b[e.n_c[i]] = e.n_b[i];
     p.a_vec = e.k_a[0] == 0;
+    for (int k = 0; k < 32; ++k) {
+        uint32_t o = 0;
+        for (int i = 0; i < e.n_k && i < 5; ++i) o |= ((uint32_t)(k >> i) & 1u) << e.k_a[i];
+        p.koff_c[k] = o;
+    }
+    p.kblock_off = e.n_k == 6 ? ((int64_t)1 << e.k_a[5]) : 0;
     // row bit j (output position n_n + j) -> A position; merge consecutive bits into runs
     int8_t pa[TNC_MAX_BITS];
     for (int i = 0; i < e.n_m; ++i) pa[e.m_c[i] - e.n_n] = e.m_a[i];
