@@ -1,3 +1,5 @@
+# One gpurun call at the end of a work session: GPU parity tests, smoke, bench (both arms), ncu launch list of the
+# bench command, per-step probes of four configurations.  Outputs land in gpurun_out/; copy what is to be kept into profiles/.
 mkdir -p gpurun_out
 ( time timeout -s KILL 1200 python -m pytest tests -q -m gpu -x ) > gpurun_out/t_gpu_final.log 2>&1; echo "gpu tests rc=$?" >> gpurun_out/t_gpu_final.log
 tail -n 6 gpurun_out/t_gpu_final.log

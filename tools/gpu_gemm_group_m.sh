@@ -1,3 +1,4 @@
+# CUDA-event time of the fat GEMM for several sweep-group sizes.
 mkdir -p gpurun_out
 {
 for gm in 16 8 4 2 32 16; do

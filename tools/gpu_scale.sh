@@ -1,3 +1,4 @@
+# gpurun --gpus 8: bench at 8 and 2 GPUs and the five BASELINE configurations at 8 GPUs (tools/run_configs.py).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt
 for N in 8 2; do
