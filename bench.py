@@ -381,6 +381,7 @@ def main():
         slice_ms = sum(ms_slice[i * SL] for i in range(len(ops)))
         best, best_ms = None, -1.0
         gemm_ms = pack_ms = simt_ms = stem_ms = skinny_ms = 0.0
+        stem_bytes = skinny_bytes = 0
         for i, ((kind, rec), st) in enumerate(zip(ops, steps)):
             if kind != "einsum":
                 continue
@@ -391,9 +392,11 @@ def main():
             elif rec.algo == N.TNC_ALGO_STEM:
                 k_ms = ms_slice[i * SL]
                 stem_ms += k_ms
+                stem_bytes += st.bytes_c64
             elif rec.algo == N.TNC_ALGO_SKINNY:
                 k_ms = ms_slice[i * SL]
                 skinny_ms += k_ms
+                skinny_bytes += st.bytes_c64
             else:
                 k_ms = ms_slice[i * SL]
                 simt_ms += k_ms
@@ -431,8 +434,10 @@ def main():
                 cap = json.load(f).get(kname)
             if cap and rec.algo == N.TNC_ALGO_TC and (len(st.m_modes), len(st.n_modes), len(st.k_modes)) == (15, 13, 15):
                 roofline["traffic"] = cap["dram_bytes"]
-                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, "
-                                            "profiles/r01_ncu_full_fat.txt); algorithmic bytes of the step: %d" % st.bytes_c64)
+                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, "
+                                            "profiles/r01_gemm_sweep_group_traffic.txt; --set full capture: "
+                                            "profiles/r01_ncu_full_fat.txt); algorithmic bytes of the step: %d; floor "
+                                            "for 74 resident 256x256 tiles streaming the whole K: ~64 GB" % st.bytes_c64)
         except (OSError, ValueError):
             pass
         roofline["step"] = {"index": st.index, "m_bits": len(st.m_modes), "n_bits": len(st.n_modes),
@@ -440,7 +445,11 @@ def main():
                             "ms": best_ms, "share_of_slice": best_ms / slice_ms}
         breakdown = {"slice_ms_profiled": slice_ms, "gemm_ms": gemm_ms, "pack_ms": pack_ms, "stem_ms": stem_ms,
                      "skinny_ms": skinny_ms, "generic_ms": simt_ms,
-                     "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms - stem_ms - skinny_ms}
+                     "other_ms": slice_ms - gemm_ms - pack_ms - simt_ms - stem_ms - skinny_ms,
+                     # the HBM-bound step classes inside the power-capped slice: algorithmic bytes / time
+                     "stem_gbs": stem_bytes / (stem_ms * 1e-3) / 1e9 if stem_ms > 0 else None,
+                     "skinny_gbs": skinny_bytes / (skinny_ms * 1e-3) / 1e9 if skinny_ms > 0 else None,
+                     "hbm_peak_gbs": pk["hbm_gbs"]}
 
     # ---- the reduced-precision complex-half mode on the same slices (rank 0, N = 1): throughput and
     # fidelity against the complex64 result
@@ -472,6 +481,23 @@ def main():
         half = {"value": 2 * (hi - lo) / (h0.elapsed_time(h1) * 1e-3), "unit": UNIT, "tc_precision": "f16",
                 "fidelity_vs_complex64": fid,
                 "max_err_over_rms": ((a - b).abs().max() / a.abs().pow(2).mean().sqrt()).item()}
+        # the same dominant GEMM in this mode issues ONE tensor-core product per useful one: its useful
+        # TFLOP/s are the issued ones (CUDA events around the launch, one profiled slice)
+        try:
+            _, hms = hplan.profile(blob, hout, lo, ws, stream.cuda_stream)
+            SLh = N.TNC_PROFILE_SLOTS
+            hbest = None
+            for i, ((kind, rec), st) in enumerate(zip(hplan.ops[N.TNC_PHASE_SLICE], hplan.op_steps[N.TNC_PHASE_SLICE])):
+                if kind == "einsum" and rec.algo == N.TNC_ALGO_TC and (hbest is None or hms[i * SLh + 3] > hbest[0]):
+                    hbest = (hms[i * SLh + 3], st)
+            if hbest is not None and hbest[0] > 0:
+                hach = hbest[1].flops / (hbest[0] * 1e-3) / 1e12
+                half["roofline"] = {"bound": "tensor", "kernel": "gemm_2cta_kernel<f16>", "achieved": hach,
+                                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                    "frac": hach / pk["bf16_tflops_sustained"],
+                                    "step": {"index": hbest[1].index, "ms": hbest[0], "flops": hbest[1].flops}}
+        except Exception as exc:      # measurement aid only
+            half["roofline_error"] = str(exc)
         del hplan
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only)
