@@ -126,7 +126,7 @@ def tc_scratch_bytes(st: Step):
         nb_a, nb_b = st.a.rows, st.b.rows
     a_panel = al((nb_a << (len(st.m_modes) + len(st.k_modes))) * 8)
     b_panel = al((nb_b << (len(st.n_modes) + len(st.k_modes))) * 16)
-    return 2 * a_panel + 2 * b_panel
+    return 2 * a_panel + 2 * b_panel + 1024      # + the amax / barrier words of the step
 
 
 def full_outer(st: Step):

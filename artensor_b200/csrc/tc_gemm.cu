@@ -1352,7 +1352,9 @@ struct TcGemmOp {
     int blocked = 0, blocked_b = 0;                   // tile-contiguous panels (A, B')
     int two_cta = 0;                                  // CTA pairs (cta_group::2) on 256 x 256 tiles
     int grid = 1;
-    uint32_t* dev_words = nullptr;                    // [0], [1]: amax bits of A, B; [32]: lockstep barrier counter
+    int64_t words_off = 0;                            // 256 bytes at the end of the step's scratch region (in the WORKSPACE, so that
+                                                      // executions with different workspaces never share them): [0], [1] amax bits
+                                                      // of A, B; [32] lockstep barrier counter
 };
 
 namespace {
@@ -1424,7 +1426,7 @@ int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype) {
     if (shape_of(e, &sh) != TNC_OK) return -1;
     const int64_t a_panel = align_up((sh.nb_a << (e.n_m + e.n_k)) * 8, 1024);
     const int64_t b_panel = align_up((sh.nb_b << (e.n_n + e.n_k)) * 16, 1024);
-    return 2 * a_panel + 2 * b_panel;
+    return 2 * a_panel + 2 * b_panel + 1024;          // + the amax / barrier words
 }
 
 int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
@@ -1562,15 +1564,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     const int nkb = (int)((sh.K + bk - 1) / bk);
     g.sync_every = nkb >= 64 ? 16 : 0;
     if (const char* env = getenv("TNC_TC_SYNC")) g.sync_every = nkb >= 64 ? atoi(env) : 0;
-    if (cudaMalloc((void**)&op->dev_words, 256) != cudaSuccess) {
-        delete op;
-        set_error("tensor-core einsum: cudaMalloc of the amax / barrier words failed");
-        return TNC_ERR_CUDA;
-    }
-    op->pa.amax = f16 ? op->dev_words : nullptr;
-    op->pb.amax = f16 ? op->dev_words + 1 : nullptr;
-    g.amax = f16 ? op->dev_words : nullptr;
-    g.sync_counter = op->dev_words + 32;
+    op->words_off = e.scratch_offset + need - 1024;
     *out = op;
     return TNC_OK;
 }
@@ -1580,7 +1574,12 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     const bool lo = op->precision != TNC_TC_F16;
     const int elem = f16 ? 2 : 4;
     int n_launch = 3;
-    if (f16 || op->args.sync_every) TNC_CUDA(cudaMemsetAsync(op->dev_words, 0, 256, s));
+    uint32_t* words = (uint32_t*)(ws + op->words_off);
+    op->pa.amax = f16 ? words : nullptr;
+    op->pb.amax = f16 ? words + 1 : nullptr;
+    op->args.amax = f16 ? words : nullptr;
+    op->args.sync_counter = words + 32;
+    if (f16 || op->args.sync_every) TNC_CUDA(cudaMemsetAsync(words, 0, 256, s));
     if (f16) {
         // one launch finds the largest magnitude of both operands (whole source tensors: an upper
         // bound of the gathered rows is all the scaling needs)
@@ -1589,7 +1588,7 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
         const int ga = (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_a + 511) / 512));
         const int gb = (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_b + 511) / 512));
         amax_kernel<<<ga + gb, 256, 0, s>>>((const float4*)(ws + op->a_off), n4_a, (const float4*)(ws + op->b_off), n4_b, ga,
-                                            op->dev_words);
+                                            words);
         TNC_CUDA(cudaGetLastError());
         n_launch = 4;
     }
@@ -1654,7 +1653,6 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
 }
 
 void tc_gemm_destroy(TcGemmOp* op) {
-    if (op && op->dev_words) cudaFree(op->dev_words);
     delete op;
 }
 

@@ -432,6 +432,36 @@ def test_batched_step_over_all_row_pairs(dev, algo):
     assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 1e-5
 
 
+def test_one_plan_two_streams_two_workspaces(dev):
+    """execute() is re-entrant per (plan, stream, workspace): the slices of one plan
+    run concurrently on two streams with a workspace and an accumulator each -- nothing of a
+    launch (amax words, lockstep counters of the GEMM steps) lives in the plan -- and give the same
+    sum as one stream."""
+    case, exp, sim = sim_from("n30_sparse64_sc26")
+    plan = sim.plan()
+    blob = plan.pack_leaves({k: v.to(dev) for k, v in case.leaves.items()})
+    n = min(4, plan.n_slices)
+    cur = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    outs = [torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev) for _ in range(3)]
+    wss = [torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    plan.execute(blob, outs[2], 0, n, wss[0], cur.cuda_stream)          # one stream
+    torch.cuda.synchronize()
+    for st in streams:
+        st.wait_stream(cur)
+    for s in range(0, n, 2):
+        plan.execute(blob, outs[0], s, s + 1, wss[0], streams[0].cuda_stream)
+        plan.execute(blob, outs[1], s + 1, s + 2, wss[1], streams[1].cuda_stream)
+    torch.cuda.synchronize()
+    both, one = (outs[0] + outs[1]).cpu().numpy(), outs[2].cpu().numpy()
+    assert np.isfinite(both).all()
+    assert np.abs(both - one).max() <= 1e-6 * np.abs(one).max()
+    from artensor_b200 import contraction as _c
+    del wss, outs
+    _c.release_workspaces()
+    torch.cuda.empty_cache()
+
+
 def _execute(dev, plan, leaves):
     blob = plan.pack_leaves({i: v.to(dev) for i, v in leaves.items()})
     out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
