@@ -91,13 +91,18 @@ __global__ void __launch_bounds__(kThreads) simt_einsum_kernel(SimtEinsumParams 
 constexpr int kChainThreads = 1024;
 __global__ void __launch_bounds__(kChainThreads) simt_chain_kernel(const ChainStep* __restrict__ steps, int n, char* ws,
                                                                    const char* __restrict__ blob) {
-    __shared__ ChainStep p;
+    __shared__ ChainStep recs[2];              // double buffer: step s + 1 is fetched while step s computes
     static_assert(sizeof(ChainStep) % 4 == 0, "copied word by word");
+    constexpr int kWords = (int)(sizeof(ChainStep) / 4);
+    if (threadIdx.x < kWords) ((uint32_t*)&recs[0])[threadIdx.x] = ((const uint32_t*)steps)[threadIdx.x];
+    __syncthreads();
     for (int s = 0; s < n; ++s) {
-        __syncthreads();                       // the previous step is complete and nobody reads `p` any more
-        for (int w = threadIdx.x; w < (int)(sizeof(ChainStep) / 4); w += kChainThreads)
-            ((uint32_t*)&p)[w] = ((const uint32_t*)(steps + s))[w];
-        __syncthreads();
+        const ChainStep& p = recs[s & 1];
+        // the last warp fetches the next record; the barrier at the end of the step publishes it together
+        // with this step's outputs
+        if (s + 1 < n && threadIdx.x >= kChainThreads - kWords)
+            ((uint32_t*)&recs[(s + 1) & 1])[threadIdx.x - (kChainThreads - kWords)] =
+                ((const uint32_t*)(steps + s + 1))[threadIdx.x - (kChainThreads - kWords)];
         const float2* A = (const float2*)(ws + p.a_off);
         const float2* B = (const float2*)(ws + p.b_off);
         float2* C = (float2*)(ws + p.c_off);
@@ -136,6 +141,7 @@ __global__ void __launch_bounds__(kChainThreads) simt_chain_kernel(const ChainSt
             }
             C[e] = make_float2(cr, ci);
         }
+        __syncthreads();                       // step s is complete (and record s + 1 is in place) for everybody
     }
 }
 
