@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <memory>
 
+#include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a tool is attached
+
 #include "tnc_internal.h"
 #include "tc_gemm.h"
 
@@ -481,8 +483,31 @@ int64_t tnc_plan_num_ops(const tnc_plan* plan, int32_t phase) {
 
 int64_t tnc_plan_last_launches(const tnc_plan* plan) { return plan ? plan->last_launches : -1; }
 
+// NVTX range per operation ("tc m15 n13 k15 rows1", "skinny ...", "chain x13", "leaves", "accum"), only
+// with TNC_NVTX=1: lets ncu / nsys filter and group the launches by step class
+struct OpRange {
+    bool on;
+    OpRange(const Op& op) {
+        static const bool enabled = getenv("TNC_NVTX") != nullptr;
+        on = enabled;
+        if (!on) return;
+        char name[96];
+        if (op.kind == OP_EINSUM && op.chain_len > 1) snprintf(name, sizeof(name), "chain x%d", op.chain_len);
+        else if (op.kind == OP_EINSUM) {
+            static const char* algo[] = {"simt", "tc", "stem", "skinny"};
+            snprintf(name, sizeof(name), "%s m%d n%d k%d rows%d", algo[op.e.algo & 3], op.e.n_m, op.e.n_n, op.e.n_k, op.e.nb);
+        } else snprintf(name, sizeof(name), "%s", op.kind == OP_LEAVES ? "leaves" : op.kind == OP_ACCUM ? "accum" : "permute");
+        nvtxRangePushA(name);
+    }
+    ~OpRange() {
+        if (on) nvtxRangePop();
+    }
+};
+
 static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_id, void* accum_out, char* ws,
                   cudaStream_t st, LaunchHook hook = nullptr, void* hook_ctx = nullptr) {
+    if (op.kind == OP_EINSUM && op.chain_len < 0) return TNC_OK;       // ran with the head of its chain
+    OpRange range(op);
     switch (op.kind) {
         case OP_LEAVES: {
             plan->last_launches += op.leaf_count > 0;
