@@ -186,3 +186,39 @@ def test_sparse_scheme_on_random_networks(seed, sc_target):
                            options=PlanOptions(stem_min_elems=1 << 3))
     emu = emulate.run_plan(plan, plan.pack_leaves(leaves).numpy(), [0]).reshape(-1)
     assert max(abs(emu[i] - want[s]) for i, s in enumerate(ordered)) < 2e-5 * scale
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_sparse_scheme_single_and_repeated_bitstrings(seed):
+    """Edge cases of the bitstring list: a single bitstring (every row mode has extent 1 after the
+    first merge) and a list with repeats (the compiler works on the distinct strings, like
+    `np.unique` in contraction.py:260, and reports them once)."""
+    rng = np.random.RandomState(500 + seed)
+    n_body, n_fq = 4, 4
+    tb = random_network(rng, n_body, 2, 0)
+    final_qubits = []
+    for q in range(n_fq):
+        t = n_body + q
+        tb[t] = [f"q{q}"]
+        tb[int(rng.randint(0, n_body))].append(f"q{q}")
+        final_qubits.append(t)
+    leaves = {t: rnd(rng, (2,) * len(bl)) for t, bl in tb.items() if t < n_body}
+    for t in final_qubits:
+        leaves[t] = rnd(rng, (2, 2))
+    one = "".join(map(str, rng.randint(0, 2, n_fq)))
+    other = "".join(map(str, rng.randint(0, 2, n_fq)))
+    for bits in ([one], [one, other, one, one, other]):
+        tree = StubTree(tb, list(final_qubits), np.random.RandomState(seed))
+        scheme, rest, ordered = S.contraction_scheme_sparse(tree, bits, sc_target=3)
+        assert rest == [] and ordered == sorted(set(bits))
+        got = np.asarray(O.tensor_contraction_sparse(dict(leaves), scheme)).reshape(-1)
+        assert got.shape == (len(ordered),)
+        for i, s_ in enumerate(ordered):
+            fixed = dict(leaves)
+            for q, t in enumerate(final_qubits):
+                fixed[t] = leaves[t][int(s_[q])]
+            want = complex(brute_force(tb, fixed, []))
+            assert abs(got[i] - want) < 2e-5 * max(abs(want), 1e-3)
+        plan = ContractionPlan(scheme, {t: tuple(v.shape) for t, v in leaves.items()}, True, build_native=False)
+        emu = emulate.run_plan(plan, plan.pack_leaves(leaves).numpy(), [0]).reshape(-1)
+        assert np.abs(emu - got).max() < 1e-5 * max(np.abs(got).max(), 1e-3)
