@@ -551,6 +551,28 @@ def test_n30_sparse_10000_amplitudes_vs_reference_and_google(dev):
     torch.cuda.empty_cache()
 
 
+def test_n30_sparse_10000_amplitudes_sliced_vs_reference_and_google(dev):
+    """BASELINE config 3 as a sliced contraction (sc_target 27: 9 sliced bonds, 512 slices, 10000
+    amplitudes each): two slices against the reference executor, the sum over all 512 against
+    Google's amplitude file, and a split of the slice range in two halves (what two ranks do)."""
+    from artensor_b200 import contraction as _c
+    case, exp, sim = sim_from("n30_sparse10000_sc27")
+    assert sim.plan().n_slices == 512
+    for k, s in enumerate(int(x) for x in exp["slice_ids"]):
+        got = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()
+        assert_amplitudes_close(got, exp["per_slice_c64"][k])
+    total = sim.contraction(device=dev)
+    halves = sim.contraction(device=dev, slice_range=(0, 256)) + sim.contraction(device=dev, slice_range=(256, 512))
+    assert (total - halves).abs().max().item() <= 2e-6 * total.abs().max().item()
+    got = total.cpu().numpy()
+    google = dict(zip(case.extra["bitstrings_in"], case.extra["google_amplitudes"]))
+    want = np.array([google[b] for b in case.bitstrings_sorted])
+    rel = np.abs(got - want) / np.abs(want)
+    assert np.median(rel) < 2e-4 and np.quantile(rel, 0.99) < 5e-3
+    _c.release_workspaces()
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------------
 # reduced-precision complex-half mode (dtype=torch.complex32): fidelity against complex64
 # ---------------------------------------------------------------------------------------------

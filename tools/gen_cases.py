@@ -148,6 +148,8 @@ CONFIGS = {
     "n30_sparse64_sc26": (n30_qsim, lambda: google_amplitudes(64)[0], dict(sc_target=26, trials=4, iters=5), None, False),
     "n30_full": (n30_qsim, lambda: [], dict(sc_target=30, trials=4, iters=5), [0], False),
     "n30_sparse10000": (n30_qsim, lambda: google_amplitudes(10000)[0], dict(sc_target=30, trials=4, iters=5), [0], False),
+    # BASELINE config 3 as a SLICED contraction (the unsliced scheme above is one slice: nothing to spread over GPUs)
+    "n30_sparse10000_sc27": (n30_qsim, lambda: google_amplitudes(10000)[0], dict(sc_target=27, trials=4, iters=5), [0, 3], False),
     "n53_m12_sparse1024": (lambda: n53_qsim(12), lambda: correlated_bitstrings(53, 10, 0), dict(sc_target=30, trials=4, iters=3), [0, 1, 5], False),
     "n53_m20_sparse1024": (lambda: n53_qsim(20), lambda: correlated_bitstrings(53, 10, 0), dict(sc_target=30, trials=4, iters=3), [0], False),
 }

@@ -28,6 +28,7 @@ CONFIGS = [
     ("2: n30 m14 full amplitude", "n30_full", None),
     ("3: n30 m14 sparse 10000 amplitudes (unsliced)", "n30_sparse10000", None),
     ("3': n30 m14 sparse 64 amplitudes, 16 slices, chunked", "n30_sparse64_sc26", None),
+    ("3'': n30 m14 sparse 10000 amplitudes, 512 slices", "n30_sparse10000_sc27", None),
     ("4: n53 m12 sparse 1024 amplitudes, sliced", "n53_m12_sparse1024", 64),
     ("5: n53 m20 sparse 1024 amplitudes, sliced", "n53_m20_sparse1024", 8),
 ]
@@ -47,7 +48,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     out_lines = []
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]           # optional: case names to run
     for title, name, n_run in CONFIGS:
+        if only and name not in only:
+            continue
         case = load_case(os.path.join(ROOT, "tests", "golden", f"{name}.case.gz"))
         exp = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.expected.npz"))
         sim = TensorNetworkSimulation.from_case(case)
@@ -92,6 +96,11 @@ def main():
             got = got.cpu().numpy()
             rms = np.sqrt(np.mean(np.abs(want) ** 2))
             line["c64_max_err_over_rms_vs_reference"] = float(np.abs(got - want.reshape(-1)).max() / rms)
+        if n == total and "google_amplitudes" in case.extra and case.bitstrings_sorted:
+            google = dict(zip(case.extra["bitstrings_in"], case.extra["google_amplitudes"]))
+            want = np.array([google[b] for b in case.bitstrings_sorted])
+            rel = np.abs(a64.reshape(-1).cpu().numpy() - want) / np.abs(want)
+            line["c64_median_rel_err_vs_google_amplitude_file"] = float(np.median(rel))
         if rank == 0:
             print(json.dumps(line), flush=True)
             out_lines.append(line)
