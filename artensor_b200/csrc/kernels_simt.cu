@@ -4,6 +4,9 @@
 // permutation allows, grids sized in multiples of the SM count.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "tnc_internal.h"
 
 namespace tnc {
@@ -80,6 +83,133 @@ __global__ void __launch_bounds__(kThreads) simt_einsum_kernel(SimtEinsumParams 
             ci = fmaf(x.y, y.x, ci);
         }
         Cplx<T>::store(C + e, make_float2(cr, ci));
+    }
+}
+
+// ------------------------------------------------------------------ long contraction, few outputs per row
+// The tail of a sparse scheme: batched steps [rows][m][k] x [rows][k][n] with a long contraction
+// (k ~ 2^7..2^13) and at most 16 outputs per row.  One thread per output (the generic kernel) walks
+// K alone with uncoalesced loads; here one CTA owns an output row, its threads split K (consecutive
+// threads take consecutive k: the contracted bits are ordered by their position in A, so the loads
+// of A are coalesced), every thread keeps all 2^RC partial sums, and the CTA reduces them.
+constexpr int kRowdotThreads = 128;
+// NM / NN: left-only / right-only output bits (NM + NN <= 4, no shared kept modes)
+template <int NM, int NN>
+__global__ void __launch_bounds__(kRowdotThreads) simt_rowdot_kernel(SimtEinsumParams p) {
+    constexpr int M = 1 << NM, NQ = 1 << NN, RC = NM + NN;
+    __shared__ float2 part[kRowdotThreads / 32][M * NQ];
+    const float2* __restrict__ A = (const float2*)p.a;
+    const float2* __restrict__ B = (const float2*)p.b;
+    float2* __restrict__ C = (float2*)p.c;
+    // offsets of the M left-only / NQ right-only index values in A / B, and of output (mi, ni) in C
+    uint32_t oa[M], ob[NQ], cm[M], cn[NQ];
+#pragma unroll
+    for (int i = 0; i < M; ++i) oa[i] = cm[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) ob[i] = cn[i] = 0;
+    {
+        int im = 0, in = 0;
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+            if (p.c2a[q] >= 0) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    oa[i] |= (((uint32_t)i >> im) & 1u) << p.c2a[q];
+                    cm[i] |= (((uint32_t)i >> im) & 1u) << q;
+                }
+                ++im;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    ob[i] |= (((uint32_t)i >> in) & 1u) << p.c2b[q];
+                    cn[i] |= (((uint32_t)i >> in) & 1u) << q;
+                }
+                ++in;
+            }
+        }
+    }
+    const uint32_t nk = 1u << p.kb;
+    const int64_t rows = p.total >> RC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        int64_t ra = 0, rb = 0;
+        if (p.rows_mode_a == TNC_ROWS_IDENTITY) ra = row;
+        else if (p.rows_mode_a >= 0) ra = p.rows_a[row];
+        if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = row;
+        else if (p.rows_mode_b >= 0) rb = p.rows_b[row];
+        const float2* __restrict__ a = A + (ra << p.rank_a);
+        const float2* __restrict__ b = B + (rb << p.rank_b);
+        float2 acc[M][NQ];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) acc[i][j] = make_float2(0.f, 0.f);
+        for (uint32_t k = threadIdx.x; k < nk; k += kRowdotThreads) {
+            const uint32_t ka = p.koff_a[k], kb = p.koff_b[k];
+            float2 x[M], y[NQ];
+#pragma unroll
+            for (int i = 0; i < M; ++i) x[i] = a[oa[i] + ka];
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) y[j] = b[ob[j] + kb];
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    acc[i][j].x = fmaf(x[i].x, y[j].x, acc[i][j].x);
+                    acc[i][j].x = fmaf(-x[i].y, y[j].y, acc[i][j].x);
+                    acc[i][j].y = fmaf(x[i].x, y[j].y, acc[i][j].y);
+                    acc[i][j].y = fmaf(x[i].y, y[j].x, acc[i][j].y);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    acc[i][j].x += __shfl_xor_sync(0xffffffffu, acc[i][j].x, d);
+                    acc[i][j].y += __shfl_xor_sync(0xffffffffu, acc[i][j].y, d);
+                }
+                if (lane == 0) part[warp][i * NQ + j] = acc[i][j];
+            }
+        __syncthreads();
+        if (threadIdx.x < M * NQ) {
+            float2 o = part[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < kRowdotThreads / 32; ++w) {
+                o.x += part[w][threadIdx.x].x;
+                o.y += part[w][threadIdx.x].y;
+            }
+            // thread t holds output (mi, ni) = (t / NQ, t % NQ); its place in C comes from the bit tables
+            uint32_t off = 0;
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+                if ((int)threadIdx.x / NQ == i) off |= cm[i];
+#pragma unroll
+            for (int j = 0; j < NQ; ++j)
+                if ((int)threadIdx.x % NQ == j) off |= cn[j];
+            C[(row << RC) + off] = o;
+        }
+        __syncthreads();
+    }
+}
+
+template <int NM>
+void launch_rowdot_n(const SimtEinsumParams& p, int nn, int grid, cudaStream_t s) {
+    if constexpr (NM <= 4) {
+        if (nn == 0) simt_rowdot_kernel<NM, 0><<<grid, kRowdotThreads, 0, s>>>(p);
+    }
+    if constexpr (NM <= 3) {
+        if (nn == 1) simt_rowdot_kernel<NM, 1><<<grid, kRowdotThreads, 0, s>>>(p);
+    }
+    if constexpr (NM <= 2) {
+        if (nn == 2) simt_rowdot_kernel<NM, 2><<<grid, kRowdotThreads, 0, s>>>(p);
+    }
+    if constexpr (NM <= 1) {
+        if (nn == 3) simt_rowdot_kernel<NM, 3><<<grid, kRowdotThreads, 0, s>>>(p);
+    }
+    if constexpr (NM == 0) {
+        if (nn == 4) simt_rowdot_kernel<NM, 4><<<grid, kRowdotThreads, 0, s>>>(p);
     }
 }
 
@@ -210,6 +340,29 @@ __global__ void __launch_bounds__(kThreads) accum_kernel(AccumParams p) {
 
 int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
     if (p.total <= 0) return TNC_OK;
+    // many rows, a long contraction, <= 16 outputs per row, no shared kept modes: one CTA per row
+    static const bool no_rowdot = getenv("TNC_NO_ROWDOT") != nullptr;      // measurement aid
+    if (!no_rowdot && dtype == TNC_C64 && p.rank_c <= 4 && p.kb >= 7 && (p.total >> p.rank_c) >= 32) {
+        int nm = 0, nn = 0;
+        bool plain = true;
+        for (int q = 0; q < p.rank_c; ++q) {
+            if (p.c2a[q] >= 0 && p.c2b[q] >= 0) plain = false;
+            else if (p.c2a[q] >= 0) ++nm;
+            else ++nn;
+        }
+        if (plain) {
+            const int grid = (int)std::min<int64_t>(p.total >> p.rank_c, (int64_t)sm_count() * 16);
+            switch (nm) {
+                case 0: launch_rowdot_n<0>(p, nn, grid, s); break;
+                case 1: launch_rowdot_n<1>(p, nn, grid, s); break;
+                case 2: launch_rowdot_n<2>(p, nn, grid, s); break;
+                case 3: launch_rowdot_n<3>(p, nn, grid, s); break;
+                default: launch_rowdot_n<4>(p, nn, grid, s); break;
+            }
+            TNC_CUDA(cudaGetLastError());
+            return TNC_OK;
+        }
+    }
     const int grid = grid_for(p.total);
     if (dtype == TNC_C64) simt_einsum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
     else simt_einsum_kernel<__half2><<<grid, kThreads, 0, s>>>(p);
