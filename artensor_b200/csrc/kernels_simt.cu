@@ -254,16 +254,16 @@ __global__ void __launch_bounds__(kChainThreads) simt_chain_kernel(const ChainSt
             }
             int64_t ra = 0, rb = 0;
             if (p.rows_mode_a == TNC_ROWS_IDENTITY) ra = row;
-            else if (p.rows_mode_a >= 0) ra = __ldg(rows_a + row);          // the plan's tables never change: cached path
+            else if (p.rows_mode_a >= 0) ra = TNC_LDG(rows_a + row);          // the plan's tables never change: cached path
             if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = row;
-            else if (p.rows_mode_b >= 0) rb = __ldg(rows_b + row);
+            else if (p.rows_mode_b >= 0) rb = TNC_LDG(rows_b + row);
             const float2* a = A + (ra << p.rank_a) + oa;
             const float2* b = B + (rb << p.rank_b) + ob;
             float cr = 0.f, ci = 0.f;
 #pragma unroll 4
             for (uint32_t k = 0; k < nk; ++k) {
-                const float2 x = __ldcg(a + __ldg(koff_a + k));
-                const float2 y = __ldcg(b + __ldg(koff_b + k));
+                const float2 x = __ldcg(a + TNC_LDG(koff_a + k));
+                const float2 y = __ldcg(b + TNC_LDG(koff_b + k));
                 cr = fmaf(x.x, y.x, cr);
                 cr = fmaf(-x.y, y.y, cr);
                 ci = fmaf(x.x, y.y, ci);

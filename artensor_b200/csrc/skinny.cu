@@ -278,13 +278,13 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                 if (KC >= 2 && p.a_vec) {
 #pragma unroll
                     for (int k = 0; k < KC; k += 2) {
-                        const float4 x = __ldg((const float4*)(ap + p.koff_c[k]));
+                        const float4 x = TNC_LDG((const float4*)(ap + p.koff_c[k]));
                         av[i][k] = make_float2(x.x, x.y);
                         av[i][k + 1] = make_float2(x.z, x.w);
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) av[i][k] = __ldg(ap + p.koff_c[k]);
+                    for (int k = 0; k < KC; ++k) av[i][k] = TNC_LDG(ap + p.koff_c[k]);
                 }
             }
             // the slot (shared memory tile, scales, TMEM accumulators) is free once the epilogue of

@@ -7,6 +7,15 @@
 
 #include "tnc_b200.h"
 
+// Read-only loads of operands: the non-coherent path by default.  -DTNC_COHERENT_LOADS (together
+// with -D__restrict__=) builds the library with L2-coherent loads instead: the experiment behind
+// DESIGN.md's note on concurrent executions of one plan.
+#ifdef TNC_COHERENT_LOADS
+#define TNC_LDG(p) __ldcg(p)
+#else
+#define TNC_LDG(p) __ldg(p)
+#endif
+
 namespace tnc {
 
 void set_error(const char* fmt, ...);
