@@ -281,6 +281,11 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
                 ph ^= 1u;
             }
         }
+        // stay until the last copy has landed: the issuing thread outlives its bulk copies
+        if (i_end > i_begin) {
+            const int last = s == 0 ? p.stages - 1 : s - 1;
+            mbar_wait(bar_full + 8u * last, s == 0 ? ph ^ 1u : ph);
+        }
         return;
     }
     // ---- consumers: one thread per row of the tile
@@ -311,6 +316,8 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
         float2 av[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) av[k] = st[koff_s[k]];
+        // the stage is next written through the async proxy: order these generic-proxy reads before it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8u * s);
         if (++s == p.stages) {

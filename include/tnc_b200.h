@@ -175,8 +175,8 @@ void tnc_plan_destroy(tnc_plan* plan);
  * synchronisation.  `leaf_blob`, `accum_out` and `workspace` are device pointers;
  * `accum_out` is read-modify-written (the caller zeroes it, simulation.py:101-105).
  * A finalized plan is immutable on the device and every word a launch writes lives in the caller's
- * workspace, so a plan may be used with any number of workspaces; keep one execution in flight per
- * plan (concurrent executions on several streams are not validated yet). */
+ * workspace, so a plan may be used with any number of workspaces and, from one host thread, on
+ * several streams with a workspace (and an accum_out) each. */
 int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin,
                      uint64_t slice_end, void* accum_out, void* workspace,
                      int64_t workspace_bytes, void* stream);

