@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
 //   * a producer warp moves whole chunks HBM -> shared memory with cp.async.bulk into a ring of
 //     stages (mbarrier full / empty), so 48-96 KB per CTA are in flight whatever the consumers do;
 //   * 256 consumer threads (one per row) copy their K amplitudes from the stage into registers,
-//     release the stage at once, and keep them for every row of the right operand that meets this
+//     release the stage at once (behind a fence.proxy.async: the next write of the stage comes
+//     through the async proxy; without it concurrent kernels on the same SM exposed a race), and keep them for every row of the right operand that meets this
 //     row of A ("segment": the batches of the step that share the A row -- all of them for a
 //     plain step with rows on B, b.rows for a full outer step, a run of the A-row table for an
 //     outer step with a row subset).  A is therefore read from HBM once;
