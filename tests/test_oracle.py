@@ -87,6 +87,19 @@ def test_oracle_n30_sliced_matches_reference_and_google():
     assert np.median(rel) < 2e-4 and rel.max() < 2e-3
 
 
+def test_oracles_on_the_sliced_10000_amplitude_scheme():
+    """n30 m14, Google's 10000 bitstrings at sc_target 27 (512 slices): slice 3 through the numpy and
+    the torch oracle against the reference executor's output (row tables of ~10^4 entries, subset
+    outer steps, a batched step with a 2^11-long contraction)."""
+    from oracle import tn_oracle_torch as OT
+    case, exp = load_golden("n30_sparse10000_sc27")
+    k = int(np.where(exp["slice_ids"] == 3)[0][0])
+    r = O.contract_slices(case.leaves, case.scheme, case.pattern, case.slicing_bonds, case.slicing_indices(), [3])
+    assert _rel(r.reshape(-1), exp["per_slice_c64"][k]) < 5e-6
+    rt = OT.contract_slices(case, [3]).reshape(-1).numpy()
+    assert _rel(rt, exp["per_slice_c64"][k]) < 5e-6
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_torch_oracle_matches_reference_goldens(name):
     """The torch-on-CPU restatement (the CPU baseline that bench.py times) is pinned the same way."""

@@ -290,3 +290,14 @@ def test_outer_pairs_detection_and_native_validation():
     assert not outer_pairs(plan_for(sub // RB, sub % RB).steps[0])                      # a pair missing
     dup = np.concatenate([order[:-1], order[:1]])
     assert not outer_pairs(plan_for(dup // RB, dup % RB).steps[0])                      # a pair twice
+
+
+
+def test_plan_of_the_sliced_10000_amplitude_scheme_lowers():
+    """n30 m14, 10000 bitstrings, sc_target 27 (512 slices): lowering on the host, hoisting, arena."""
+    case, exp = load_golden("n30_sparse10000_sc27")
+    plan = make_plan(case)
+    w = plan.work_summary()
+    assert plan.n_slices == 512 and w["hoisted_steps"] > 100 and w["exec_flops_per_slice"] <= w["ref_flops_per_slice"]
+    assert plan.workspace_bytes < (1 << 30)
+    assert plan.out_shape == (10000,)
