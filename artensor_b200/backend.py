@@ -156,6 +156,25 @@ def tc_eligible(st: Step, precision="3xtf32"):
     return len(st.k_modes) >= min_k and len(st.n_modes) >= 1 and len(st.h_modes) == 0
 
 
+def tc_uses_3m(st: Step, precision="3xf16"):
+    """Mirror of the 3M (Karatsuba) selection in tc_gemm_create(): the 3xF16 precision, whole 64-k blocks
+    (k >= 6 bits), >= 128 complex columns (n >= 7 bits), whole 256-row pair tiles, B's rows not
+    folded into N.  Such a step issues 0.75 real tensor-core products per useful complex one
+    (2.25 with the hi/lo split) instead of 1 (3)."""
+    if precision != "3xf16" or os.environ.get("TNC_TC_3M") == "0" or os.environ.get("TNC_TC_2CTA") == "0":
+        return False
+    k, n, m = len(st.k_modes), len(st.n_modes), len(st.m_modes)
+    if not tc_eligible(st, precision) or k < 6 or n < 7 or m < 7:
+        return False
+    outer = full_outer(st) or outer_pairs(st)
+    if outer:
+        return False                      # B's rows are folded into N (n >= 4): plain [row of B][n][k] panel
+    fold_rows = st.rb is None or st.nb == 1
+    nb_a = st.nb if st.ra is not None else 1
+    rows = (nb_a << m) if fold_rows else (1 << m)
+    return rows % 256 == 0
+
+
 def stem_eligible(st: Step):
     """Mirror of stem_supported() in csrc/stem.cu: B[k][n] and the k offsets must fit shared memory."""
     k, n = len(st.k_modes), len(st.n_modes)

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     auto done_bar = [&](int s) { return bars + 8u * (kMaxSlots + s); };
     auto free_bar = [&](int s) { return bars + 8u * (2 * kMaxSlots + s); };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int K = KC * KB, N = 1 << p.nb;
 
     // ---------------------------------------------------------------- set-up (all threads)
@@ -199,9 +199,11 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     // the MMAs of one tile: every sub-tile / k-block into its own accumulator of the slot
     const uint32_t idesc = umma_idesc<PREC>(kTileRows, p.n_mma);
     const uint64_t db_hi = umma_desc(b_hi), db_lo = umma_desc(b_lo);
+    // called by a whole converged warp: every lane waits, one elected lane issues (elect_one, tc_common.cuh)
     auto issue_mma = [&](int slot, uint32_t use) {
         mbar_wait(full_bar(slot), use & 1u);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
             const uint32_t abase = a0 + (uint32_t)slot * slot_bytes + (uint32_t)kb * (PANELS * kTileBytes);
@@ -226,6 +228,8 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             }
         }
         umma_commit(done_bar(slot));
+        }
+        __syncwarp();
     };
 
     if (warp < kProducerWarps) {
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
         const bool idle = group >= p.groups;
         if (KB == 2 && group == 2) {
             // two k-blocks: groups 0 and 1 convert, the first warp of group 2 issues the MMAs
-            if ((warp & 3) == 0 && lane == 0)
+            if ((warp & 3) == 0)
                 for (int64_t j = 0;; ++j) {
                     if ((int64_t)blockIdx.x + j * gridDim.x >= p.tiles) break;
                     issue_mma((int)(j % p.slots), (uint32_t)(j / p.slots));
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             mbar_arrive(full_bar(slot));
             // KB == 1: one thread of the group issues the tile's MMAs once every producer of the tile
             // has arrived (KB == 2: the idle third group does, see below)
-            if (KB == 1 && (warp & 3) == 0 && lane == 0) issue_mma(slot, use);
+            if (KB == 1 && (warp & 3) == 0) issue_mma(slot, use);
             __syncwarp();
             slot += step;                                                 // step <= slots (groups <= slots)
             if (slot >= p.slots) {

@@ -97,6 +97,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// One lane of a converged warp (the warp must execute this together).  Code guarded by it is known to
+// ptxas to run in a single thread, so descriptors and barrier addresses stay in uniform registers; a
+// `lane == 0` branch instead makes every tcgen05 / TMA instruction pay a warp-uniformisation loop
+// (ELECT + PLOP3 + BRA.U.ANY, ~30 issue slots per MMA: measured, the MMA thread became the bottleneck
+// of the 3M kernel at 59 % tensor-pipe utilisation).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a warp-uniform value (threadIdx-derived values are divergent to the compiler)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(kPack2Threads, 4) pack2_kernel(const Pack2Para
     const int lane = t & 31;
     float sc = 1.f;
     if (p.mode == PACK_SPLIT_F16) sc = f16_scale(*p.amax);
+    if (p.mode == PACK_PLANAR3_F16) sc = 0.5f * f16_scale(*p.amax);
 
     auto bases = [&](int64_t tl, int64_t& sb, int64_t& db) {
         const int64_t blk = tl >> obits;
@@ -445,6 +446,32 @@ __global__ void __launch_bounds__(kPack2Threads, 4) pack2_kernel(const Pack2Para
                     __half2* hl = (__half2*)p.dst_lo + (blk << (p.rank + 1)) + e;
                     *(uint4*)hl = make_uint4(l0[0], l0[1], l0[2], l0[3]);
                     *(uint4*)(hl + second) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+                }
+            } else if (p.mode == PACK_PLANAR3_F16) {
+                // 3M panels: planes re, im, re + im (hi then lo each) of 2^13 halves per 2^13 amplitudes; the
+                // four amplitudes are four consecutive k of one row: one 8-byte store per plane
+                const int planes = p.dst_lo ? 6 : 3;
+                __half* base = (__half*)p.dst_hi + ((d >> 13) * planes << 13) + (d & 8191);
+                float v[3][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[0][e] = x[e].x * sc;
+                    v[1][e] = x[e].y * sc;
+                    v[2][e] = v[0][e] + v[1][e];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    __half h[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h[e] = __float2half_rn(v[c][e]);
+                    const __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+                    __half* o = base + ((p.dst_lo ? 2 * c : c) << 13);
+                    *(uint2*)o = make_uint2(*(const uint32_t*)&h01, *(const uint32_t*)&h23);
+                    if (p.dst_lo) {
+                        const __half2 l01 = __floats2half2_rn(v[c][0] - __half2float(h[0]), v[c][1] - __half2float(h[1]));
+                        const __half2 l23 = __floats2half2_rn(v[c][2] - __half2float(h[2]), v[c][3] - __half2float(h[3]));
+                        *(uint2*)(o + 8192) = make_uint2(*(const uint32_t*)&l01, *(const uint32_t*)&l23);
+                    }
                 }
             } else {                                  // PACK_SPLIT_F16
                 uint32_t h[4], l[4];
@@ -597,17 +624,22 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
         set_error("pack: bad descriptor (rank %d, blocks %d)", d.rank, d.nb);
         return TNC_ERR_INVALID;
     }
-    if ((d.mode == PACK_SPLIT_F16 || d.mode == PACK_EXPAND_SPLIT_F16) && !d.amax) {
+    if (d.mode == PACK_PLANAR3_F16 && d.rank < 13) {
+        set_error("pack: the 3M panels need rank >= 13 (got %d)", d.rank);
+        return TNC_ERR_UNSUPPORTED;
+    }
+    if ((d.mode == PACK_SPLIT_F16 || d.mode == PACK_EXPAND_SPLIT_F16 || d.mode == PACK_PLANAR3_F16) && !d.amax) {
         set_error("pack: the fp16 modes need the operand's amax word");
         return TNC_ERR_INVALID;
     }
     static const bool fast = !(getenv("TNC_PACK_FAST") && atoi(getenv("TNC_PACK_FAST")) == 0);
     if (fast && d.rank >= 8 && d.rank - 8 < 32 &&
         (d.mode == PACK_COPY || d.mode == PACK_SPLIT || d.mode == PACK_SPLIT_F16 || d.mode == PACK_ACCUM ||
+         d.mode == PACK_PLANAR3_F16 ||
          (d.mode == PACK_EXPAND_SPLIT_F16 && d.inner_bits >= 2)))
         return launch_pack2(d, src, dst_hi, dst_lo, s);
-    if (d.mode == PACK_ACCUM) {
-        set_error("pack: the accumulate mode needs rank >= 8 (got %d)", d.rank);
+    if (d.mode == PACK_ACCUM || d.mode == PACK_PLANAR3_F16) {
+        set_error("pack: this mode needs the fast kernel (rank >= 8, got %d)", d.rank);
         return TNC_ERR_UNSUPPORTED;
     }
     PackParams p{};
@@ -744,6 +776,7 @@ struct GemmArgs {
     int32_t sync_every;       // k-blocks between grid-wide lockstep barriers (0 = none)
     uint32_t* sync_counter;   // zeroed before the launch
     const uint32_t* amax;     // fp16 precisions: amax words of A and B (the epilogue undoes their scaling)
+    float out_scale;          // extra factor of the fp16 epilogue: 4 for the 3M panels (scaled one bit lower), else 1
 };
 
 // Grid-wide barrier among the co-resident persistent CTAs (one thread per CTA calls it).  It only
@@ -826,7 +859,12 @@ __device__ __forceinline__ void drain_chunk(uint32_t taddr, float* acc) {
             tmem_ld16(taddr + c + 16, v + 16);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);
+            for (int j = 0; j < 32; j += 2) {
+                const float2 r = __fadd2_rn(make_float2(acc[c + j], acc[c + j + 1]),
+                                            make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                acc[c + j] = r.x;
+                acc[c + j + 1] = r.y;
+            }
         }
     } else if constexpr (CPT == 16) {
         uint32_t v[16];
@@ -851,7 +889,7 @@ template <int CPT, bool F16>
 __device__ __forceinline__ void store_tile_rows(const GemmArgs& g, uint32_t stage, int batch, int row0, int col0, float* acc,
                                                 int lane) {
     float sab = 1.f;
-    if constexpr (F16) sab = f16_inv_scale(g.amax[0]) * f16_inv_scale(g.amax[1]);
+    if constexpr (F16) sab = f16_inv_scale(g.amax[0]) * f16_inv_scale(g.amax[1]) * g.out_scale;
     // Output address of GEMM element (row, col).  Folded outer-rows steps (n_inner != 0): the GEMM
     // columns are (row of B, n), and C wants the row pair outermost, so every n_inner columns
     // belong to another row block of C; n_inner >= 32, so a 32-column slab never straddles two.
@@ -909,7 +947,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     auto tmem_full_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + b); };
     auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + 2 + b); };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
     const int nkb = (g.K + BK - 1) / BK;
 
@@ -936,7 +974,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             uint32_t it = 0, epoch = 0;          // k-blocks loaded so far (stage ring position), barrier epochs
             bool wait_peers = true;
             for (int round = 0; round < g.rounds; ++round) {
@@ -946,13 +984,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 if (valid) t = tile_coord<BN>(g, tile);
                 const int ba = g.a_batched ? t.batch : 0, bb = g.b_batched ? t.batch : 0;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    if (g.sync_every && kb % g.sync_every == 0)
-                        wait_peers = lockstep_barrier(g.sync_counter, ++epoch * gridDim.x, wait_peers);
+                    if (g.sync_every && kb % g.sync_every == 0) {
+                        ++epoch;
+                        if (lane == 0) wait_peers = lockstep_barrier(g.sync_counter, epoch * gridDim.x, wait_peers);
+                        __syncwarp();
+                    }
                     if (!valid) continue;
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     ++it;
                     mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (elect_one()) {
                     mbar_expect_tx(full_bar(s), C::STAGE);
                     const uint32_t st = base + s * C::STAGE;
                     // blocked panels: one contiguous [rows][128 bytes] block per (tile, k-block)
@@ -966,11 +1008,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                         tma_load_3d(st + C::A_LO, &map_a_lo, full_bar(s), a0, a1, a2);
                         tma_load_3d(st + C::B_LO, &map_b_lo, full_bar(s), b0, b1, b2);
                     }
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = umma_idesc<PREC>(BM, BN);
             const int KC = g.kc;
             uint32_t it = 0, gc = 0;             // k-blocks consumed, accumulation chunks produced
@@ -990,13 +1034,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t st = base + s * C::STAGE;
-                    umma_kblock<PREC, 1>(tacc, umma_desc(st), umma_desc(st + C::A_LO), umma_desc(st + C::B_HI),
-                                         umma_desc(st + C::B_LO), idesc, acc);
-                    umma_commit(empty_bar(s));     // frees the stage when these MMAs have read it
-                    if (kb % KC == KC - 1 || kb == nkb - 1) {
-                        umma_commit(tmem_full_bar(gc & 1u));
-                        ++gc;
+                    const bool last = kb % KC == KC - 1 || kb == nkb - 1;
+                    if (elect_one()) {
+                        umma_kblock<PREC, 1>(tacc, umma_desc(st), umma_desc(st + C::A_LO), umma_desc(st + C::B_HI),
+                                             umma_desc(st + C::B_LO), idesc, acc);
+                        umma_commit(empty_bar(s));     // frees the stage when these MMAs have read it
+                        if (last) umma_commit(tmem_full_bar(gc & 1u));
                     }
+                    __syncwarp();
+                    if (last) ++gc;
                 }
             }
         }
@@ -1109,7 +1155,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     auto tmem_full_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + b); };
     auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + 2 + b); };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = (int)blockIdx.x >> 1, pairs = (int)gridDim.x >> 1;
     const int nkb = (g.K + BK - 1) / BK;
@@ -1143,7 +1189,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int pair_tiles = g.tiles / 2;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             uint32_t it = 0, epoch = 0;
             bool wait_peers = true;
             for (int round = 0; round < g.rounds; ++round) {
@@ -1154,13 +1200,17 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 const int ba = g.a_batched ? t.batch : 0, bb = g.b_batched ? t.batch : 0;
                 const int m_tile128 = 2 * t.m_tile + (int)rank;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    if (g.sync_every && kb % g.sync_every == 0)
-                        wait_peers = lockstep_barrier(g.sync_counter, ++epoch * gridDim.x, wait_peers);
+                    if (g.sync_every && kb % g.sync_every == 0) {
+                        ++epoch;
+                        if (lane == 0) wait_peers = lockstep_barrier(g.sync_counter, epoch * gridDim.x, wait_peers);
+                        __syncwarp();
+                    }
                     if (!valid) continue;
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     ++it;
                     mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE);     // both CTAs' bytes land on rank 0's barrier
                     const uint32_t st = base + s * C::STAGE;
                     const int a0 = g.blocked ? 0 : kb * BK, a1 = g.blocked ? 0 : m_tile128 * BM;
@@ -1173,11 +1223,13 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                         tma_load_3d_2sm(st + C::A_LO, &map_a_lo, full_bar(s), a0, a1, a2);
                         tma_load_3d_2sm(st + C::B_LO, &map_b_lo, full_bar(s), b0, b1, b2);
                     }
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             // N = 256, M = 256 (128 rows in each CTA of the pair)
             constexpr uint32_t idesc = umma_idesc<PREC>(256, BN);
             const int KC = g.kc;
@@ -1198,13 +1250,15 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t st = base + s * C::STAGE;
-                    umma_kblock<PREC, 2>(tacc, umma_desc(st), umma_desc(st + C::A_LO), umma_desc(st + C::B_HI),
-                                         umma_desc(st + C::B_LO), idesc, acc);
-                    umma_commit_2sm(empty_bar(s));
-                    if (kb % KC == KC - 1 || kb == nkb - 1) {
-                        umma_commit_2sm(tmem_full_bar(gc & 1u));
-                        ++gc;
+                    const bool last = kb % KC == KC - 1 || kb == nkb - 1;
+                    if (elect_one()) {
+                        umma_kblock<PREC, 2>(tacc, umma_desc(st), umma_desc(st + C::A_LO), umma_desc(st + C::B_HI),
+                                             umma_desc(st + C::B_LO), idesc, acc);
+                        umma_commit_2sm(empty_bar(s));
+                        if (last) umma_commit_2sm(tmem_full_bar(gc & 1u));
                     }
+                    __syncwarp();
+                    if (last) ++gc;
                 }
             }
         }
@@ -1238,6 +1292,252 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // nobody leaves while the pair's MMAs may still read its shared memory
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+
+// =====================================================================================
+// 3M (Karatsuba) complex product on CTA pairs.  With planar fp16 panels re / im / (re + im) of both
+// operands,
+//     P1 = Ar Br,   P2 = Ai Bi,   P3 = (Ar + Ai)(Br + Bi)       (three REAL M x N x K products)
+//     Cr = P1 - P2,               Ci = P3 - P1 - P2
+// is 6 M N K real flops instead of the 8 of the interleaved 4M form above: 25 % fewer tensor-core
+// instructions per useful flop, which is the only lever left on a GEMM that already keeps the
+// tensor pipe busy under the power cap.  Same output tile as gemm_2cta_kernel (a pair owns 256
+// rows x 128 complex columns of C, interleaved fp32 accumulators in the epilogue warps'
+// registers), same chunked accumulation: tensor memory only ever holds the sum of `kc` k-blocks
+// of ONE product.  TMEM is a ring of four 128-column slots that the products of consecutive
+// chunks walk through (P1, P2, P3, P1, ...); the epilogue warps fold each finished slot into the
+// registers with the product's signs (no temporaries: Cr += P1, Ci -= P1; Cr -= P2, Ci -= P2;
+// Ci += P3, every add rounded to nearest) and free it at once.  The pipeline unit is one product
+// of one k-block: a stage holds A_p hi/lo (this CTA's 128 rows x 64 k) and B_p hi/lo (this CTA's
+// 64 of the tile's 128 columns) = 48 KB, four stages.
+// =====================================================================================
+template <int PREC>
+struct Cfg3 {
+    static constexpr int BN = 256;                      // real (interleaved) columns of the output tile
+    static constexpr int BNC = 128;                     // complex columns = N of every MMA
+    static constexpr int PANELS = Prec<PREC>::PANELS;   // hi (+ lo)
+    static constexpr int BK = BKB / 2;                  // 64 complex k per k-block (planar fp16 rows of 128 bytes)
+    static constexpr int A_TILE = BM * BKB;             // one part of this CTA's 128 rows
+    static constexpr int B_TILE = (BNC / 2) * BKB;      // one part of this CTA's half of the B tile
+    static constexpr int A_LO = A_TILE, B_HI = PANELS * A_TILE, B_LO = PANELS * A_TILE + B_TILE;
+    static constexpr int STAGE = PANELS * (A_TILE + B_TILE);
+    static constexpr int STAGES = (kSmemBudget / STAGE) > 8 ? 8 : (kSmemBudget / STAGE);
+    static constexpr int SLOTS = 4;                     // TMEM ring: 4 x 128 columns
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int CPT = BN / 2;                  // interleaved floats per epilogue thread (64 complex)
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + kStageBytes;
+    static_assert(Prec<PREC>::F16, "the 3M kernel is fp16 only");
+};
+
+// Folds 64 columns of product P (0: Ar Br, 1: Ai Bi, 2: (Ar + Ai)(Br + Bi)) into the planar accumulators
+// (re[j], im[j] = columns 2j, 2j + 1) with packed fp32x2 adds: 2.5 instructions per complex output and chunk.
+template <int P>
+__device__ __forceinline__ void drain_3m(uint32_t taddr, float2* re, float2* im) {
+    const float2 neg = make_float2(-1.f, -1.f);
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float2 x = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            const int o = (c + j) >> 1;
+            if (P == 0) {
+                re[o] = __fadd2_rn(re[o], x);
+                im[o] = __ffma2_rn(x, neg, im[o]);
+            } else if (P == 1) {
+                re[o] = __ffma2_rn(x, neg, re[o]);
+                im[o] = __ffma2_rn(x, neg, im[o]);
+            } else {
+                im[o] = __fadd2_rn(im[o], x);
+            }
+        }
+    }
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+    using C = Cfg3<PREC>;
+    constexpr int BN = C::BN;
+    constexpr int BK = C::BK;
+    constexpr int HL = C::PANELS;
+    extern __shared__ unsigned char gemm_smem_raw[];
+    const uint32_t raw = smem_u32(gemm_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* aligned = gemm_smem_raw + (base - raw);
+    // barriers: full[STAGES], empty[STAGES], tmem_full[SLOTS], tmem_empty[SLOTS]; then the TMEM base slot
+    const uint32_t bars = base + C::STAGES * C::STAGE;
+    uint32_t* tmem_slot = (uint32_t*)(aligned + C::STAGES * C::STAGE + (2 * C::STAGES + 2 * C::SLOTS) * 8);
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tmem_full_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + b); };
+    auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + C::SLOTS + b); };
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)blockIdx.x >> 1, pairs = (int)gridDim.x >> 1;
+    const int nkb = (g.K / 2) / BK;                     // g.K counts interleaved reals: K / 2 complex k
+    const int KC = g.kc;
+    const int nchunks = (nkb + KC - 1) / KC;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < C::SLOTS; ++b) {
+            mbar_init(tmem_full_bar(b), 1);
+            mbar_init(tmem_empty_bar(b), 2 * kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    GemmArgs gp = g;
+    gp.m_tiles = g.m_tiles / 2;                         // tile_coord counts 256-row pair tiles
+    const int pair_tiles = g.tiles / 2;
+
+    if (warp == 0) {
+        {
+            uint32_t it = 0, epoch = 0;
+            bool wait_peers = true;
+            for (int round = 0; round < g.rounds; ++round) {
+                const int tile = round * pairs + pair;
+                const bool valid = tile < pair_tiles;
+                TileCoord t{};
+                if (valid) t = tile_coord<BN>(gp, tile);
+                const int ba = g.a_batched ? t.batch : 0, bb = g.b_batched ? t.batch : 0;
+                const int m_tile128 = 2 * t.m_tile + (int)rank;
+                const int a_blk = nkb * (m_tile128 + g.m_tiles * ba), b_blk = nkb * (t.n_tile + g.n_tiles * bb);
+                for (int chunk = 0; chunk < nchunks; ++chunk) {
+                    const int kb0 = chunk * KC, kb1 = min(nkb, kb0 + KC);
+                    if (g.sync_every && kb0 % g.sync_every == 0) {
+                        ++epoch;
+                        if (lane == 0) wait_peers = lockstep_barrier(g.sync_counter, epoch * gridDim.x, wait_peers);
+                        __syncwarp();
+                    }
+                    if (!valid) continue;
+                    for (int p = 0; p < 3; ++p)
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            const int s = it % C::STAGES;
+                            const uint32_t ph = (it / C::STAGES) & 1;
+                            ++it;
+                            mbar_wait(empty_bar(s), ph ^ 1u);
+                            if (elect_one()) {
+                                if (rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE);
+                                const uint32_t st = base + s * C::STAGE;
+                                // A: one box of HL x 128 rows (hi then lo of part p); B: this CTA's 64 rows of hi, of lo
+                                tma_load_3d_2sm(st, &map_a, full_bar(s), 0, 0, (a_blk + kb) * 3 + p);
+                                tma_load_3d_2sm(st + C::B_HI, &map_b, full_bar(s), 0, 64 * (int)rank,
+                                                ((b_blk + kb) * 3 + p) * HL);
+                                if constexpr (HL == 2)
+                                    tma_load_3d_2sm(st + C::B_LO, &map_b, full_bar(s), 0, 64 * (int)rank,
+                                                    ((b_blk + kb) * 3 + p) * HL + 1);
+                            }
+                            __syncwarp();
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc<PREC>(256, C::BNC);
+            uint32_t it = 0, gs = 0;                     // stages consumed, TMEM slots produced
+            for (int round = 0; round < g.rounds; ++round) {
+                if (round * pairs + pair >= pair_tiles) break;
+                for (int chunk = 0; chunk < nchunks; ++chunk) {
+                    const int kb0 = chunk * KC, kb1 = min(nkb, kb0 + KC);
+                    for (int p = 0; p < 3; ++p, ++gs) {
+                        const uint32_t slot = gs & 3u;
+                        const uint32_t tacc = tmem + slot * (uint32_t)C::BNC;
+                        mbar_wait(tmem_empty_bar(slot), ((gs >> 2) & 1u) ^ 1u);
+                        tc_fence_after();
+                        uint32_t acc = 0;
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            const int s = it % C::STAGES;
+                            const uint32_t ph = (it / C::STAGES) & 1;
+                            ++it;
+                            mbar_wait(full_bar(s), ph);
+                            tc_fence_after();
+                            const uint32_t st = base + s * C::STAGE;
+                            if (elect_one()) {
+                                umma_kblock<PREC, 2>(tacc, umma_desc(st), umma_desc(st + C::A_LO), umma_desc(st + C::B_HI),
+                                                     umma_desc(st + C::B_LO), idesc, acc);
+                                umma_commit_2sm(empty_bar(s));
+                                if (kb == kb1 - 1) umma_commit_2sm(tmem_full_bar(slot));
+                            }
+                            __syncwarp();
+                            acc = 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int CPT = C::CPT;
+        uint32_t gs = 0;
+        for (int round = 0; round < g.rounds; ++round) {
+            const int tile = round * pairs + pair;
+            if (tile >= pair_tiles) break;
+            const TileCoord t = tile_coord<BN>(gp, tile);
+            float2 re[CPT / 4], im[CPT / 4];
+#pragma unroll
+            for (int j = 0; j < CPT / 4; ++j) re[j] = im[j] = make_float2(0.f, 0.f);
+            const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+            auto slot_wait = [&]() {
+                mbar_wait(tmem_full_bar(gs & 3u), (gs >> 2) & 1u);
+                tc_fence_after();
+                return lane_base + (gs & 3u) * (uint32_t)C::BNC;
+            };
+            auto slot_free = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_on_cta(tmem_empty_bar(gs & 3u), 0);
+                ++gs;
+            };
+#pragma unroll 1
+            for (int chunk = 0; chunk < nchunks; ++chunk) {
+                drain_3m<0>(slot_wait(), re, im);
+                slot_free();
+                drain_3m<1>(slot_wait(), re, im);
+                slot_free();
+                drain_3m<2>(slot_wait(), re, im);
+                slot_free();
+            }
+            float acc[CPT];                              // interleaved (re, im) per complex column
+#pragma unroll
+            for (int j = 0; j < CPT / 4; ++j) {
+                acc[4 * j] = re[j].x;
+                acc[4 * j + 1] = im[j].x;
+                acc[4 * j + 2] = re[j].y;
+                acc[4 * j + 3] = im[j].y;
+            }
+            store_tile_rows<CPT, true>(g, base + C::STAGES * C::STAGE + 256 + (uint32_t)(warp - 2) * 4096u, t.batch,
+                                       (2 * t.m_tile + (int)rank) * BM + q * 32, t.n0 + half * CPT, acc, lane);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
@@ -1330,6 +1630,30 @@ int launch_gemm_2cta(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, c
     return TNC_OK;
 }
 
+template <int PREC>
+int launch_gemm3m(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
+    static bool configured_on[kMaxDevices] = {};       // the attribute is per device
+    bool& configured = configured_on[current_device()];
+    if (!configured) {
+        TNC_CUDA(cudaFuncSetAttribute(gemm3m_2cta_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<PREC>::SMEM));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg3<PREC>::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm3m_2cta_kernel<PREC>, maps[0], maps[2], g));
+    return TNC_OK;
+}
+
 int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -1351,6 +1675,7 @@ struct TcGemmOp {
     CUtensorMap maps[4];
     int blocked = 0, blocked_b = 0;                   // tile-contiguous panels (A, B')
     int two_cta = 0;                                  // CTA pairs (cta_group::2) on 256 x 256 tiles
+    int use_3m = 0;                                   // 3M complex product on planar panels (gemm3m_2cta_kernel)
     int grid = 1;
     int64_t words_off = 0;                            // 256 bytes at the end of the step's scratch region (in the WORKSPACE, so that
                                                       // executions with different workspaces never share them): [0], [1] amax bits
@@ -1474,7 +1799,34 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     if (const char* env = getenv("TNC_TC_BLOCKED"))
         if (atoi(env) == 0) op->blocked = 0;
     op->blocked_b = op->blocked && sh.n_inner == 0;
-    {
+    // CTA pairs on 256 x 256 tiles
+    op->two_cta = bn == 256 && sh.M % 256 == 0 && sh.M / BM >= 2;
+    if (const char* env = getenv("TNC_TC_2CTA"))
+        if (atoi(env) == 0) op->two_cta = 0;
+    // 3M complex product (gemm3m_2cta_kernel): fp16 precisions, whole 64-k blocks and pair tiles
+    // (3xF16 only: in the single-product complex-half mode the 4M kernel is as fast -- both sit at the same
+    // power / shared-memory ceiling, 52.3 vs 53.4 ms on the fat step -- and 1.4x more accurate, the imaginary
+    // part of 3M being a difference of larger products)
+    op->use_3m = precision == TNC_TC_3XF16 && op->two_cta && op->blocked_b && e.n_k >= 6 && sh.N % 256 == 0;
+    if (const char* env = getenv("TNC_TC_3M"))
+        if (atoi(env) == 0) op->use_3m = 0;
+    if (op->use_3m) {
+        // planar panels, both operands alike: [tile of 128 rows][block of 64 k][re, im, re + im][hi, lo][128 rows][64 k]
+        op->pa.mode = op->pb.mode = PACK_PLANAR3_F16;
+        int8_t pm[TNC_MAX_BITS], pn[TNC_MAX_BITS];      // operand position of row bit j (output order)
+        for (int i = 0; i < e.n_m; ++i) pm[e.m_c[i] - e.n_n] = e.m_a[i];
+        for (int i = 0; i < e.n_n; ++i) pn[e.n_c[i]] = e.n_b[i];
+        int d = 0;
+        for (int i = 0; i < 6; ++i) op->pa.src_pos[d++] = e.k_a[i];
+        for (int j = 0; j < 7; ++j) op->pa.src_pos[d++] = pm[j];
+        for (int i = 6; i < e.n_k; ++i) op->pa.src_pos[d++] = e.k_a[i];
+        for (int j = 7; j < e.n_m; ++j) op->pa.src_pos[d++] = pm[j];
+        d = 0;
+        for (int i = 0; i < 6; ++i) op->pb.src_pos[d++] = e.k_b[i];
+        for (int j = 0; j < 7; ++j) op->pb.src_pos[d++] = pn[j];
+        for (int i = 6; i < e.n_k; ++i) op->pb.src_pos[d++] = e.k_b[i];
+        for (int j = 7; j < e.n_n; ++j) op->pb.src_pos[d++] = pn[j];
+    } else {
         int8_t pm[TNC_MAX_BITS];                       // A position of row bit j (output order)
         for (int i = 0; i < e.n_m; ++i) pm[e.m_c[i] - e.n_n] = e.m_a[i];
         int d = 0;
@@ -1494,13 +1846,15 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     op->pb.nb = (int32_t)sh.nb_b;
     op->pb.rows_mode = sh.outer ? TNC_ROWS_IDENTITY : e.rows_b;
     op->pb.rows = dev_rows_b;
-    op->pb.mode = f16 ? PACK_EXPAND_SPLIT_F16 : PACK_EXPAND_SPLIT;
     op->pb.inner_bits = e.n_k;
     op->pb.kb_log2 = kbl;
     op->pb.blocked = op->blocked_b;
     for (int l = 0; (1 << l) <= bn; ++l) op->pb.bn_log2 = l;
-    for (int i = 0; i < e.n_k; ++i) op->pb.src_pos[i] = e.k_b[i];
-    for (int i = 0; i < e.n_n; ++i) op->pb.src_pos[e.n_k + e.n_c[i]] = e.n_b[i];
+    if (!op->use_3m) {
+        op->pb.mode = f16 ? PACK_EXPAND_SPLIT_F16 : PACK_EXPAND_SPLIT;
+        for (int i = 0; i < e.n_k; ++i) op->pb.src_pos[i] = e.k_b[i];
+        for (int i = 0; i < e.n_n; ++i) op->pb.src_pos[e.n_k + e.n_c[i]] = e.n_b[i];
+    }
     op->a_off = e.a.offset;
     op->b_off = e.b.offset;
     op->c_off = e.c.offset;
@@ -1556,14 +1910,16 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     g.tiles = (int32_t)op->tiles;
     g.blocked = op->blocked;
     g.blocked_b = op->blocked_b;
-    op->two_cta = bn == 256 && sh.M % 256 == 0 && g.m_tiles >= 2;
-    if (const char* env = getenv("TNC_TC_2CTA"))
-        if (atoi(env) == 0) op->two_cta = 0;
+    g.out_scale = op->use_3m ? 4.f : 1.f;
     // lockstep only pays off for long k loops shared by many tiles
     const int bk = bk_of(precision);
     const int nkb = (int)((sh.K + bk - 1) / bk);
     g.sync_every = nkb >= 64 ? 16 : 0;
     if (const char* env = getenv("TNC_TC_SYNC")) g.sync_every = nkb >= 64 ? atoi(env) : 0;
+    if (op->use_3m) {
+        // k-blocks of 64 complex k; the barrier spacing is rounded to whole accumulation chunks
+        g.sync_every = (g.sync_every / 2 + g.kc - 1) / g.kc * g.kc;
+    }
     op->words_off = e.scratch_offset + need - 1024;
     *out = op;
     return TNC_OK;
@@ -1605,7 +1961,16 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
         char* lo_a = ws + (lo ? op->alo_off : op->ahi_off);
         char* lo_b = ws + (lo ? op->blo_off : op->bhi_off);
         const int64_t nkb = op->K / bk;
-        if (op->blocked) {
+        if (op->use_3m) {
+            // planar panels: blocks of [hi, lo][128 rows][64 halves], three parts per (tile, 64-k block)
+            const int hl = lo ? 2 : 1;
+            const int64_t nkb3 = op->K / 2 / 64;
+            const int64_t blocks_a = nkb3 * op->args.m_tiles * batch_a, blocks_b = nkb3 * op->args.n_tiles * batch_b;
+            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, 2, 64, 128 * hl, blocks_a * 3, 128 * hl)) != TNC_OK) return rc;
+            if ((rc = make_map(&op->maps[2], ws + op->bhi_off, 2, 64, 128, blocks_b * 3 * hl, 64)) != TNC_OK) return rc;
+            op->maps[1] = op->maps[0];
+            op->maps[3] = op->maps[2];
+        } else if (op->blocked) {
             // `blocks` blocks of [rows][128 bytes], one per (tile, k-block)
             const int64_t blocks_a = nkb * op->args.m_tiles * batch_a;
             if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
@@ -1615,7 +1980,8 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
             if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
             if ((rc = make_map(&op->maps[1], lo_a, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
         }
-        if (op->blocked_b) {
+        if (op->use_3m) {
+        } else if (op->blocked_b) {
             const int64_t blocks_b = nkb * op->args.n_tiles * batch_b;
             if ((rc = make_map(&op->maps[2], ws + op->bhi_off, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
             if ((rc = make_map(&op->maps[3], lo_b, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
@@ -1633,7 +1999,9 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     int64_t grid = std::min<int64_t>(op->tiles, sm_count());
     if (op->two_cta) grid &= ~(int64_t)1;               // whole pairs; tiles is even here
     g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
-    if (op->two_cta) {
+    if (op->use_3m) {
+        rc = launch_gemm3m<TNC_TC_3XF16>(op->maps, g, grid, s);
+    } else if (op->two_cta) {
         switch (op->precision) {
             case TNC_TC_3XF16: rc = launch_gemm_2cta<TNC_TC_3XF16>(op->maps, g, grid, s); break;
             case TNC_TC_F16: rc = launch_gemm_2cta<TNC_TC_F16>(op->maps, g, grid, s); break;

@@ -29,7 +29,11 @@ void tc_gemm_destroy(TcGemmOp* op);
 // dst[b][q] = f(src[row(b)][p]) where bit i of q is bit src_pos[i] of p; tiled through shared
 // memory so that both the global reads and the global writes are contiguous runs.
 enum PackMode { PACK_COPY = 0, PACK_SPLIT = 1, PACK_EXPAND_SPLIT = 2, PACK_SPLIT_F16 = 3, PACK_EXPAND_SPLIT_F16 = 4,
-                PACK_ACCUM = 5 /* dst += permuted src (fast kernel only: rank >= 8) */ };
+                PACK_ACCUM = 5 /* dst += permuted src (fast kernel only: rank >= 8) */,
+                PACK_PLANAR3_F16 = 6 /* panels of the 3M complex product (fast kernel only: rank >= 13): per 2^13
+                                        amplitudes of the destination order, the fp16 planes re, im, re + im -- each
+                                        as hi then lo when dst_lo is non-null -- of 2^13 halves each, scaled by half
+                                        the fp16 operand scale (re + im must stay in range) */ };
 struct PackDesc {
     int32_t rank;                 // bits per block (source and destination)
     int32_t nb;                   // destination blocks

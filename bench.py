@@ -23,13 +23,17 @@ Timed regions
   roofline  the dominant kernel of a slice (the fat tcgen05 GEMM) timed with CUDA events per launch
           via tnc_plan_profile; achieved = 8*M*N*K algorithmic flops / that time.
   cpu_baseline / --impl reference
-          the reference's own arithmetic (torch.einsum on CPU, oracle/tn_oracle_torch.py) on the
-          host cores, on a bounded sample of one slice: every step of the scheme is run on
-          synthetic operands of its true shape; steps larger than 2^24 elements are run on a
-          sub-block and scaled linearly.
+          the reference's own executor restated on CPU torch (oracle/tn_oracle_torch.py) on the host
+          cores.  `--impl reference` runs ONE TRUE SLICE -- the real leaves through every scheme step --
+          spread over its K timed steps (step i = the i-th 1/K of the slice's scheme steps), checks
+          the result against the reference's recorded output and caches the seconds under /tmp;
+          the GPU arm's `cpu_baseline` quotes that measurement when it finds it on the same host,
+          else a bounded timing model (every step's einsum on synthetic operands, large steps on
+          sub-blocks), which is also printed beside the true slice as a cross-check.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -193,6 +197,9 @@ def step_shapes_of(plan):
 
 
 def cpu_sample(plan, max_elems, budget_s=240.0):
+    """Timing MODEL of one slice on the host cores (a cross-check, not the baseline): every step's
+    torch.einsum on synthetic operands of its true shape, steps above `max_elems` elements on a
+    sub-block and scaled linearly."""
     import torch
     from oracle import tn_oracle_torch as OT
     torch.set_num_threads(os.cpu_count() or 1)
@@ -200,39 +207,136 @@ def cpu_sample(plan, max_elems, budget_s=240.0):
     return secs, n, scaled, wall
 
 
+def host_mem_gib():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 2 ** 20
+    except OSError:
+        pass
+    return None
+
+
+def cpu_cache_path(workload):
+    import socket
+    return os.path.join("/tmp", f"tnc_cpu_true_slice_{workload}_{socket.gethostname()}_{os.cpu_count()}.json")
+
+
+def check_against_golden(workload, slice_id, result):
+    """max |err| / rms of a CPU slice result against the reference's recorded output, when the
+    fixture holds this slice id (None otherwise)."""
+    import numpy as np
+    try:
+        exp = np.load(os.path.join(ROOT, "tests", "golden", f"{workload}.expected.npz"))
+        ids = [int(x) for x in exp["slice_ids"]]
+        if slice_id not in ids:
+            return None
+        want = exp["per_slice_c64"][ids.index(slice_id)].reshape(-1)
+        got = result.reshape(-1).numpy()
+        return float(np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)))
+    except (OSError, KeyError):
+        return None
+
+
 def reference_arm(args):
-    """The reference's CPU path (torch.einsum per step) on the host cores; rank 0 only."""
+    """The reference's CPU path on the host cores; rank 0 only.
+
+    ONE TRUE SLICE of the workload -- its real leaves through every scheme step exactly as
+    `tensor_contraction_sparse` executes them (oracle/tn_oracle_torch.py: run_sparse on the sliced
+    leaves) -- is spread over the K timed steps: step i executes the i-th contiguous 1/K of the
+    slice's scheme steps, so the timed region is one real slice, every step a bounded sample, and
+    `value` = 1 slice / (sum of the K step times).  The W warm-up steps execute the leading W/K of
+    another slice and are discarded.  The result is compared with the reference's recorded output
+    of that slice, and the synthetic-operand timing model is printed beside it as a cross-check."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from artensor_b200.backend import ContractionPlan
+    from oracle import tn_oracle_torch as OT
     case = load_workload(args.workload)
     plan = plan_of(case, None, build_native=False)
     cores = os.cpu_count() or 1
-    max_elems = args.cpu_max_elems
-    times = []
-    for it in range(args.warmup + args.steps):
-        secs, n, scaled, wall = cpu_sample(plan, max_elems)
-        if it >= args.warmup:
-            times.append(secs)
-    per_slice = sum(times) / len(times)
-    value = 1.0 / per_slice
-    sample = (f"one slice of {args.workload}: all {n} steps run with torch.einsum on synthetic operands of their true "
-              f"shapes; {scaled} steps above 2^{max_elems.bit_length() - 1} elements run on a sub-block and scaled "
-              f"linearly; {wall:.1f} s of CPU work per sample")
+    torch.set_num_threads(cores)
+    K, W = max(1, args.steps), max(0, args.warmup)
+    n_steps = len(case.scheme)
+    bounds = [(n_steps * i) // K for i in range(K + 1)]
+    try:
+        import numpy as np
+        exp = np.load(os.path.join(ROOT, "tests", "golden", f"{args.workload}.expected.npz"))
+        slice_id = int(exp["slice_ids"][0])
+    except (OSError, KeyError):
+        slice_id = 0
+    need_gib = 4.0 * plan.workspace_bytes / 2 ** 30 if plan.workspace_bytes > (1 << 30) else 1.0
+    avail = host_mem_gib()
+    mode = "true_slice"
+    if avail is not None and avail < need_gib and not os.environ.get("TNC_BENCH_FORCE_TRUE_SLICE"):
+        mode = "model"          # the host cannot hold the slice's intermediates: say so loudly, fall back to the model
+    step_ms, result_err, true_secs = [], None, None
+    if mode == "true_slice":
+        # warm-up: leading steps of another slice, discarded
+        if W > 0:
+            gen = OT.slice_stepper(case, (slice_id + 1) % max(1, 1 << len(case.slicing_bonds)))
+            stop = bounds[min(W, K)]
+            for k, _ in gen:
+                if k is None or k + 1 >= stop:
+                    break
+            del gen
+        gen = OT.slice_stepper(case, slice_id)
+        per_step = []
+        result = None
+        for k, v in gen:
+            if k is None:
+                result = v
+            else:
+                per_step.append(v)
+        for i in range(K):
+            step_ms.append(1e3 * sum(per_step[bounds[i]:bounds[i + 1]]))
+        true_secs = sum(per_step)
+        result_err = check_against_golden(args.workload, slice_id, result)
+        with open(cpu_cache_path(args.workload), "w") as f:
+            json.dump({"workload": args.workload, "slice_id": slice_id, "seconds": true_secs, "cores": cores,
+                       "torch": torch.__version__, "max_err_over_rms_vs_reference_output": result_err}, f)
+    model = None
+    try:
+        secs, n, scaled, wall = cpu_sample(plan, args.cpu_max_elems, budget_s=120.0)
+        model = {"seconds_per_slice": secs, "steps_scaled_from_sub_blocks": scaled, "cpu_seconds_spent": wall,
+                 "error_vs_true_slice": (secs / true_secs - 1.0) if true_secs else None}
+    except Exception as exc:      # the cross-check must not take the line down
+        model = {"failed": str(exc)}
+    if mode == "model":
+        true_secs = model["seconds_per_slice"]
+        step_ms = [1e3 * true_secs / K] * K
+    value = 1.0 / true_secs
+    if mode == "true_slice":
+        sample = (f"ONE true slice (id {slice_id}) of {args.workload}: the real leaves through all {n_steps} scheme steps "
+                  f"with torch.einsum / gather / cat exactly as tensor_contraction_sparse runs them "
+                  f"(oracle/tn_oracle_torch.py), {true_secs:.1f} s on {cores} threads; the {K} timed steps are the "
+                  f"consecutive 1/{K} parts of that slice, the {W} warm-up steps the leading part of another slice; "
+                  f"max |err| / rms against the reference's recorded output of the slice: {result_err}")
+    else:
+        sample = (f"TIMING MODEL ONLY (host has {avail:.0f} GiB available, a true slice needs ~{need_gib:.0f} GiB): every "
+                  f"step's torch.einsum on synthetic operands, large steps on sub-blocks scaled linearly")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_slice * 1e3 * args.slices_per_step, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": sum(step_ms) / len(step_ms), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
-        "config": {"workload": args.workload, "slices_per_step_per_gpu": args.slices_per_step,
-                   "amplitudes_per_slice": int(plan.out_shape[0]) if plan.out_shape else 1},
+        "config": bench_config(args.workload, plan, args.slices_per_step),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "torch": torch.__version__},
+                         "mode": mode, "torch": torch.__version__, "timing_model_cross_check": model},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def bench_config(workload, plan, slices_per_step):
+    """The `config` object both arms print (identical keys and values for the same workload)."""
+    work = plan.work_summary()
+    return {"workload": workload, "slices_per_step_per_gpu": slices_per_step, "sliced_bonds": plan.n_sliced,
+            "total_slices_of_task": f"2^{plan.n_sliced}",
+            "amplitudes_per_slice": int(math.prod(plan.out_shape)),
+            "scheme_steps": work["steps"], "l2": "working set >> L2 (multi-GiB intermediates), no flush"}
 
 
 def plan_of(case, tc_min_flops, build_native=True):
@@ -255,6 +359,7 @@ def main():
     from artensor_b200 import TensorNetworkSimulation, PlanOptions
     from artensor_b200 import _native as N
     from artensor_b200 import contraction as C
+    from artensor_b200.backend import tc_uses_3m
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -366,7 +471,7 @@ def main():
                "h2d_bytes_per_step": int(plan.leaf_blob_elems * 8), "d2h_bytes_per_step": int(res.numel() * 8)}
 
     # ---- roofline of the dominant kernel, measured live (rank 0)
-    roofline, work, breakdown = None, plan.work_summary(), None
+    roofline, work, breakdown, slice_roofline = None, plan.work_summary(), None, None
     if rank == 0:
         pk = peaks()
         reps = 2
@@ -409,7 +514,9 @@ def main():
             ach = st.flops / (best_ms * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
             kind = "tf32" if precision == "3xtf32" else "f16"
-            products = 1 if precision == "f16" else 3
+            three_m = tc_uses_3m(st, precision)
+            # real tensor-core products issued per useful complex one: hi/lo split (x3), 3M complex product (x0.75)
+            products = (1 if precision == "f16" else 3) * (0.75 if three_m else 1.0)
             lib = measure_cublas_peak(dev, kind)
             roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                         "traffic": None, "peak_kind": f"bf16 dense sustained ({pk['source']})",
@@ -419,26 +526,30 @@ def main():
                                    "frac_of_cublas_sustained": products * ach / lib["sustained"],
                                    "frac_of_peak": products * ach / peak},
                         "note": "achieved = 8*M*N*K useful complex64 flops.  The fp32-accurate precisions split every "
-                                "operand in hi + lo and issue 3 tensor-core products per useful one, so the useful-flop "
-                                "ceiling is peak/3; `issued` compares the issued tensor flops with cuBLAS 8192^3 in the "
-                                "same operand type measured in this run"}
+                                "operand in hi + lo (3 real products per useful one) and the 3M complex product needs "
+                                "6*M*N*K real flops instead of 8 (x0.75), so the useful-flop ceiling is peak / "
+                                "products_per_useful_flop; `issued` compares the issued tensor flops with cuBLAS "
+                                "8192^3 in the same operand type measured in this run"}
         else:
             ach = st.bytes_c64 / (best_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "traffic": None, "peak_kind": f"copy bandwidth ({pk['source']})"}
-        kname = {N.TNC_ALGO_TC: f"gemm_2cta_kernel<{precision}>", N.TNC_ALGO_STEM: "stem_kernel", N.TNC_ALGO_SKINNY: "skinny_kernel",
+        kname = {N.TNC_ALGO_TC: f"{'gemm3m_2cta_kernel' if tc_uses_3m(st, precision) else 'gemm_2cta_kernel'}<{precision}>", N.TNC_ALGO_STEM: "stem_kernel", N.TNC_ALGO_SKINNY: "skinny_kernel",
                  N.TNC_ALGO_SIMT: "simt_einsum_kernel"}[rec.algo]
         roofline["kernel"] = kname
-        try:      # DRAM bytes of this kernel on this very step, from the committed ncu --set full capture
+        # DRAM bytes per launch of this kernel on a step of this shape: the committed ncu captures
+        # (profiles/ncu_traffic.json lists kernel, shape and source file of every capture)
+        try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                cap = json.load(f).get(kname)
-            if cap and rec.algo == N.TNC_ALGO_TC and (len(st.m_modes), len(st.n_modes), len(st.k_modes)) == (15, 13, 15):
-                roofline["traffic"] = cap["dram_bytes"]
-                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, "
-                                            "profiles/r01_gemm_sweep_group_traffic.txt; --set full capture: "
-                                            "profiles/r01_ncu_full_fat.txt); algorithmic bytes of the step: %d; floor "
-                                            "for 74 resident 256x256 tiles streaming the whole K: ~64 GB" % st.bytes_c64)
-        except (OSError, ValueError):
+                caps = json.load(f)["captures"]
+            shape = [len(st.m_modes), len(st.n_modes), len(st.k_modes)]
+            for cap in caps:
+                if cap["kernel"] == kname and cap["shape_bits_mnk"] == shape:
+                    roofline["traffic"] = cap["dram_bytes"]
+                    roofline["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel "
+                                                f"on this step shape (ncu --set full, {cap['source']}); algorithmic bytes "
+                                                f"of the step: {st.bytes_c64}")
+        except (OSError, ValueError, KeyError):
             pass
         roofline["step"] = {"index": st.index, "m_bits": len(st.m_modes), "n_bits": len(st.n_modes),
                             "k_bits": len(st.k_modes), "rows": st.nb, "flops": st.flops, "bytes": st.bytes_c64,
@@ -450,6 +561,27 @@ def main():
                      "stem_gbs": stem_bytes / (stem_ms * 1e-3) / 1e9 if stem_ms > 0 else None,
                      "skinny_gbs": skinny_bytes / (skinny_ms * 1e-3) / 1e9 if skinny_ms > 0 else None,
                      "hbm_peak_gbs": pk["hbm_gbs"]}
+        # whole-slice roofline: sum over the executed steps of max(flops / P, bytes / BW), against
+        # the steady-state time of a slice in the timed region.  Two ceilings: P = measured dense peak (one
+        # tensor-core product per useful flop: the complex-half mode's ceiling) and P / products for the
+        # products each step really has to issue in this precision (hi/lo split, 3M where it applies).
+        ideal_single = ideal_issued = 0.0
+        P, BW = pk["bf16_tflops_sustained"] * 1e12, pk["hbm_gbs"] * 1e9
+        for (kind, rec), st in zip(ops, steps):
+            if kind != "einsum":
+                continue
+            prod = 1.0
+            if rec.algo == N.TNC_ALGO_TC:
+                prod = (1 if precision == "f16" else 3) * (0.75 if tc_uses_3m(st, precision) else 1.0)
+            ideal_single += max(st.flops / P, st.bytes_c64 / BW)
+            ideal_issued += max(st.flops * prod / P, st.bytes_c64 / BW)
+        ms_per_slice = ms_max / (total_slices / world)
+        slice_roofline = {"ideal_ms_one_product": ideal_single * 1e3, "ideal_ms_issued_products": ideal_issued * 1e3,
+                          "measured_ms_per_slice": ms_per_slice, "frac_one_product": ideal_single * 1e3 / ms_per_slice,
+                          "frac_issued_products": ideal_issued * 1e3 / ms_per_slice,
+                          "note": "sum over executed steps of max(8BMNK / P, 8(|A|+|B|+|C|) / BW); P = measured bf16 "
+                                  "dense sustained, BW = measured copy bandwidth; measured = steady-state ms per slice "
+                                  "of the timed region (`value`)"}
 
     # ---- the reduced-precision complex-half mode on the same slices (rank 0, N = 1): throughput and
     # fidelity against the complex64 result
@@ -492,7 +624,10 @@ def main():
                     hbest = (hms[i * SLh + 3], st)
             if hbest is not None and hbest[0] > 0:
                 hach = hbest[1].flops / (hbest[0] * 1e-3) / 1e12
-                half["roofline"] = {"bound": "tensor", "kernel": "gemm_2cta_kernel<f16>", "achieved": hach,
+                half["roofline"] = {"bound": "tensor",
+                                    "kernel": ("gemm3m_2cta_kernel" if tc_uses_3m(hbest[1], "f16") else "gemm_2cta_kernel") + "<f16>",
+                                    "products_per_useful_flop": 0.75 if tc_uses_3m(hbest[1], "f16") else 1.0,
+                                    "achieved": hach,
                                     "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                     "frac": hach / pk["bf16_tflops_sustained"],
                                     "step": {"index": hbest[1].index, "ms": hbest[0], "flops": hbest[1].flops}}
@@ -503,27 +638,43 @@ def main():
     # ---- CPU baseline on the host cores (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cached = None
+        try:
+            with open(cpu_cache_path(args.workload)) as f:
+                cached = json.load(f)
+        except (OSError, ValueError):
+            pass
         try:
             secs, n, scaled, wall = cpu_sample(plan, args.cpu_max_elems)
-            cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": (f"one slice of {args.workload}: all {n} steps run with torch.einsum on synthetic operands "
-                              f"of their true shapes, {scaled} steps above 2^{args.cpu_max_elems.bit_length() - 1} "
-                              f"elements on a sub-block and scaled linearly ({wall:.1f} s of CPU work)")}
+            model = (f"timing model: all {n} steps run with torch.einsum on synthetic operands of their true shapes, "
+                     f"{scaled} steps above 2^{args.cpu_max_elems.bit_length() - 1} elements on a sub-block and scaled "
+                     f"linearly ({wall:.1f} s of CPU work) = {secs:.1f} s per slice")
+            if cached and cached.get("cores") == cores:
+                cpu = {"value": 1.0 / cached["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": (f"ONE true slice (id {cached['slice_id']}) of {args.workload} run on this host by "
+                                  f"`bench.py --impl reference` ({cached['seconds']:.1f} s, real leaves through every "
+                                  f"scheme step, oracle/tn_oracle_torch.py; max |err| / rms vs the reference's recorded "
+                                  f"output {cached.get('max_err_over_rms_vs_reference_output')}); cross-check in this run, "
+                                  f"{model} ({secs / cached['seconds'] - 1.0:+.1%} vs the true slice)")}
+            else:
+                cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"one slice of {args.workload}, {model} (no true-slice measurement cached on this host: "
+                                 f"run `bench.py --impl reference` first)"}
         except Exception as exc:  # the baseline must never take the GPU line down
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {exc}"}
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {exc}"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": f"complex64 ({precision} split-precision products on tcgen05, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": args.workload, "slices_per_step_per_gpu": S, "sliced_bonds": plan.n_sliced,
-                       "total_slices_of_task": f"2^{plan.n_sliced}", "amplitudes_per_slice": int(out.numel()),
-                       "scheme_steps": work["steps"], "l2": "working set >> L2 (multi-GiB intermediates), no flush"},
+            "config": bench_config(args.workload, plan, S),
             "useful_tflops": work["ref_flops_per_slice"] * value / 1e12,
             "flops_per_slice": work["ref_flops_per_slice"], "bytes_per_slice": work["ref_bytes_per_slice"],
             "extrapolated_full_task_seconds": (2.0 ** plan.n_sliced) / value,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "breakdown": breakdown,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "slice_roofline": slice_roofline, "breakdown": breakdown,
             "cpu_baseline": cpu, "half_mode": half,
         }
         emit(line)

@@ -13,7 +13,8 @@ the outputs of the real reference recorded in tests/golden/*.expected.npz.
 
   run_normal   <- tensor_contraction          artensor/contraction.py:62-76
   run_sparse   <- tensor_contraction_sparse   artensor/contraction.py:132-205
-  step_time_model / estimate_slice_seconds: timing helpers (no reference counterpart)
+  slice_stepper <- one iteration of the slice loop, simulation.py:107-114, step by step
+  estimate_slice_seconds: timing model on synthetic operands (no reference counterpart; a cross-check)
 """
 import time
 
@@ -68,6 +69,27 @@ def contract_slices(case, slice_ids, dtype=torch.complex64):
         r = func(slice_leaves(leaves, case.slicing_bonds, sidx, int(s)), case.scheme)
         acc = r.clone() if acc is None else acc + r
     return acc
+
+
+def slice_stepper(case, slice_id, dtype=torch.complex64):
+    """ONE true slice of `case` (its real leaves, every scheme step, exactly what
+    `tensor_contraction[_sparse]` would execute for that slice: simulation.py:107-114), cut into
+    single scheme steps: a generator that executes step k when advanced and yields
+    (k, seconds of that step); after the last step it yields (None, result tensor).  The leaf
+    slicing (`select(...).clone()`, simulation.py:110-113) is charged to step 0.  `bench.py --impl
+    reference` spreads the steps of one slice over its timed bench steps with this."""
+    from artensor_b200.cases import slice_leaves
+    sparse = case.pattern != "normal"
+    t0 = time.perf_counter()
+    leaves = {k: v.to(dtype) for k, v in case.leaves.items()}
+    tensors = slice_leaves(leaves, case.slicing_bonds, case.slicing_indices(), int(slice_id))
+    out = None
+    for k, step in enumerate(case.scheme):
+        if k > 0:
+            t0 = time.perf_counter()
+        out = (run_sparse if sparse else run_normal)(tensors, [step])
+        yield k, time.perf_counter() - t0
+    yield None, out
 
 
 # --------------------------------------------------------------------------- timing helpers

@@ -533,6 +533,47 @@ def test_tc_two_cta_blocked_tiles(dev):
         assert err < tol, f"{precision}: max err / rms = {err:.3e}"
 
 
+TC_3M_SHAPES = [(8, 7, 6), (10, 8, 8), (9, 7, 12), (11, 9, 7), (8, 7, 14)]
+
+
+@pytest.mark.parametrize("precision,tol", [("3xf16", 1e-5)])
+@pytest.mark.parametrize("shape", TC_3M_SHAPES)
+def test_tc_3m_complex_product(dev, shape, precision, tol, monkeypatch):
+    """Steps of the fat-GEMM class (>= 64 complex k, >= 128 complex columns, whole 256-row pair
+    tiles) run the 3M (Karatsuba) complex product on planar re / im / re+im panels: it must meet
+    the same bar as the interleaved 4M form it replaces, K = 64 (one k-block) to K = 16384."""
+    m, n, k = shape
+    scheme, leaves, want = single_step_case(m, n, k, seed=m * 100 + n * 10 + k)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    got = run_single_step(dev, scheme, leaves, "tc", precision)
+    err = np.abs(got - want) / rms
+    monkeypatch.setenv("TNC_TC_3M", "0")
+    got4 = run_single_step(dev, scheme, leaves, "tc", precision)
+    err4 = np.abs(got4 - want) / rms
+    print(f"{precision} m={m} n={n} k={k}: 3M max {err.max():.3e} rms {np.sqrt(np.mean(err ** 2)):.3e} | "
+          f"4M max {err4.max():.3e} rms {np.sqrt(np.mean(err4 ** 2)):.3e}")
+    assert not np.array_equal(got, got4), "TNC_TC_3M=0 did not select another kernel"
+    assert err.max() < tol and err4.max() < tol
+
+
+def test_tc_3m_operand_scaling_and_zero(dev):
+    """The 3M panels are scaled one bit lower than the 4M ones (re + im must stay inside fp16):
+    results must not depend on the operands' magnitudes, and a zero operand gives exact zeros."""
+    scheme, leaves, _ = single_step_case(9, 7, 7, seed=78)
+    rng = np.random.RandomState(4)
+    for scale_a, scale_b in [(1e-9, 1.0), (1e6, 1e-12), (6e4, 6e4)]:
+        a = leaves[0].numpy() * scale_a
+        b = leaves[1].numpy() * scale_b
+        a = a * np.where(rng.rand(*a.shape) < 0.25, 2.0 ** -20, 1.0).astype(np.float32)
+        lv = {0: torch.from_numpy(a.astype(np.complex64)), 1: torch.from_numpy(b.astype(np.complex64))}
+        want = np.einsum(scheme[0][1], a.astype(np.complex128), b.astype(np.complex128), optimize=True)
+        got = run_single_step(dev, scheme, lv, "tc", "3xf16")
+        err = np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2))
+        assert err < 1e-5, f"scales {scale_a:g}, {scale_b:g}: max err / rms = {err:.3e}"
+    leaves[1] = torch.zeros_like(leaves[1])
+    assert np.all(run_single_step(dev, scheme, leaves, "tc", "3xf16") == 0)
+
+
 @pytest.mark.parametrize("algo", ["tc", "tc:3xtf32", "stem", "skinny"])
 @pytest.mark.parametrize("name", SMALL)
 def test_forced_algorithm_on_every_step_matches_reference(dev, name, algo):
