@@ -9,10 +9,10 @@ import os
 
 TNC_MAX_BITS = 40
 TNC_MAX_SLICED = 8
-TNC_ABI_VERSION = 5
+TNC_ABI_VERSION = 6
 TNC_PROFILE_SLOTS = 4
 
-TNC_C64, TNC_C32 = 0, 1
+TNC_C64 = 0
 TNC_PHASE_ONCE, TNC_PHASE_SLICE = 0, 1
 TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM, TNC_ALGO_SKINNY = 0, 1, 2, 3
 TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2

@@ -254,8 +254,11 @@ class ContractionPlan:
                  build_native=True):
         self.options = options or PlanOptions()
         self.sparse = sparse
-        self.dtype = {"c64": N.TNC_C64, "c32": N.TNC_C32}[dtype]
-        self.elem_bytes = 8 if self.dtype == N.TNC_C64 else 4
+        if dtype != "c64":
+            raise ValueError(f"dtype {dtype!r}: tensors are stored as complex64 (the complex-half mode is "
+                             f"PlanOptions.tc_precision='f16', an operand precision)")
+        self.dtype = N.TNC_C64
+        self.elem_bytes = 8
         self.slicing_bonds = list(slicing_bonds)
         self.n_sliced = len(self.slicing_bonds)
         if self.n_sliced > 62:
@@ -520,13 +523,27 @@ class ContractionPlan:
             blob = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
             blob = blob.to(torch.complex64)
             return blob if device is None else blob.to(device)
-        stage = getattr(self, "_stage", None)
-        if stage is None or stage.numel() != self.leaf_blob_elems:
-            pin = torch.device(device).type == "cuda" and torch.cuda.is_available()
-            stage = torch.empty(self.leaf_blob_elems, dtype=torch.complex64, pin_memory=pin)
-            self._stage = stage
+        # pinned staging buffers: a ring of two, each guarded by the CUDA event recorded behind its
+        # last host->device copy -- the copy is asynchronous, so the buffer must not be refilled
+        # while an earlier call's copy may still be queued behind a long execute
+        pin = torch.device(device).type == "cuda" and torch.cuda.is_available()
+        ring = getattr(self, "_stages", None)
+        if ring is None:
+            ring = self._stages = {"next": 0, "slots": [None, None]}
+        i = ring["next"]
+        ring["next"] = (i + 1) % len(ring["slots"])
+        slot = ring["slots"][i]
+        if slot is None or slot[0].numel() != self.leaf_blob_elems:
+            slot = ring["slots"][i] = [torch.empty(self.leaf_blob_elems, dtype=torch.complex64, pin_memory=pin), None]
+        stage, event = slot
+        if event is not None:
+            event.synchronize()
         torch.cat(parts, out=stage)
-        return stage.to(device, non_blocking=True)
+        blob = stage.to(device, non_blocking=True)
+        if pin:
+            slot[1] = torch.cuda.Event()
+            slot[1].record(torch.cuda.current_stream(device))
+        return blob
 
     def execute(self, leaf_blob, out, slice_begin, slice_end, workspace, stream_ptr):
         """Enqueue the contraction of slices [slice_begin, slice_end) on the given stream;

@@ -18,8 +18,6 @@ here a SchemeError / NativeError (both RuntimeError/ValueError subclasses) is ra
 
 There is no CPU path: tensors must live on a CUDA device and libtnc_b200.so must be built.
 """
-import weakref
-
 import torch
 
 from . import _native as N
@@ -39,10 +37,30 @@ def mode_options(mode, options=None):
     options = options or default_options()
     return replace(options, tc_precision="f16") if mode == "chalf" else options
 
-# scheme object id -> (weakref-free) cache of compiled plans keyed by leaf shapes / dtype.
-# Schemes are plain lists; we key on id() and keep a reference to the scheme so the id stays valid.
+# Compiled plans, keyed by the CONTENT of the scheme (a scheme list mutated in place must not hit
+# the plan of its old contents), the leaf shapes, the slicing and the options.
 _PLAN_CACHE = {}
 _PLAN_CACHE_MAX = 16
+
+
+def scheme_fingerprint(scheme):
+    """Digest of everything in a scheme that the plan depends on: edges, einsum strings, the row
+    index tensors of sparse steps, reshape / next shapes."""
+    import hashlib
+    import numpy as np
+    h = hashlib.blake2b(digest_size=16)
+    for step in scheme:
+        h.update(repr((tuple(step[0]), step[1], len(step))).encode())
+        if len(step) >= 3:
+            for side in step[2]:
+                h.update(b"|")
+                for idx in side:
+                    arr = idx.numpy() if torch.is_tensor(idx) else np.asarray(idx)
+                    h.update(np.ascontiguousarray(arr, dtype=np.int64).tobytes())
+                    h.update(b";")
+        if len(step) >= 5:
+            h.update(repr((step[3], tuple(step[4]))).encode())
+    return h.hexdigest()
 
 
 def _leaf_shapes(tensors, ids):
@@ -69,31 +87,38 @@ def get_plan(scheme, tensors, sparse, *, slicing_bonds=(), slicing_indices=None,
     ids = _scheme_ids(scheme)
     shapes = _leaf_shapes(tensors, ids)
     options = options or default_options()
-    key = (id(scheme), sparse, dtype, tuple(sorted(shapes.items())), tuple(slicing_bonds),
+    key = (scheme_fingerprint(scheme), sparse, dtype, tuple(sorted(shapes.items())), tuple(slicing_bonds),
            repr(sorted((slicing_indices or {}).items(), key=repr)), repr(options))
     hit = _PLAN_CACHE.get(key)
-    if hit is not None and hit[0] is scheme:
-        return hit[1]
+    if hit is not None:
+        return hit
     plan = ContractionPlan(scheme, shapes, sparse, slicing_bonds=slicing_bonds, slicing_indices=slicing_indices,
                            dtype=dtype, options=options)
     if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
         _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-    _PLAN_CACHE[key] = (scheme, plan)
+    _PLAN_CACHE[key] = plan
     return plan
 
 
 _WORKSPACES = {}
 
 
-def get_workspace(device, nbytes):
-    """One growing workspace per device (the arena of include/tnc_b200.h)."""
+def get_workspace(device, nbytes, stream=None):
+    """One growing workspace (the arena of include/tnc_b200.h) per (device, stream): executions
+    enqueued on different streams of one device never share an arena, executions on one stream are
+    ordered by the stream.  `stream` is a torch.cuda.Stream, default the current one."""
     device = torch.device(device)
-    ws = _WORKSPACES.get(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if stream is None:
+        stream = torch.cuda.current_stream(device)
+    key = (device, int(stream.cuda_stream))
+    ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
-        _WORKSPACES.pop(device, None)
+        _WORKSPACES.pop(key, None)
         ws = None
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _WORKSPACES[device] = ws
+        _WORKSPACES[key] = ws
     return ws
 
 
@@ -143,8 +168,11 @@ def tensor_contraction_sparse(tensors, contraction_scheme, scientific_notation=F
     the same contract, result == tensor * 10**factor with max|tensor| == 1."""
     plan, out = _run(tensors, contraction_scheme, sparse=True)
     for s in contraction_scheme:
-        j = s[0][1]
-        tensors[j] = []
+        # consumed right operands are dropped like the reference does (contraction.py:174,188,191);
+        # single-chunk batched steps keep tensors[j] there (:175-178: the gathered rows) -- here the
+        # entry is left as it was, the gathered copy is never materialised
+        if not (len(s) > 3 and len(s[2][0]) == 1 and len(s[2][1]) == 1):
+            tensors[s[0][1]] = []
     tensors[plan.result_slot] = out
     if scientific_notation:
         nf = out.abs().max()

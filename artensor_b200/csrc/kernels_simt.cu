@@ -39,10 +39,6 @@ template <> struct Cplx<float2> {
     static __device__ __forceinline__ float2 load(const float2* p) { return *p; }
     static __device__ __forceinline__ void store(float2* p, float2 v) { *p = v; }
 };
-template <> struct Cplx<__half2> {
-    static __device__ __forceinline__ float2 load(const __half2* p) { return __half22float2(*p); }
-    static __device__ __forceinline__ void store(__half2* p, float2 v) { *p = __float22half2_rn(v); }
-};
 
 // ------------------------------------------------------------------ generic einsum
 // One thread per output element.  The output index is split into its bits; every bit that
@@ -364,8 +360,11 @@ int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
         }
     }
     const int grid = grid_for(p.total);
-    if (dtype == TNC_C64) simt_einsum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
-    else simt_einsum_kernel<__half2><<<grid, kThreads, 0, s>>>(p);
+    if (dtype != TNC_C64) {
+        set_error("einsum: only complex64 tensors are supported");
+        return TNC_ERR_UNSUPPORTED;
+    }
+    simt_einsum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }
@@ -381,10 +380,11 @@ int launch_leaf_gather(const LeafDev* dev_leaves, int n, int max_elems, const vo
                        void* arena, uint64_t slice_id, int dtype, cudaStream_t s) {
     (void)max_elems;
     if (n <= 0) return TNC_OK;
-    if (dtype == TNC_C64)
-        leaf_gather_kernel<float2><<<n, 128, 0, s>>>(dev_leaves, (const float2*)blob, (char*)arena, slice_id);
-    else
-        leaf_gather_kernel<__half2><<<n, 128, 0, s>>>(dev_leaves, (const __half2*)blob, (char*)arena, slice_id);
+    if (dtype != TNC_C64) {
+        set_error("leaves: only complex64 tensors are supported");
+        return TNC_ERR_UNSUPPORTED;
+    }
+    leaf_gather_kernel<float2><<<n, 128, 0, s>>>(dev_leaves, (const float2*)blob, (char*)arena, slice_id);
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }
@@ -407,8 +407,11 @@ int launch_accum(const AccumParams& p, int dtype, cudaStream_t s) {
     const int64_t total = p.rows << p.rank;
     if (total <= 0) return TNC_OK;
     const int grid = grid_for(total);
-    if (dtype == TNC_C64) accum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
-    else accum_kernel<__half2><<<grid, kThreads, 0, s>>>(p);
+    if (dtype != TNC_C64) {
+        set_error("accumulate: only complex64 tensors are supported");
+        return TNC_ERR_UNSUPPORTED;
+    }
+    accum_kernel<float2><<<grid, kThreads, 0, s>>>(p);
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }

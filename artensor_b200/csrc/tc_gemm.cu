@@ -1671,8 +1671,13 @@ struct TcGemmOp {
     int bn = 256;
     GemmArgs args{};
     int64_t tiles = 0;
-    char* maps_for = nullptr;                         // workspace base the tensor maps were encoded for
-    CUtensorMap maps[4];
+    // tensor maps per workspace base (they embed device addresses); the only state a run touches, under `mu`:
+    // a plan may be executed from several host threads, each with its own workspace and stream
+    struct Maps {
+        CUtensorMap m[4];
+    };
+    std::mutex mu;
+    std::map<char*, Maps> maps_by_ws;
     int blocked = 0, blocked_b = 0;                   // tile-contiguous panels (A, B')
     int two_cta = 0;                                  // CTA pairs (cta_group::2) on 256 x 256 tiles
     int use_3m = 0;                                   // 3M complex product on planar panels (gemm3m_2cta_kernel)
@@ -1931,10 +1936,9 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     const int elem = f16 ? 2 : 4;
     int n_launch = 3;
     uint32_t* words = (uint32_t*)(ws + op->words_off);
-    op->pa.amax = f16 ? words : nullptr;
-    op->pb.amax = f16 ? words + 1 : nullptr;
-    op->args.amax = f16 ? words : nullptr;
-    op->args.sync_counter = words + 32;
+    PackDesc pa = op->pa, pb = op->pb;                  // the op itself stays read-only: a run only fills local copies
+    pa.amax = f16 ? words : nullptr;
+    pb.amax = f16 ? words + 1 : nullptr;
     if (f16 || op->args.sync_every) TNC_CUDA(cudaMemsetAsync(words, 0, 256, s));
     if (f16) {
         // one launch finds the largest magnitude of both operands (whole source tensors: an upper
@@ -1948,13 +1952,21 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
         TNC_CUDA(cudaGetLastError());
         n_launch = 4;
     }
-    int rc = launch_pack(op->pa, ws + op->a_off, ws + op->ahi_off, lo ? ws + op->alo_off : nullptr, s);
+    int rc = launch_pack(pa, ws + op->a_off, ws + op->ahi_off, lo ? ws + op->alo_off : nullptr, s);
     if (rc != TNC_OK) return rc;
     if (hook) hook(ctx);
-    rc = launch_pack(op->pb, ws + op->b_off, ws + op->bhi_off, lo ? ws + op->blo_off : nullptr, s);
+    rc = launch_pack(pb, ws + op->b_off, ws + op->bhi_off, lo ? ws + op->blo_off : nullptr, s);
     if (rc != TNC_OK) return rc;
     if (hook) hook(ctx);
-    if (op->maps_for != ws) {
+    TcGemmOp::Maps maps;
+    std::unique_lock<std::mutex> lock(op->mu);
+    auto cached = op->maps_by_ws.find(ws);
+    if (cached != op->maps_by_ws.end()) {
+        maps = cached->second;
+        lock.unlock();
+    } else {
+        lock.unlock();
+        CUtensorMap* const om = maps.m;
         const int64_t batch_a = op->a_batched ? op->batch : 1, batch_b = op->b_batched ? op->batch : 1;
         const int box_b = op->two_cta ? 128 : op->bn;
         const int bk = bk_of(op->precision);
@@ -1966,52 +1978,56 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
             const int hl = lo ? 2 : 1;
             const int64_t nkb3 = op->K / 2 / 64;
             const int64_t blocks_a = nkb3 * op->args.m_tiles * batch_a, blocks_b = nkb3 * op->args.n_tiles * batch_b;
-            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, 2, 64, 128 * hl, blocks_a * 3, 128 * hl)) != TNC_OK) return rc;
-            if ((rc = make_map(&op->maps[2], ws + op->bhi_off, 2, 64, 128, blocks_b * 3 * hl, 64)) != TNC_OK) return rc;
-            op->maps[1] = op->maps[0];
-            op->maps[3] = op->maps[2];
+            if ((rc = make_map(&om[0], ws + op->ahi_off, 2, 64, 128 * hl, blocks_a * 3, 128 * hl)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[2], ws + op->bhi_off, 2, 64, 128, blocks_b * 3 * hl, 64)) != TNC_OK) return rc;
+            om[1] = om[0];
+            om[3] = om[2];
         } else if (op->blocked) {
             // `blocks` blocks of [rows][128 bytes], one per (tile, k-block)
             const int64_t blocks_a = nkb * op->args.m_tiles * batch_a;
-            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
-            if ((rc = make_map(&op->maps[1], lo_a, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[0], ws + op->ahi_off, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[1], lo_a, elem, bk, BM, blocks_a, BM)) != TNC_OK) return rc;
         } else {
             // K-major panel [batch][rows][K]; folded rows are part of M
-            if ((rc = make_map(&op->maps[0], ws + op->ahi_off, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
-            if ((rc = make_map(&op->maps[1], lo_a, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[0], ws + op->ahi_off, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[1], lo_a, elem, op->K, op->M, batch_a, BM)) != TNC_OK) return rc;
         }
         if (op->use_3m) {
         } else if (op->blocked_b) {
             const int64_t blocks_b = nkb * op->args.n_tiles * batch_b;
-            if ((rc = make_map(&op->maps[2], ws + op->bhi_off, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
-            if ((rc = make_map(&op->maps[3], lo_b, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[2], ws + op->bhi_off, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[3], lo_b, elem, bk, op->bn, blocks_b, box_b)) != TNC_OK) return rc;
         } else {
             // [batch][rows][K]; a folded panel ([row of B][n][k], no batch) is one matrix of N rows
-            if ((rc = make_map(&op->maps[2], ws + op->bhi_off, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
-            if ((rc = make_map(&op->maps[3], lo_b, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[2], ws + op->bhi_off, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
+            if ((rc = make_map(&om[3], lo_b, elem, op->K, op->N, batch_b, box_b)) != TNC_OK) return rc;
         }
-        op->maps_for = ws;
+        lock.lock();
+        op->maps_by_ws.emplace(ws, maps);
+        lock.unlock();
     }
     GemmArgs g = op->args;
     g.c = (float*)(ws + op->c_off);
+    g.amax = f16 ? words : nullptr;
+    g.sync_counter = words + 32;
     // persistent grid: one CTA per SM (the shared-memory footprint allows no more), every CTA
     // walks tiles c, c + grid, ...
     int64_t grid = std::min<int64_t>(op->tiles, sm_count());
     if (op->two_cta) grid &= ~(int64_t)1;               // whole pairs; tiles is even here
     g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
     if (op->use_3m) {
-        rc = launch_gemm3m<TNC_TC_3XF16>(op->maps, g, grid, s);
+        rc = launch_gemm3m<TNC_TC_3XF16>(maps.m, g, grid, s);
     } else if (op->two_cta) {
         switch (op->precision) {
-            case TNC_TC_3XF16: rc = launch_gemm_2cta<TNC_TC_3XF16>(op->maps, g, grid, s); break;
-            case TNC_TC_F16: rc = launch_gemm_2cta<TNC_TC_F16>(op->maps, g, grid, s); break;
-            default: rc = launch_gemm_2cta<TNC_TC_3XTF32>(op->maps, g, grid, s); break;
+            case TNC_TC_3XF16: rc = launch_gemm_2cta<TNC_TC_3XF16>(maps.m, g, grid, s); break;
+            case TNC_TC_F16: rc = launch_gemm_2cta<TNC_TC_F16>(maps.m, g, grid, s); break;
+            default: rc = launch_gemm_2cta<TNC_TC_3XTF32>(maps.m, g, grid, s); break;
         }
     } else {
         switch (op->precision) {
-            case TNC_TC_3XF16: rc = launch_gemm_bn<TNC_TC_3XF16>(op->bn, op->maps, g, grid, s); break;
-            case TNC_TC_F16: rc = launch_gemm_bn<TNC_TC_F16>(op->bn, op->maps, g, grid, s); break;
-            default: rc = launch_gemm_bn<TNC_TC_3XTF32>(op->bn, op->maps, g, grid, s); break;
+            case TNC_TC_3XF16: rc = launch_gemm_bn<TNC_TC_3XF16>(op->bn, maps.m, g, grid, s); break;
+            case TNC_TC_F16: rc = launch_gemm_bn<TNC_TC_F16>(op->bn, maps.m, g, grid, s); break;
+            default: rc = launch_gemm_bn<TNC_TC_3XTF32>(op->bn, maps.m, g, grid, s); break;
         }
     }
     if (rc != TNC_OK) return rc;

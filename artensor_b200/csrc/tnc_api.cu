@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <memory>
 
@@ -62,8 +63,8 @@ struct tnc_plan {
     int64_t leaves_off = 0;
     char* dev_blob = nullptr;
     int64_t workspace_bytes = 0;
-    int64_t last_launches = 0;
-    int elem_bytes() const { return dtype == TNC_C64 ? 8 : 4; }
+    std::atomic<int64_t> last_launches{0};   // written once at the end of an execute / profile call
+    int elem_bytes() const { return 8; }
 };
 
 namespace {
@@ -103,7 +104,7 @@ int tnc_abi_version(void) { return TNC_ABI_VERSION; }
 const char* tnc_last_error(void) { return g_error.c_str(); }
 
 int tnc_plan_create(int32_t dtype, int32_t n_sliced_bonds, tnc_plan** out) {
-    if (!out || (dtype != TNC_C64 && dtype != TNC_C32) || n_sliced_bonds < 0 || n_sliced_bonds > 63) {
+    if (!out || dtype != TNC_C64 || n_sliced_bonds < 0 || n_sliced_bonds > 63) {
         set_error("plan_create: bad arguments (dtype=%d, sliced bonds=%d)", dtype, n_sliced_bonds);
         return TNC_ERR_INVALID;
     }
@@ -481,7 +482,7 @@ int64_t tnc_plan_num_ops(const tnc_plan* plan, int32_t phase) {
     return (int64_t)plan->ops[phase].size();
 }
 
-int64_t tnc_plan_last_launches(const tnc_plan* plan) { return plan ? plan->last_launches : -1; }
+int64_t tnc_plan_last_launches(const tnc_plan* plan) { return plan ? plan->last_launches.load() : -1; }
 
 // NVTX range per operation ("tc m15 n13 k15 rows1", "skinny ...", "chain x13", "leaves", "accum"), only
 // with TNC_NVTX=1: lets ncu / nsys filter and group the launches by step class
@@ -504,13 +505,15 @@ struct OpRange {
     }
 };
 
-static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_id, void* accum_out, char* ws,
-                  cudaStream_t st, LaunchHook hook = nullptr, void* hook_ctx = nullptr) {
+// Enqueues one operation; the plan is only read (a finalized plan may be executed from several host
+// threads at once, each with its own workspace and stream), launches are counted into *n_launches.
+static int run_op(const tnc_plan* plan, const Op& op, const void* leaf_blob, uint64_t slice_id, void* accum_out, char* ws,
+                  cudaStream_t st, int64_t* n_launches, LaunchHook hook = nullptr, void* hook_ctx = nullptr) {
     if (op.kind == OP_EINSUM && op.chain_len < 0) return TNC_OK;       // ran with the head of its chain
     OpRange range(op);
     switch (op.kind) {
         case OP_LEAVES: {
-            plan->last_launches += op.leaf_count > 0;
+            *n_launches += op.leaf_count > 0;
             const LeafDev* dl = (const LeafDev*)(plan->dev_blob + plan->leaves_off) + op.leaf_begin;
             return launch_leaf_gather(dl, op.leaf_count, 0, leaf_blob, ws, slice_id, plan->dtype, st);
         }
@@ -518,19 +521,19 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
             const tnc_einsum& e = op.e;
             if (op.chain_len < 0) return TNC_OK;                 // ran with the head of its chain
             if (op.chain_len > 1) {
-                plan->last_launches += 1;
+                *n_launches += 1;
                 return launch_simt_chain((const ChainStep*)(plan->dev_blob + op.chain_off), op.chain_len, ws, plan->dev_blob, st);
             }
             if (op.tc) {
                 int launches = 0;
                 int rc = tc_gemm_run(op.tc.get(), ws, st, hook, hook_ctx, &launches);
-                plan->last_launches += launches;
+                *n_launches += launches;
                 return rc;
             }
             if (e.algo == TNC_ALGO_STEM || e.algo == TNC_ALGO_SKINNY) {
                 const int32_t* ra = e.rows_a >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_a]) : nullptr;
                 const int32_t* rb = e.rows_b >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_b]) : nullptr;
-                plan->last_launches += 1;
+                *n_launches += 1;
                 if (e.algo == TNC_ALGO_SKINNY)
                     return launch_skinny(e, plan->tc_precision, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st);
                 const int32_t* seg = op.seg_off >= 0 ? (const int32_t*)(plan->dev_blob + op.seg_off) : nullptr;
@@ -558,11 +561,11 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
                 p.c2a[e.h_c[i]] = e.h_a[i];
                 p.c2b[e.h_c[i]] = e.h_b[i];
             }
-            plan->last_launches += 1;
+            *n_launches += 1;
             return launch_simt_einsum(p, plan->dtype, st);
         }
         case OP_PERMUTE: {
-            plan->last_launches += 1;
+            *n_launches += 1;
             if (plan->dtype == TNC_C64) {
                 PackDesc d{};
                 d.rank = op.p.src.rank;
@@ -581,7 +584,7 @@ static int run_op(tnc_plan* plan, Op& op, const void* leaf_blob, uint64_t slice_
             return launch_permute(p, plan->elem_bytes(), st);
         }
         case OP_ACCUM: {
-            plan->last_launches += 1;
+            *n_launches += 1;
             if (plan->dtype == TNC_C64 && op.a.src.rank >= 8 && op.a.src.rank < 40) {
                 // large results: the tiled permutation kernel in read-add-write mode
                 PackDesc d{};
@@ -632,17 +635,21 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
     }
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    plan->last_launches = 0;
-    if (slice_begin == slice_end) return TNC_OK;
+    int64_t launches = 0;
+    if (slice_begin == slice_end) {
+        plan->last_launches = 0;
+        return TNC_OK;
+    }
     for (auto& op : plan->ops[TNC_PHASE_ONCE]) {
-        int rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, st);
+        int rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, st, &launches);
         if (rc != TNC_OK) return rc;
     }
     for (uint64_t s = slice_begin; s < slice_end; ++s)
         for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
-            int rc = run_op(plan, op, leaf_blob, s, accum_out, ws, st);
+            int rc = run_op(plan, op, leaf_blob, s, accum_out, ws, st, &launches);
             if (rc != TNC_OK) return rc;
         }
+    plan->last_launches = launches;
     return TNC_OK;
 }
 
@@ -673,7 +680,7 @@ int tnc_plan_profile(tnc_plan* plan, const void* leaf_blob, uint64_t slice_id, v
     }
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    plan->last_launches = 0;
+    int64_t launches = 0;
     float* outs[2] = {ms_once, ms_slice};
     for (int ph = 0; ph < 2; ++ph) {
         const size_t n = plan->ops[ph].size();
@@ -686,7 +693,7 @@ int tnc_plan_profile(tnc_plan* plan, const void* leaf_blob, uint64_t slice_id, v
         for (size_t i = 0; i < n && rc == TNC_OK; ++i) {
             first[i] = ctx.events.size() - 1;
             const size_t before = ctx.events.size();
-            rc = run_op(plan, plan->ops[ph][i], leaf_blob, slice_id, accum_out, ws, st, profile_hook, &ctx);
+            rc = run_op(plan, plan->ops[ph][i], leaf_blob, slice_id, accum_out, ws, st, &launches, profile_hook, &ctx);
             if (rc == TNC_OK && ctx.events.size() == before) ctx.mark();   // single-launch operation
             if (ctx.failed && rc == TNC_OK) {
                 set_error("profile: could not record an event");
@@ -706,6 +713,7 @@ int tnc_plan_profile(tnc_plan* plan, const void* leaf_blob, uint64_t slice_id, v
         for (auto& e : ctx.events) cudaEventDestroy(e);
         if (rc != TNC_OK) return rc;
     }
+    plan->last_launches = launches;
     return TNC_OK;
 }
 

@@ -38,6 +38,18 @@ def _reference():
             "TensorNetworkSimulation.from_case()") from e
 
 
+def _reference_simulation_class():
+    """The reference's own `TensorNetworkSimulation` (simulation.py:33-148) when `artensor` is
+    importable: the class below subclasses it and overrides only the hot path (SURVEY.md 7.1
+    step 2).  Without the reference (the GPU box) the base is `object` and only frozen cases
+    (`from_case`) can be contracted."""
+    try:
+        import artensor
+        return artensor.TensorNetworkSimulation
+    except ImportError:  # pragma: no cover - depends on the environment
+        return object
+
+
 def check_bitstrings(bitstrings):
     """simulation.py:14-23"""
     if len(bitstrings):
@@ -45,18 +57,10 @@ def check_bitstrings(bitstrings):
     return 'normal', 1
 
 
-def get_bond_tensors(tensor_bonds):
-    """simulation.py:25-31"""
-    bond_tensors = {}
-    for i, bonds in tensor_bonds.items():
-        for b in bonds:
-            bond_tensors.setdefault(b, set()).add(i)
-    return bond_tensors
-
-
 def slicing_dims(tensors, tensor_bonds, slicing_bonds):
     """{bond: [(tid, dim)]} with dim counted on the actual un-sliced tensor (the hidden
-    bitstring-batch dim of sparse final-qubit leaves included)."""
+    bitstring-batch dim of sparse final-qubit leaves included; simulation.py:60-65 counts on the
+    bond list and misses it)."""
     out = {}
     for bond in slicing_bonds:
         lst = []
@@ -76,43 +80,50 @@ def partition_slices(begin, end, rank, world):
     return lo, hi
 
 
-class TensorNetworkSimulation:
+_Base = _reference_simulation_class()
+
+
+class TensorNetworkSimulation(_Base):
+    """The reference's simulation object with the hot path replaced.
+
+    Inherited unchanged when the reference is importable: the constructor's fields, the
+    constructors `from_circuit_file` / `from_tn_circuit` (simulation.py:119-148) and the order
+    search inside `prepare_contraction` (simulation.py:47-77).  Overridden: `update_scheme`
+    (scheme compilers of this package), `contraction` (the native executor instead of the Python
+    slice loop) and the slicing bookkeeping that `prepare_contraction` leaves behind."""
+
     def __init__(self, tensors, tensor_bonds, bond_dims, final_qubits, bitstrings, pattern, max_bitstrings) -> None:
-        self.tensors = tensors
-        self.tensor_bonds = tensor_bonds
-        self.bond_dims = bond_dims
-        self.final_qubits = final_qubits
-        self.bitstrings = bitstrings
-        self.pattern = pattern
-        self.max_bitstrings = max_bitstrings
+        if _Base is not object:
+            super().__init__(tensors, tensor_bonds, bond_dims, final_qubits, bitstrings, pattern, max_bitstrings)
+        else:
+            self.tensors, self.tensor_bonds, self.bond_dims = tensors, tensor_bonds, bond_dims
+            self.final_qubits, self.bitstrings = final_qubits, bitstrings
+            self.pattern, self.max_bitstrings = pattern, max_bitstrings
         self.plan_options = PlanOptions()
         self.scheme_compiler = "b200"      # or "reference": contraction.py:23-59 / :208-342 unchanged
+        self.shard_bonds = []              # open output bonds fixed per shard (prepare_open_qubit_shards)
+        self.permute_dims = None
         self._plan_cache = {}
 
-    # ---- planning: the reference's order search, unchanged (simulation.py:47-88) ----
+    # ---- planning ----
     def prepare_contraction(self, sc_target=30, trials=6, iters=20, betas=np.linspace(0.1, 10, 100),
                             slicing_repeat=4, start_seed=0, alpha=32.0):
-        ref = _reference()
-        bond_tensors = get_bond_tensors(self.tensor_bonds)
-        betas = np.linspace(3.0, 21.0, 61)   # simulation.py:52 overrides the argument
-        order_slicing, slicing_bonds, self.ctree = ref.find_order(
-            self.tensor_bonds, self.bond_dims, self.final_qubits, 0, self.max_bitstrings,
-            sc_target=sc_target, trials=trials, iters=iters, betas=betas, start_seed=start_seed,
-            slicing_repeat=slicing_repeat, alpha=alpha)
-        self.slicing_bonds = list(slicing_bonds)
+        """The reference's order search and slicing, unchanged (simulation.py:47-77 through
+        `super()`); afterwards the slicing indices are recounted on the real tensors
+        (`slicing_dims`) and kept in slice-id order."""
+        if _Base is object:
+            _reference()                   # raises the explanatory ImportError
+        self._sc_target = sc_target
+        self.shard_bonds = []
+        super().prepare_contraction(sc_target=sc_target, trials=trials, iters=iters, betas=betas,
+                                    slicing_repeat=slicing_repeat, start_seed=start_seed, alpha=alpha)
+        self.slicing_bonds = list(self.slicing_indices.keys())
         self.slicing_indices = slicing_dims(self.tensors, self.tensor_bonds, self.slicing_bonds)
-        self.update_scheme(sc_target, self.bitstrings)
-        self.permute_dims = None
         if len(self.output_bonds) > 0:
-            bond_inds = []
-            for x in range(len(self.output_bonds)):
-                assert len(bond_tensors[self.output_bonds[x]]) == 1
-                tensor_id = next(iter(bond_tensors[self.output_bonds[x]]))
-                assert tensor_id in self.final_qubits
-                bond_inds.append(list(self.final_qubits).index(tensor_id))
-            self.permute_dims = tuple(int(d) for d in np.argsort(bond_inds))
-            if self.pattern == 'sparse':
-                self.permute_dims = [0] + [dim + 1 for dim in self.permute_dims]
+            self.permute_dims = [int(d) for d in self.permute_dims]
+        else:
+            self.permute_dims = None
+        self._plan_cache.clear()
 
     def update_scheme(self, sc_target=30, bitstrings=[]):
         """simulation.py:79-88.  The tree is compiled by artensor_b200.scheme (layout-friendly mode
@@ -131,6 +142,36 @@ class TensorNetworkSimulation:
             assert len(self.bitstrings_sorted) <= self.max_bitstrings
         self._plan_cache.clear()
 
+    def prepare_open_qubit_shards(self, n_bits):
+        """Full-amplitude contractions over several GPUs: the FIRST `n_bits`
+        output qubits (most significant in the qubit-ordered result) are fixed per shard instead
+        of being kept as open modes, so that shard `v` computes `result[bits of v, ...]` and the
+        2^n_bits shards CONCATENATE to the full tensor -- no 2^n-amplitude reduce.  The shard
+        bonds are sliced out of a copy of the contraction tree (the reference's own
+        `ContractionTree.slicing`, contraction_tree.py:203-221) and the scheme is recompiled; in
+        the slice id they are the most significant bits, so a shard is a contiguous slice range."""
+        if self.pattern != 'normal':
+            raise ValueError("open-qubit sharding applies to full-amplitude (normal) contractions")
+        if self.shard_bonds:
+            raise ValueError("the simulation is already sharded")
+        n_out = len(self.output_bonds)
+        if not 0 < n_bits < n_out:
+            raise ValueError(f"n_bits must be in (0, {n_out})")
+        by_qubit = [self.output_bonds[self.permute_dims[q]] for q in range(n_out)]   # output bond of qubit q
+        shard_bonds = by_qubit[:n_bits]
+        regular = list(self.slicing_bonds)
+        tree = deepcopy(self.ctree)
+        for bond in shard_bonds:
+            tree.slicing(bond)
+        self.ctree = tree
+        self.shard_bonds = shard_bonds
+        self.slicing_bonds = shard_bonds + regular
+        self.slicing_indices = slicing_dims(self.tensors, self.tensor_bonds, self.slicing_bonds)
+        self.update_scheme(getattr(self, "_sc_target", 30), self.bitstrings)
+        rest = by_qubit[n_bits:]
+        order = [rest.index(b) for b in self.output_bonds]       # qubit rank of every remaining output dim
+        self.permute_dims = [int(d) for d in np.argsort(order)]
+
     # ---- the hot path ----
     def plan(self, mode="c64"):
         """Compiled plan for a compute mode: "c64" (fp32-accurate) or "chalf" (reduced-precision
@@ -148,7 +189,7 @@ class TensorNetworkSimulation:
         return self.tensors.keys() if isinstance(self.tensors, dict) else range(len(self.tensors))
 
     def contraction(self, tensors=None, dtype=torch.complex64, device='cuda', slice_range=None, group=None,
-                    reduce_result=True):
+                    reduce_result=True, gather_shards=False):
         """Sum of the contraction over slices (simulation.py:90-117).
 
         dtype:       torch.complex64 (fp32-accurate) or torch.complex32 (reduced-precision
@@ -157,7 +198,11 @@ class TensorNetworkSimulation:
         group:       torch.distributed process group (or True for the default group): the slice
                      range is block-partitioned over its ranks and the partial amplitude tensors are
                      summed with one all-reduce (NCCL over NVLink when the tensors are CUDA).
-        """
+
+        After `prepare_open_qubit_shards(b)` the 2^b shards are block-partitioned over the ranks
+        instead: every rank contracts ALL slices of its shards and returns them stacked,
+        `[shards of this rank] + [2] * remaining qubits` (qubit order); nothing is reduced.
+        `gather_shards=True` all-gathers them into the full `[2] * n` tensor on every rank."""
         device = torch.device(device)
         if device.type != 'cuda':
             raise RuntimeError("artensor_b200 executes on CUDA devices only (no CPU fallback); got device=%r" % (device,))
@@ -166,41 +211,53 @@ class TensorNetworkSimulation:
         src = self.tensors if tensors is None else tensors
         ids = list(self._ids())
         plan = self.plan(_c._DTYPES[dtype])
-        begin, end = (0, plan.n_slices) if slice_range is None else slice_range
+        dist = pg = None
         if group is not None:
             import torch.distributed as dist
             pg = None if group is True else group
+        if self.shard_bonds:
+            return self._contract_shards(plan, {i: src[i] for i in ids}, device, dist, pg, slice_range, gather_shards)
+        begin, end = (0, plan.n_slices) if slice_range is None else slice_range
+        if dist is not None:
             begin, end = partition_slices(begin, end, dist.get_rank(pg), dist.get_world_size(pg))
         with torch.cuda.device(device):
             blob = plan.pack_leaves({i: src[i] for i in ids}, device=device)
             collect_tensor = torch.zeros(plan.out_shape, dtype=torch.complex64, device=device)
             ws = _c.get_workspace(device, plan.workspace_bytes)
             plan.execute(blob, collect_tensor, begin, end, ws, torch.cuda.current_stream(device).cuda_stream)
-            if group is not None and reduce_result:
-                import torch.distributed as dist
-                dist.all_reduce(torch.view_as_real(collect_tensor), op=dist.ReduceOp.SUM,
-                                group=None if group is True else group)
+            if dist is not None and reduce_result:
+                dist.all_reduce(torch.view_as_real(collect_tensor), op=dist.ReduceOp.SUM, group=pg)
         if len(self.output_bonds) > 0 and self.permute_dims is not None:
             collect_tensor = collect_tensor.permute(self.permute_dims)
         return collect_tensor
 
+    def _contract_shards(self, plan, leaves, device, dist, pg, slice_range, gather):
+        n_shards = 1 << len(self.shard_bonds)
+        per_shard = plan.n_slices // n_shards                     # the regular slices, summed inside a shard
+        rank, world = (dist.get_rank(pg), dist.get_world_size(pg)) if dist is not None else (0, 1)
+        if n_shards % world:
+            raise ValueError(f"{n_shards} shards cannot be split evenly over {world} ranks")
+        first, last = partition_slices(0, n_shards, rank, world)
+        lo, hi = (0, per_shard) if slice_range is None else slice_range
+        with torch.cuda.device(device):
+            blob = plan.pack_leaves(leaves, device=device)
+            out = torch.zeros((last - first,) + tuple(plan.out_shape), dtype=torch.complex64, device=device)
+            ws = _c.get_workspace(device, plan.workspace_bytes)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            for k, shard in enumerate(range(first, last)):
+                plan.execute(blob, out[k], shard * per_shard + lo, shard * per_shard + hi, ws, stream)
+            if self.permute_dims is not None:
+                out = out.permute([0] + [d + 1 for d in self.permute_dims])
+            if gather:
+                if dist is not None and world > 1:
+                    out = out.contiguous()
+                    full = torch.empty((world,) + tuple(out.shape), dtype=out.dtype, device=device)
+                    dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(out), group=pg)
+                    out = full
+                out = out.reshape([2] * (len(self.shard_bonds) + len(plan.out_shape)))
+        return out
+
     # ---- constructors ----
-    @classmethod
-    def from_circuit_file(cls, circuit_filename, bitstrings=[]):
-        ref = _reference()
-        return cls.from_tn_circuit(ref.TensorNetworkCircuit(circuit_filename), bitstrings)
-
-    @classmethod
-    def from_tn_circuit(cls, circ, bitstrings=[]):
-        """simulation.py:135-148, with the reference's own network simplification."""
-        ref = _reference()
-        pattern, max_bitstrings = check_bitstrings(bitstrings)
-        tensors, tensor_bonds, bond_dims, final_qubits = circ.to_numerical_tn()
-        numerical_tn = ref.NumericalTensorNetwork(tensors, tensor_bonds, bond_dims, final_qubits)
-        tensor_bonds_reorder, final_qubit_inds = numerical_tn._simplify(pattern)
-        tensors = {i: numerical_tn.tensors[j] for i, j in enumerate(numerical_tn.tensors.keys())}
-        return cls(tensors, tensor_bonds_reorder, bond_dims, final_qubit_inds, bitstrings, pattern, max_bitstrings)
-
     @classmethod
     def from_case(cls, case):
         """Rebuild a prepared simulation from a frozen case (artensor_b200.cases); no reference needed."""
@@ -212,6 +269,7 @@ class TensorNetworkSimulation:
         sim.bitstrings_sorted = case.bitstrings_sorted
         sim.slicing_bonds = list(case.slicing_bonds)
         sim.slicing_indices = case.slicing_indices()
+        sim.shard_bonds = list(case.slicing_bonds[:int(case.extra.get("n_shard_bonds", 0))])
         sim.tensor_contraction_func = _c.tensor_contraction if case.pattern == 'normal' else _c.tensor_contraction_sparse
         return sim
 

@@ -267,7 +267,14 @@ def reference_arm(args):
         slice_id = int(exp["slice_ids"][0])
     except (OSError, KeyError):
         slice_id = 0
-    need_gib = 4.0 * plan.workspace_bytes / 2 ** 30 if plan.workspace_bytes > (1 << 30) else 1.0
+    # host memory a true slice needs: live intermediates + einsum's permuted operand copies + its output
+    live, cur, peak = {}, 0, 0
+    for st in plan.steps:
+        a, b, c = st.a.numel * 8, st.b.numel * 8, st.c.numel * 8
+        peak = max(peak, cur + a + b + c)
+        cur += c - live.pop(st.i, 0) - live.pop(st.j, 0)
+        live[st.i] = c
+    need_gib = 1.3 * peak / 2 ** 30 + 2.0
     avail = host_mem_gib()
     mode = "true_slice"
     if avail is not None and avail < need_gib and not os.environ.get("TNC_BENCH_FORCE_TRUE_SLICE"):

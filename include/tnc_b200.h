@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TNC_ABI_VERSION 5
+#define TNC_ABI_VERSION 6
 #define TNC_MAX_BITS 40          /* max bit modes per group / per tensor */
 #define TNC_MAX_SLICED 8         /* max sliced bonds on one leaf */
 
@@ -44,9 +44,13 @@ typedef enum tnc_status {
     TNC_ERR_STATE = 5            /* plan not finalized / already finalized */
 } tnc_status;
 
+/* Storage type of the tensors in the arena.  complex64 only: the reduced-precision complex-half
+ * mode (torch.complex32 at the Python boundary) is an OPERAND precision of the tensor-core steps
+ * (TNC_TC_F16 below) -- intermediates stay complex64 because n53 amplitudes (~1e-8) are below the
+ * fp16 range (the reference needs its per-step rescaling for them, contraction.py:197-200).  ABI 5
+ * declared a TNC_C32 storage type that no tensor-core path ever implemented; it was removed. */
 typedef enum tnc_dtype {
-    TNC_C64 = 0,                 /* complex64 (interleaved fp32 pairs) */
-    TNC_C32 = 1                  /* complex-half (interleaved fp16 pairs) */
+    TNC_C64 = 0                  /* complex64 (interleaved fp32 pairs) */
 } tnc_dtype;
 
 typedef enum tnc_phase {

@@ -234,3 +234,50 @@ def test_einsum_equation_first_appearance():
     assert S.einsum_equation([-1, "x", "y"], ["y", "z"], [-1, "x", "z"]) == "ABC,CD->ABD"
     with pytest.raises(S.SchemeError):
         S.einsum_equation(list(range(60)), [], [])
+
+
+# ------------------------------------------------------------------------------------------------
+# open-qubit sharding of full-amplitude contractions
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_regular,n_bits", [(0, 1), (2, 2), (3, 3)])
+def test_open_qubit_shards_concatenate_to_the_full_state(n_regular, n_bits):
+    """`prepare_open_qubit_shards(b)` fixes the first b output qubits per shard: every shard's sum
+    over its (regular) slices, run by the REFERENCE executor in complex128, must equal the
+    matching block of the un-sharded full state, with and without regular slicing.  (The n12 tree
+    needs no slicing at sc_target >= 12 and below that the reference slices OPEN bonds, SURVEY.md
+    4.3; so the regular sliced bonds are taken by hand: inner bonds of the tree.)"""
+    ref = reference()
+    from artensor.contraction import tensor_contraction
+    from artensor_b200 import TensorNetworkSimulation
+    sim = TensorNetworkSimulation.from_circuit_file(N12, [])
+    assert isinstance(sim, ref.TensorNetworkSimulation)           # the subclass of the reference's class
+    sim.prepare_contraction(sc_target=30, trials=2, iters=5, slicing_repeat=1, start_seed=0)
+    assert sim.slicing_bonds == [] and len(sim.output_bonds) == 12
+    if n_regular:
+        tree = deepcopy(sim.ctree)
+        inner = sorted(b for b, ts in tree.tn.bond_tensors.items() if len(ts) == 2)[5:5 + n_regular]
+        for b in inner:
+            tree.slicing(b)
+        sim.ctree, sim.slicing_bonds = tree, inner
+        sim.slicing_indices = slicing_dims(sim.tensors, sim.tensor_bonds, inner)
+        qubit_of = {b: q for q, b in zip(np.argsort(np.argsort(sim.permute_dims)), sim.output_bonds)}
+        sim.update_scheme()
+        sim.permute_dims = [int(d) for d in np.argsort([qubit_of[b] for b in sim.output_bonds])]
+    leaves = {i: t.to(torch.complex128) for i, t in sim.tensors.items()}
+
+    def contract(slice_ids):
+        total = None
+        for s in slice_ids:
+            out = tensor_contraction(slice_leaves(leaves, sim.slicing_bonds, sim.slicing_indices, s), sim.scheme)
+            total = out.clone() if total is None else total + out
+        return total.permute(sim.permute_dims)
+    full = contract(range(1 << n_regular))                          # [2] * 12 in qubit order
+    sim.prepare_open_qubit_shards(n_bits)
+    assert len(sim.shard_bonds) == n_bits and sim.slicing_bonds[:n_bits] == sim.shard_bonds
+    assert len(sim.slicing_bonds) == n_regular + n_bits and len(sim.output_bonds) == 12 - n_bits
+    per_shard = 1 << n_regular
+    blocks = [contract(range(v * per_shard, (v + 1) * per_shard)) for v in range(1 << n_bits)]
+    got = torch.stack(blocks).reshape([2] * 12)
+    assert (got - full).abs().max().item() < 1e-12 * full.abs().max().item()
+    with pytest.raises(ValueError):
+        sim.prepare_open_qubit_shards(1)                            # already sharded

@@ -147,6 +147,9 @@ CONFIGS = {
     "n12_sparse100_sc8_own": (n12_qsim, lambda: random_bitstrings(12, 100, 2), dict(sc_target=8, trials=4, iters=10), None, True),
     "n30_sparse64_sc26": (n30_qsim, lambda: google_amplitudes(64)[0], dict(sc_target=26, trials=4, iters=5), None, False),
     "n30_full": (n30_qsim, lambda: [], dict(sc_target=30, trials=4, iters=5), [0], False),
+    # BASELINE config 2 sharded over its first 3 output qubits: 8 shards x 4 regular
+    # slices; slice id = (shard, regular slice), the expected outputs are the reference executor's on that scheme
+    "n30_full_shard3": (n30_qsim, lambda: [], dict(sc_target=30, trials=4, iters=5), [0, 9, 22, 31], False),
     "n30_sparse10000": (n30_qsim, lambda: google_amplitudes(10000)[0], dict(sc_target=30, trials=4, iters=5), [0], False),
     # BASELINE config 3 as a SLICED contraction (the unsliced scheme above is one slice: nothing to spread over GPUs)
     "n30_sparse10000_sc27": (n30_qsim, lambda: google_amplitudes(10000)[0], dict(sc_target=27, trials=4, iters=5), [0, 3], False),
@@ -182,13 +185,16 @@ def build(name):
     bitstrings = bits_fn()
     if not os.path.exists(case_path):
         t0 = time.time()
-        if name.endswith("_own"):
+        shard_bits = int(name.rsplit("_shard", 1)[1]) if "_shard" in name else 0
+        if name.endswith("_own") or shard_bits:
             from artensor_b200 import TensorNetworkSimulation as OwnSimulation
             sim = OwnSimulation.from_circuit_file(circ_fn(), bitstrings)
             assert sim.scheme_compiler == "b200"
         else:
             sim = TensorNetworkSimulation.from_circuit_file(circ_fn(), bitstrings)
         sim.prepare_contraction(slicing_repeat=1, start_seed=0, **prep)
+        if shard_bits:
+            sim.prepare_open_qubit_shards(shard_bits)
         validate_scheme(sim.scheme, sim.pattern)
         print(f"[{name}] order search {time.time() - t0:.1f}s; steps={len(sim.scheme)} "
               f"slicing_bonds={len(sim.slicing_indices)}", flush=True)
@@ -199,7 +205,7 @@ def build(name):
             permute_dims=getattr(sim, "permute_dims", None) if len(sim.output_bonds) else None,
             bitstrings_sorted=getattr(sim, "bitstrings_sorted", None),
             n_qubits=len(sim.final_qubits),
-            extra={"prepare": {k: v for k, v in prep.items()}, "bitstrings_in": bitstrings,
+            extra={"prepare": {k: v for k, v in prep.items()}, "bitstrings_in": bitstrings, "n_shard_bonds": shard_bits,
                    **google_extra(name, bitstrings),
                    "ref_slicing_indices": {b: [(int(t), int(d)) for t, d in v] for b, v in sim.slicing_indices.items()}},
         )
