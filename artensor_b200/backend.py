@@ -110,7 +110,7 @@ class PlanOptions:
     skinny_min_n: int = 4
     swap_operands: bool = True
     hoist: bool = True
-    tc_precision: str = field(default_factory=lambda: os.environ.get("TNC_TC_PRECISION", "3xf16"))
+    tc_precision: str = "3xf16"
 
     def __post_init__(self):
         if self.tc_precision not in N.TC_PRECISIONS:
@@ -161,8 +161,10 @@ def tc_uses_3m(st: Step, precision="3xf16"):
     (k >= 6 bits), >= 128 complex columns (n >= 7 bits), whole 256-row pair tiles, B's rows not
     folded into N.  Such a step issues 0.75 real tensor-core products per useful complex one
     (2.25 with the hi/lo split) instead of 1 (3)."""
-    if precision != "3xf16" or os.environ.get("TNC_TC_3M") == "0" or os.environ.get("TNC_TC_2CTA") == "0":
+    if precision != "3xf16":
         return False
+    if os.environ.get("TNC_EXPERIMENTS", "0") not in ("", "0") and "0" in (os.environ.get("TNC_TC_3M"), os.environ.get("TNC_TC_2CTA")):
+        return False                      # experiment knobs of the library (include/tnc_b200.h)
     k, n, m = len(st.k_modes), len(st.n_modes), len(st.m_modes)
     if not tc_eligible(st, precision) or k < 6 or n < 7 or m < 7:
         return False

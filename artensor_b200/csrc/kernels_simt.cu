@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) accum_kernel(AccumParams p) {
 int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
     if (p.total <= 0) return TNC_OK;
     // many rows, a long contraction, <= 16 outputs per row, no shared kept modes: one CTA per row
-    static const bool no_rowdot = getenv("TNC_NO_ROWDOT") != nullptr;      // measurement aid
+    static const bool no_rowdot = knob("TNC_NO_ROWDOT") != nullptr;      // measurement aid
     if (!no_rowdot && dtype == TNC_C64 && p.rank_c <= 4 && p.kb >= 7 && (p.total >> p.rank_c) >= 32) {
         int nm = 0, nn = 0;
         bool plain = true;

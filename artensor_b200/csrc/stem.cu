@@ -248,9 +248,9 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
     const int64_t tile_mask = ((int64_t)1 << tile_bits) - 1;
     int s = 0;
     uint32_t ph = 0;
-    if (tid >= kBulkConsumers) {
-        if (tid != kBulkConsumers) return;
-        // ---- producer: one thread issues the bulk copies of each tile
+    if (uniform_warp_idx() == kBulkConsumers / 32) {
+        // ---- producer warp: every lane walks the tiles and waits, one elected lane issues the bulk
+        // copies of each tile (elect_one, tc_common.cuh: descriptors stay in uniform registers)
         int n_hi = 0;
         int8_t hi_pos[4];
         for (int i = 0; i < KB; ++i)
@@ -270,19 +270,22 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
             int64_t aoff = ra << p.rank_a;
             for (int i = 0; i < p.n_runs; ++i) aoff |= ((tile >> p.run_src[i]) & (int64_t)p.run_mask[i]) << p.run_dst[i];
             mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-            mbar_expect_tx(bar_full + 8u * s, stage_bytes);
-            const uint32_t dst = stage0 + (uint32_t)s * stage_bytes;
-            for (int c = 0; c < (1 << n_hi); ++c) {
-                int64_t o = aoff;
-                for (int i = 0; i < n_hi; ++i) o |= (int64_t)((c >> i) & 1) << hi_pos[i];
-                bulk_load(dst + (uint32_t)c * chunk_bytes, p.a + o, chunk_bytes, bar_full + 8u * s);
+            if (elect_one()) {
+                mbar_expect_tx(bar_full + 8u * s, stage_bytes);
+                const uint32_t dst = stage0 + (uint32_t)s * stage_bytes;
+                for (int c = 0; c < (1 << n_hi); ++c) {
+                    int64_t o = aoff;
+                    for (int i = 0; i < n_hi; ++i) o |= (int64_t)((c >> i) & 1) << hi_pos[i];
+                    bulk_load(dst + (uint32_t)c * chunk_bytes, p.a + o, chunk_bytes, bar_full + 8u * s);
+                }
             }
+            __syncwarp();
             if (++s == p.stages) {
                 s = 0;
                 ph ^= 1u;
             }
         }
-        // stay until the last copy has landed: the issuing thread outlives its bulk copies
+        // stay until the last copy has landed: the issuing warp outlives its bulk copies
         if (i_end > i_begin) {
             const int last = s == 0 ? p.stages - 1 : s - 1;
             mbar_wait(bar_full + 8u * last, s == 0 ? ph ^ 1u : ph);
@@ -488,7 +491,7 @@ int launch_stem_bulk(const tnc_einsum& e, const void* a, const void* b, void* c,
     // long run, but the variants with >= 8 outputs x >= 8 amplitudes per row need more than the 72
     // registers that leaves them (measured inside n53 / n30 slices: 1.18 vs 1.38 ms for n = k = 3
     // at two CTAs, 2.15 vs 3.2 ms for n = 2, k = 4 at three).
-    static const int forced_per_sm = getenv("TNC_STEM_BULK_CTAS") ? atoi(getenv("TNC_STEM_BULK_CTAS")) : 0;
+    static const int forced_per_sm = knob("TNC_STEM_BULK_CTAS") ? atoi(knob("TNC_STEM_BULK_CTAS")) : 0;
     int per_sm = forced_per_sm ? (forced_per_sm >= 3 ? 3 : 2) : ((nch >= 8 && e.n_k >= 3) || nch >= 16 ? 2 : 3);
     int stages = (int)(((per_sm == 3 ? 74 : 112) * 1024 - fixed) / stage_bytes);
     if (stages < 2 && per_sm == 3) {
@@ -539,7 +542,7 @@ int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, cons
         set_error("stem einsum: unsupported shape or output layout (k=%d n=%d h=%d)", e.n_k, e.n_n, e.n_h);
         return TNC_ERR_UNSUPPORTED;
     }
-    static const bool no_bulk = getenv("TNC_STEM_NO_BULK") != nullptr;      // measurement aid
+    static const bool no_bulk = knob("TNC_STEM_NO_BULK") != nullptr;      // measurement aid
     if (!no_bulk && bulk_applies(e)) {
         const int rc = launch_stem_bulk(e, a, b, c, dev_rows_a, dev_rows_b, dev_seg_begin, n_seg, s);
         if (rc != TNC_ERR_UNSUPPORTED) return rc;

@@ -632,7 +632,7 @@ int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, 
         set_error("pack: the fp16 modes need the operand's amax word");
         return TNC_ERR_INVALID;
     }
-    static const bool fast = !(getenv("TNC_PACK_FAST") && atoi(getenv("TNC_PACK_FAST")) == 0);
+    static const bool fast = !(knob("TNC_PACK_FAST") && atoi(knob("TNC_PACK_FAST")) == 0);
     if (fast && d.rank >= 8 && d.rank - 8 < 32 &&
         (d.mode == PACK_COPY || d.mode == PACK_SPLIT || d.mode == PACK_SPLIT_F16 || d.mode == PACK_ACCUM ||
          d.mode == PACK_PLANAR3_F16 ||
@@ -1727,7 +1727,7 @@ int shape_of(const tnc_einsum& e, Shape* sh) {
         sh->batch = e.b.rows;
         // ... or, when a row of B spans whole 32-column slabs, B's rows extend N instead: ONE GEMM
         // that reads the (large) left panel once per 256 columns instead of once per row of B
-        if (((int64_t)2 << e.n_n) >= 32 && !(getenv("TNC_TC_FOLDN") && atoi(getenv("TNC_TC_FOLDN")) == 0)) {
+        if (((int64_t)2 << e.n_n) >= 32 && !(knob("TNC_TC_FOLDN") && atoi(knob("TNC_TC_FOLDN")) == 0)) {
             sh->n_inner = 2 << e.n_n;
             sh->batch = 1;
         }
@@ -1801,19 +1801,19 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     // multiple of 128 rows, N a multiple of the tile width (a folded B' panel keeps the plain
     // [row of B][n][k] order: its row count need not be a multiple of the tile)
     op->blocked = e.n_k >= kbl && e.n_m >= 7 && sh.N >= bn;
-    if (const char* env = getenv("TNC_TC_BLOCKED"))
+    if (const char* env = knob("TNC_TC_BLOCKED"))
         if (atoi(env) == 0) op->blocked = 0;
     op->blocked_b = op->blocked && sh.n_inner == 0;
     // CTA pairs on 256 x 256 tiles
     op->two_cta = bn == 256 && sh.M % 256 == 0 && sh.M / BM >= 2;
-    if (const char* env = getenv("TNC_TC_2CTA"))
+    if (const char* env = knob("TNC_TC_2CTA"))
         if (atoi(env) == 0) op->two_cta = 0;
     // 3M complex product (gemm3m_2cta_kernel): fp16 precisions, whole 64-k blocks and pair tiles
     // (3xF16 only: in the single-product complex-half mode the 4M kernel is as fast -- both sit at the same
     // power / shared-memory ceiling, 52.3 vs 53.4 ms on the fat step -- and 1.4x more accurate, the imaginary
     // part of 3M being a difference of larger products)
     op->use_3m = precision == TNC_TC_3XF16 && op->two_cta && op->blocked_b && e.n_k >= 6 && sh.N % 256 == 0;
-    if (const char* env = getenv("TNC_TC_3M"))
+    if (const char* env = knob("TNC_TC_3M"))
         if (atoi(env) == 0) op->use_3m = 0;
     if (op->use_3m) {
         // planar panels, both operands alike: [tile of 128 rows][block of 64 k][re, im, re + im][hi, lo][128 rows][64 k]
@@ -1895,14 +1895,14 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     // (measured on the fat GEMM of n53 m20, ncu: 143.6 GB of DRAM traffic against 168.3 GB at 16 and
     // 181.4 GB at 4, same time; the floor for 74 resident 256x256 tiles is ~64 GB)
     g.group_m = 8;
-    if (const char* env = getenv("TNC_TC_GROUP_M")) {  // experiment knob: row tiles per sweep group
+    if (const char* env = knob("TNC_TC_GROUP_M")) {  // experiment knob: row tiles per sweep group
         const int v = atoi(env);
         if (v >= 1 && v <= 1024) g.group_m = v;
     }
     g.a_batched = op->a_batched;
     g.b_batched = op->b_batched;
     g.kc = kDefaultKC[precision];
-    if (const char* env = getenv("TNC_TC_KC")) {       // experiment knob
+    if (const char* env = knob("TNC_TC_KC")) {       // experiment knob
         const int v = atoi(env);
         if (v >= 1 && v <= 64) g.kc = v;
     }
@@ -1920,7 +1920,7 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     const int bk = bk_of(precision);
     const int nkb = (int)((sh.K + bk - 1) / bk);
     g.sync_every = nkb >= 64 ? 16 : 0;
-    if (const char* env = getenv("TNC_TC_SYNC")) g.sync_every = nkb >= 64 ? atoi(env) : 0;
+    if (const char* env = knob("TNC_TC_SYNC")) g.sync_every = nkb >= 64 ? atoi(env) : 0;
     if (op->use_3m) {
         // k-blocks of 64 complex k; the barrier spacing is rounded to whole accumulation chunks
         g.sync_every = (g.sync_every / 2 + g.kc - 1) / g.kc * g.kc;

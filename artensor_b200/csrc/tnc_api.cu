@@ -404,7 +404,7 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
             }
         }
     // runs of consecutive tiny generic steps -> one chain launch each
-    static const bool no_chain = getenv("TNC_NO_CHAIN") != nullptr;       // measurement aid
+    static const bool no_chain = knob("TNC_NO_CHAIN") != nullptr;       // measurement aid
     auto chainable = [&](const Op& op) {
         if (no_chain || plan->dtype != TNC_C64 || op.kind != OP_EINSUM || op.e.algo != TNC_ALGO_SIMT) return false;
         const int64_t total = (int64_t)op.e.nb << op.e.c.rank;

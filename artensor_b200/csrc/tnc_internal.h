@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,15 @@
 namespace tnc {
 
 void set_error(const char* fmt, ...);
+
+// Experiment knobs (listed in include/tnc_b200.h): environment variables that select kernel variants
+// for A/B measurements.  They are read ONLY when TNC_EXPERIMENTS=1 is set as well, so that a stray
+// variable can never change the numerics or the speed of the product path silently.
+inline const char* knob(const char* name) {
+    const char* on = getenv("TNC_EXPERIMENTS");
+    if (!on || on[0] == '\0' || on[0] == '0') return nullptr;
+    return getenv(name);
+}
 
 constexpr int kMaxDevices = 64;
 inline int current_device() {

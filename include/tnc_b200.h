@@ -202,6 +202,28 @@ int tnc_permute_bits(const void* src, void* dst, int32_t rank, int64_t rows,
 
 const char* tnc_last_error(void);
 
+/* ---- environment ----
+ * TNC_NVTX=1          every operation runs inside an NVTX range named after its class and shape
+ *                     ("tc m15 n13 k15 rows1", "skinny ...", "chain x13", "leaves", "accum").
+ *
+ * Experiment knobs: kernel variants for A/B measurements (tools/, profiles/).  They are honoured
+ * ONLY together with TNC_EXPERIMENTS=1 and are not part of the contract; some change rounding
+ * (never beyond the documented tolerances' order of magnitude) -- the product path runs without.
+ *   TNC_TC_3M=0          interleaved 4M complex product instead of the 3M (Karatsuba) kernel
+ *   TNC_TC_2CTA=0        single-CTA tiles instead of cta_group::2 pairs (also disables 3M)
+ *   TNC_TC_KC=<n>        k-blocks accumulated in tensor memory before the fp32 register add
+ *                        (default 1; more = faster, larger round-toward-zero bias)
+ *   TNC_TC_SYNC=<n>      k-blocks between the grid-wide lockstep barriers of a GEMM (0 = none)
+ *   TNC_TC_GROUP_M=<n>   row tiles per sweep group of the persistent tile order
+ *   TNC_TC_BLOCKED=0     row-major instead of tile-contiguous packed panels
+ *   TNC_TC_FOLDN=0       outer-row steps loop over B's rows instead of folding them into N
+ *   TNC_PACK_FAST=0      generic pack kernel instead of the register-resident one
+ *   TNC_STEM_NO_BULK=1   per-thread streaming kernel instead of the bulk-copy one
+ *   TNC_STEM_BULK_CTAS=<2|3>  resident CTAs per SM of the bulk-copy streaming kernel
+ *   TNC_NO_CHAIN=1       one launch per tiny generic step instead of chained launches
+ *   TNC_NO_ROWDOT=1      generic kernel instead of the row-dot kernel for long contractions
+ */
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,3 +121,30 @@ def test_torch_oracle_step_shrinking_is_linear():
     assert scale == 4 and sa == [16, 2, 2] and sb == [16, 2, 2]
     secs, n, scaled, _ = OT.estimate_slice_seconds([("abcde,efc->abdf", [2] * 5, [2, 2, 2])], max_elems=8)
     assert n == 1 and scaled == 1 and secs > 0
+
+
+def test_open_qubit_shard_is_a_block_of_the_unsharded_slice():
+    """n30 m14 full amplitude sharded over its first 3 output qubits (fixture n30_full_shard3,
+    SURVEY.md 8e): slice id 0 = (shard 0, regular slice 0), contracted by the torch oracle, must be
+    the block of the UNSHARDED slice 0 whose shard qubits are 0 -- checked on the entries of the
+    reference's recorded output of that slice (fixture n30_full) that fall into the block."""
+    from oracle import tn_oracle_torch
+    full, fexp = load_golden("n30_full")
+    case, exp = load_golden("n30_full_shard3")
+    n_sh = int(case.extra["n_shard_bonds"])
+    assert n_sh == 3 and case.slicing_bonds[n_sh:] == full.slicing_bonds and int(fexp["slice_ids"][0]) == 0
+    got = tn_oracle_torch.contract_slices(case, [0]).reshape(-1).numpy()
+    want_own = exp["per_slice_c64"][list(exp["slice_ids"]).index(0)]
+    assert _rel(got[exp["sample_idx"]], want_own) < 1e-5              # the reference executor on the sharded scheme
+    # entries of the unsharded slice: flat index -> bit of every output bond
+    idx = fexp["sample_idx"]
+    n_out = len(full.output_bonds)
+    bit = {b: (idx >> (n_out - 1 - d)) & 1 for d, b in enumerate(full.output_bonds)}
+    in_block = np.ones(len(idx), dtype=bool)
+    for b in case.slicing_bonds[:n_sh]:
+        in_block &= bit[b] == 0                                       # shard 0: every shard qubit is 0
+    pos = np.zeros(len(idx), dtype=np.int64)
+    for d, b in enumerate(case.output_bonds):
+        pos |= bit[b] << (len(case.output_bonds) - 1 - d)
+    assert in_block.sum() > 500
+    assert _rel(got[pos[in_block]], fexp["per_slice_c64"][0][in_block]) < 1e-5

@@ -1,4 +1,5 @@
 # 3M complex product: parity tests, then the fat GEMM of the n53 m20 tree (m15 n13 k15) timed with and without it
+export TNC_EXPERIMENTS=1   # the TNC_* variant knobs below are only honoured with this (include/tnc_b200.h)
 mkdir -p gpurun_out
 ( timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -q -x -s -k "3m or two_cta or long_contraction or tc_single" ) > gpurun_out/t_3m.log 2>&1; echo "rc=$?" >> gpurun_out/t_3m.log
 grep -E "3M max|passed|failed|rc=|Error|error" gpurun_out/t_3m.log | tail -n 30

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
+export TNC_EXPERIMENTS=1   # the TNC_* variant knobs below are only honoured with this (include/tnc_b200.h)
 ( timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -q -x -s -k "3m or two_cta or long_contraction" ) > gpurun_out/t_3m.log 2>&1; echo "rc=$?" >> gpurun_out/t_3m.log
 grep -E "3M max|passed|failed|rc=|Error|error" gpurun_out/t_3m.log | tail -n 12
 for kc in 1 2 4; do

@@ -1,4 +1,5 @@
 # CUDA-event time of the fat GEMM for several sweep-group sizes.
+export TNC_EXPERIMENTS=1   # the TNC_* variant knobs below are only honoured with this (include/tnc_b200.h)
 mkdir -p gpurun_out
 {
 for gm in 16 8 4 2 32 16; do
