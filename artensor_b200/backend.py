@@ -111,6 +111,11 @@ class PlanOptions:
     swap_operands: bool = True
     hoist: bool = True
     tc_precision: str = "3xf16"
+    # Replay the slice phase as one CUDA graph per slice (TNC_OPT_CUDA_GRAPH).  None = automatic:
+    # on for sliced plans whose slice is light enough (< graph_max_flops executed flops) for the
+    # launch gaps of its ~100 kernels to matter (n53 m12: 3.3 ms per slice over 140 launches)
+    cuda_graph: Optional[bool] = None
+    graph_max_flops: float = 5e12
 
     def __post_init__(self):
         if self.tc_precision not in N.TC_PRECISIONS:
@@ -355,6 +360,11 @@ class ContractionPlan:
         base[N.TNC_PHASE_ONCE] = 0
         base[N.TNC_PHASE_SLICE] = arenas[N.TNC_PHASE_ONCE].high
         self.workspace_bytes = max(arenas[N.TNC_PHASE_ONCE].high + arenas[N.TNC_PHASE_SLICE].high, ALIGN)
+        exec_flops = sum(st.flops for st, ph in zip(self.steps, self.step_phase) if ph == N.TNC_PHASE_SLICE)
+        self.cuda_graph = (self.n_sliced >= 1 and exec_flops < self.options.graph_max_flops
+                           if self.options.cuda_graph is None else bool(self.options.cuda_graph))
+        if self.cuda_graph:
+            self.workspace_bytes += ALIGN           # the library's slice-id word lives in the last 256 bytes
 
         ops = {N.TNC_PHASE_ONCE: [], N.TNC_PHASE_SLICE: []}
         for phase in ops:
@@ -477,6 +487,7 @@ class ContractionPlan:
         self._lib, self._handle = lib, handle
         try:
             N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_TC_PRECISION, N.TC_PRECISIONS[self.options.tc_precision]))
+            N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_CUDA_GRAPH, 1 if self.cuda_graph else 0))
             for t in self.tables:
                 tid = C.c_int32()
                 N.check(lib.tnc_plan_add_table(handle, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t), C.byref(tid)))

@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(kChainThreads) simt_chain_kernel(const ChainSt
 template <typename T>
 __global__ void __launch_bounds__(128) leaf_gather_kernel(const LeafDev* __restrict__ leaves,
                                                           const T* __restrict__ blob, char* arena,
-                                                          uint64_t slice_id) {
+                                                          uint64_t slice_id, const uint64_t* slice_word) {
+    // graph-replayed slices read their id from a word in the workspace that the graph's last node bumps
+    if (slice_word) slice_id = *slice_word;
     const LeafDev L = leaves[blockIdx.x];
     T* dst = (T*)(arena + L.dst_offset);
     uint32_t fixed = 0;
@@ -376,15 +378,25 @@ int launch_simt_chain(const ChainStep* dev_steps, int n, void* workspace, const 
     return TNC_OK;
 }
 
+__global__ void slice_word_kernel(uint64_t* word, uint64_t value, int add) {
+    *word = add ? *word + value : value;
+}
+
+int launch_slice_word(uint64_t* word, uint64_t value, bool add, cudaStream_t s) {
+    slice_word_kernel<<<1, 1, 0, s>>>(word, value, add ? 1 : 0);
+    TNC_CUDA(cudaGetLastError());
+    return TNC_OK;
+}
+
 int launch_leaf_gather(const LeafDev* dev_leaves, int n, int max_elems, const void* blob,
-                       void* arena, uint64_t slice_id, int dtype, cudaStream_t s) {
+                       void* arena, uint64_t slice_id, const uint64_t* slice_word, int dtype, cudaStream_t s) {
     (void)max_elems;
     if (n <= 0) return TNC_OK;
     if (dtype != TNC_C64) {
         set_error("leaves: only complex64 tensors are supported");
         return TNC_ERR_UNSUPPORTED;
     }
-    leaf_gather_kernel<float2><<<n, 128, 0, s>>>(dev_leaves, (const float2*)blob, (char*)arena, slice_id);
+    leaf_gather_kernel<float2><<<n, 128, 0, s>>>(dev_leaves, (const float2*)blob, (char*)arena, slice_id, slice_word);
     TNC_CUDA(cudaGetLastError());
     return TNC_OK;
 }

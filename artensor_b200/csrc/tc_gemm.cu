@@ -1335,16 +1335,19 @@ struct Cfg3 {
 
 // Folds 64 columns of product P (0: Ar Br, 1: Ai Bi, 2: (Ar + Ai)(Br + Bi)) into the planar accumulators
 // (re[j], im[j] = columns 2j, 2j + 1) with packed fp32x2 adds: 2.5 instructions per complex output and chunk.
-template <int P>
-__device__ __forceinline__ void drain_3m(uint32_t taddr, float2* re, float2* im) {
+// `release` runs as soon as the slot's last columns sit in registers (before their adds).
+template <int P, int DB, typename Release>
+__device__ __forceinline__ void drain_3m(uint32_t taddr, float2* re, float2* im, Release release) {
     const float2 neg = make_float2(-1.f, -1.f);
 #pragma unroll
-    for (int c = 0; c < 64; c += 16) {
-        uint32_t v[16];
+    for (int c = 0; c < 64; c += DB) {
+        uint32_t v[DB];
         tmem_ld16(taddr + c, v);
+        if constexpr (DB == 32) tmem_ld16(taddr + c + 16, v + 16);
         tmem_ld_wait();
+        if (c + DB == 64) release();
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
+        for (int j = 0; j < DB; j += 2) {
             const float2 x = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
             const int o = (c + j) >> 1;
             if (P == 0) {
@@ -1360,7 +1363,7 @@ __device__ __forceinline__ void drain_3m(uint32_t taddr, float2* re, float2* im)
     }
 }
 
-template <int PREC>
+template <int PREC, int DB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
     using C = Cfg3<PREC>;
@@ -1516,12 +1519,9 @@ gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             };
 #pragma unroll 1
             for (int chunk = 0; chunk < nchunks; ++chunk) {
-                drain_3m<0>(slot_wait(), re, im);
-                slot_free();
-                drain_3m<1>(slot_wait(), re, im);
-                slot_free();
-                drain_3m<2>(slot_wait(), re, im);
-                slot_free();
+                drain_3m<0, DB>(slot_wait(), re, im, slot_free);
+                drain_3m<1, DB>(slot_wait(), re, im, slot_free);
+                drain_3m<2, DB>(slot_wait(), re, im, slot_free);
             }
             float acc[CPT];                              // interleaved (re, im) per complex column
 #pragma unroll
@@ -1630,12 +1630,12 @@ int launch_gemm_2cta(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, c
     return TNC_OK;
 }
 
-template <int PREC>
+template <int PREC, int DB>
 int launch_gemm3m(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
     static bool configured_on[kMaxDevices] = {};       // the attribute is per device
     bool& configured = configured_on[current_device()];
     if (!configured) {
-        TNC_CUDA(cudaFuncSetAttribute(gemm3m_2cta_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<PREC>::SMEM));
+        TNC_CUDA(cudaFuncSetAttribute(gemm3m_2cta_kernel<PREC, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<PREC>::SMEM));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -1650,7 +1650,7 @@ int launch_gemm3m(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cuda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm3m_2cta_kernel<PREC>, maps[0], maps[2], g));
+    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm3m_2cta_kernel<PREC, DB>, maps[0], maps[2], g));
     return TNC_OK;
 }
 
@@ -2016,7 +2016,8 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     if (op->two_cta) grid &= ~(int64_t)1;               // whole pairs; tiles is even here
     g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
     if (op->use_3m) {
-        rc = launch_gemm3m<TNC_TC_3XF16>(maps.m, g, grid, s);
+        static const int drain = knob("TNC_TC_DRAIN") ? atoi(knob("TNC_TC_DRAIN")) : 16;
+        rc = drain == 32 ? launch_gemm3m<TNC_TC_3XF16, 32>(maps.m, g, grid, s) : launch_gemm3m<TNC_TC_3XF16, 16>(maps.m, g, grid, s);
     } else if (op->two_cta) {
         switch (op->precision) {
             case TNC_TC_3XF16: rc = launch_gemm_2cta<TNC_TC_3XF16>(maps.m, g, grid, s); break;

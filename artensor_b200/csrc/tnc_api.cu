@@ -5,7 +5,9 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <map>
 #include <memory>
+#include <mutex>
 
 #include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a tool is attached
 
@@ -64,6 +66,18 @@ struct tnc_plan {
     char* dev_blob = nullptr;
     int64_t workspace_bytes = 0;
     std::atomic<int64_t> last_launches{0};   // written once at the end of an execute / profile call
+    // CUDA-graph replay of the slice phase (TNC_OPT_CUDA_GRAPH): one instantiated graph per
+    // (workspace, leaf blob, accumulator) the plan has been executed with
+    bool use_graph = false;
+    std::atomic<bool> graph_failed{false};
+    std::mutex graph_mu;
+    struct GraphKey {
+        const void *ws, *blob, *out;
+        bool operator<(const GraphKey& o) const {
+            return ws != o.ws ? ws < o.ws : blob != o.blob ? blob < o.blob : out < o.out;
+        }
+    };
+    std::map<GraphKey, std::pair<cudaGraphExec_t, int64_t>> graphs;      // exec, launches per replay
     int elem_bytes() const { return 8; }
 };
 
@@ -128,6 +142,13 @@ int tnc_plan_set_option(tnc_plan* plan, int32_t option, int64_t value) {
             }
             plan->tc_precision = (int)value;
             return TNC_OK;
+        case TNC_OPT_CUDA_GRAPH:
+            if (value != 0 && value != 1) {
+                set_error("set_option: TNC_OPT_CUDA_GRAPH takes 0 or 1, got %lld", (long long)value);
+                return TNC_ERR_INVALID;
+            }
+            plan->use_graph = value != 0;
+            return TNC_OK;
     }
     set_error("set_option: unknown option %d", option);
     return TNC_ERR_INVALID;
@@ -137,6 +158,7 @@ void tnc_plan_destroy(tnc_plan* plan) {
     if (!plan) return;
     for (int ph = 0; ph < 2; ++ph)
         for (auto& op : plan->ops[ph]) op.tc.reset();
+    for (auto& g : plan->graphs) cudaGraphExecDestroy(g.second.first);
     if (plan->dev_blob) cudaFree(plan->dev_blob);
     delete plan;
 }
@@ -346,8 +368,9 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
         set_error("finalize: bad arguments or already finalized");
         return plan && plan->finalized ? TNC_ERR_STATE : TNC_ERR_INVALID;
     }
-    // every tensor must fit the declared arena
-    auto fits = [&](const tnc_tensor& t) { return t.offset + tensor_bytes(plan, t) <= workspace_bytes; };
+    // every tensor must fit the declared arena (graph replay keeps its slice-id word in the last 256 bytes)
+    const int64_t usable = workspace_bytes - (plan->use_graph ? 256 : 0);
+    auto fits = [&](const tnc_tensor& t) { return t.offset + tensor_bytes(plan, t) <= usable; };
     for (int ph = 0; ph < 2; ++ph)
         for (auto& op : plan->ops[ph]) {
             bool ok = true;
@@ -508,14 +531,15 @@ struct OpRange {
 // Enqueues one operation; the plan is only read (a finalized plan may be executed from several host
 // threads at once, each with its own workspace and stream), launches are counted into *n_launches.
 static int run_op(const tnc_plan* plan, const Op& op, const void* leaf_blob, uint64_t slice_id, void* accum_out, char* ws,
-                  cudaStream_t st, int64_t* n_launches, LaunchHook hook = nullptr, void* hook_ctx = nullptr) {
+                  cudaStream_t st, int64_t* n_launches, LaunchHook hook = nullptr, void* hook_ctx = nullptr,
+                  const uint64_t* slice_word = nullptr) {
     if (op.kind == OP_EINSUM && op.chain_len < 0) return TNC_OK;       // ran with the head of its chain
     OpRange range(op);
     switch (op.kind) {
         case OP_LEAVES: {
             *n_launches += op.leaf_count > 0;
             const LeafDev* dl = (const LeafDev*)(plan->dev_blob + plan->leaves_off) + op.leaf_begin;
-            return launch_leaf_gather(dl, op.leaf_count, 0, leaf_blob, ws, slice_id, plan->dtype, st);
+            return launch_leaf_gather(dl, op.leaf_count, 0, leaf_blob, ws, slice_id, slice_word, plan->dtype, st);
         }
         case OP_EINSUM: {
             const tnc_einsum& e = op.e;
@@ -644,7 +668,66 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
         int rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, st, &launches);
         if (rc != TNC_OK) return rc;
     }
-    for (uint64_t s = slice_begin; s < slice_end; ++s)
+    uint64_t s = slice_begin;
+    if (plan->use_graph && !plan->graph_failed && slice_end - slice_begin >= 2) {
+        // Replay the slice phase as one CUDA graph per slice: the slice id lives in a workspace word that
+        // the leaf gather reads and the graph's last node increments.  Captured once per (workspace,
+        // leaf blob, accumulator); a capture that fails falls back to plain launches for good.
+        uint64_t* word = (uint64_t*)(ws + plan->workspace_bytes - 256);
+        tnc_plan::GraphKey key{workspace, leaf_blob, accum_out};
+        cudaGraphExec_t exec = nullptr;
+        int64_t per_replay = 0;
+        {
+            std::lock_guard<std::mutex> lock(plan->graph_mu);
+            auto it = plan->graphs.find(key);
+            if (it != plan->graphs.end()) {
+                exec = it->second.first;
+                per_replay = it->second.second;
+            }
+        }
+        if (!exec) {
+            // captured on a stream of its own (the caller's may be the legacy default stream, which cannot
+            // capture); nothing executes during capture, the graph is then launched on the caller's stream
+            cudaGraph_t graph = nullptr;
+            cudaStream_t cap = nullptr;
+            int rc = TNC_OK;
+            if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
+                    rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, cap, &per_replay, nullptr, nullptr, word);
+                    if (rc != TNC_OK) break;
+                }
+                if (rc == TNC_OK) rc = launch_slice_word(word, 1, true, cap);
+                ++per_replay;
+                const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+                if (rc == TNC_OK && ce == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)
+                    exec = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (cap) cudaStreamDestroy(cap);
+            if (!exec) {
+                cudaGetLastError();                      // clear the sticky capture error, if any
+                plan->graph_failed = true;
+            } else {
+                std::lock_guard<std::mutex> lock(plan->graph_mu);
+                auto ins = plan->graphs.emplace(key, std::make_pair(exec, per_replay));
+                if (!ins.second) {                       // another thread was faster
+                    cudaGraphExecDestroy(exec);
+                    exec = ins.first->second.first;
+                }
+            }
+        }
+        if (exec) {
+            int rc = launch_slice_word(word, slice_begin, false, st);
+            if (rc != TNC_OK) return rc;
+            for (; s < slice_end; ++s) {
+                TNC_CUDA(cudaGraphLaunch(exec, st));
+                launches += per_replay;
+            }
+        }
+    }
+    for (; s < slice_end; ++s)
         for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
             int rc = run_op(plan, op, leaf_blob, s, accum_out, ws, st, &launches);
             if (rc != TNC_OK) return rc;

@@ -104,8 +104,11 @@ struct LeafDev {
     int8_t sliced_shift[TNC_MAX_SLICED];   // slice-id bit index (LSB-based)
     int8_t keep_pos[TNC_MAX_BITS];
 };
+// `slice_word` (nullable): device word holding the slice id instead of the argument (CUDA-graph replay)
 int launch_leaf_gather(const LeafDev* dev_leaves, int n, int max_elems, const void* blob,
-                       void* arena, uint64_t slice_id, int dtype, cudaStream_t s);
+                       void* arena, uint64_t slice_id, const uint64_t* slice_word, int dtype, cudaStream_t s);
+// *word = value, or *word += value (one thread)
+int launch_slice_word(uint64_t* word, uint64_t value, bool add, cudaStream_t s);
 
 // ---------------------------------------------------------------- permute / accumulate
 struct PermuteParams {

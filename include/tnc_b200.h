@@ -68,7 +68,12 @@ typedef enum tnc_tc_precision {
 } tnc_tc_precision;
 
 typedef enum tnc_option {
-    TNC_OPT_TC_PRECISION = 0     /* value: tnc_tc_precision */
+    TNC_OPT_TC_PRECISION = 0,    /* value: tnc_tc_precision */
+    TNC_OPT_CUDA_GRAPH = 1       /* value 1: tnc_plan_execute replays the slice phase as ONE CUDA graph per slice
+                                    (captured on first use per workspace / leaf blob / accumulator) instead of
+                                    ~100 stream launches -- for slices of a few ms, where launch gaps are a
+                                    measurable share.  The last 256 bytes of the workspace then belong to the
+                                    library (the slice-id word): declare 256 bytes more at finalize. */
 } tnc_option;
 
 typedef enum tnc_algo {

@@ -206,6 +206,36 @@ def test_plan_permute_operation_through_the_abi(dev, rank):
     assert torch.equal(out.cpu(), src.cpu()[torch.from_numpy(spos)])
 
 
+@pytest.mark.parametrize("name", ["n12_sparse64_sc9", "n12_sparse100_sc8_own", "n30_sparse64_sc26"])
+def test_cuda_graph_replay_of_the_slice_phase(dev, name):
+    """TNC_OPT_CUDA_GRAPH: the slice phase captured once and replayed per slice (the slice id comes
+    from a workspace word the graph increments) must give bit for bit what plain launches give --
+    whole range, sub-ranges starting anywhere, repeated calls, a second workspace."""
+    from artensor_b200 import PlanOptions, ContractionPlan
+    case, exp, sim = sim_from(name)
+    shapes = {k: tuple(v.shape) for k, v in case.leaves.items()}
+    mk = lambda g: ContractionPlan(case.scheme, shapes, case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
+                                   slicing_indices=case.slicing_indices(), options=PlanOptions(cuda_graph=g))
+    plain, graph = mk(False), mk(True)
+    assert graph.cuda_graph and not plain.cuda_graph and graph.workspace_bytes == plain.workspace_bytes + 1024
+    blob = plain.pack_leaves({k: v.to(dev) for k, v in case.leaves.items()})
+    st = torch.cuda.current_stream().cuda_stream
+    n = plain.n_slices
+
+    def run(plan, ws, lo, hi):
+        out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
+        plan.execute(blob, out, lo, hi, ws, st)
+        torch.cuda.synchronize()
+        return out
+    wp = torch.empty(plain.workspace_bytes, dtype=torch.uint8, device=dev)
+    wg = [torch.empty(graph.workspace_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    for lo, hi in [(0, n), (1, n - 1), (n // 2, min(n, n // 2 + 3)), (0, n), (n - 2, n)]:
+        want = run(plain, wp, lo, hi)
+        for w in wg:
+            assert torch.equal(run(graph, w, lo, hi), want), f"slices [{lo}, {hi})"
+    assert graph.last_launches > 0
+
+
 def test_native_errors_are_raised_not_fatal(dev):
     from artensor_b200 import _native as N
     case, _, sim = sim_from("n12_sparse64_sc9")
