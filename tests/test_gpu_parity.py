@@ -822,6 +822,25 @@ def test_n53_m12_sum_over_64_slices_has_no_coherent_bias(dev):
     _c.release_workspaces()
 
 
+@pytest.mark.parametrize("name", ["n12_sparse5_f64leaves", "n12_sparse64_sc9_f64leaves"])
+def test_f64_built_leaves_against_the_state_vector(dev, name):
+    """leaves built in float64 and cast once (`from_circuit_file(leaf_precision=
+    "double")`).  Truth here is not another tensor-network run but the float64 STATE VECTOR of the
+    circuit (`TensorNetworkCircuit.state_vec`, recorded in the case): with float32-built leaves
+    nothing agrees with it better than ~1e-5 (the reference's known-answer table, 9 printed digits,
+    is itself 2-8e-6 off it); with float64-built leaves the CUDA complex64 result must sit within
+    3e-6 of the rms amplitude of it, amplitude by amplitude within 1e-5 relative + that floor."""
+    case, exp, sim = sim_from(name)
+    sv = case.extra["statevector_f64"]
+    want = np.array([sv[b] for b in case.bitstrings_sorted])
+    got = sim.contraction(device=dev).cpu().numpy().reshape(-1).astype(np.complex128)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    err = np.abs(got - want)
+    print(f"{name}: CUDA vs float64 state vector: max |err| / rms {err.max() / rms:.2e}, max relative {np.max(err / np.abs(want)):.2e}")
+    assert err.max() <= 3e-6 * rms
+    assert (err <= 1e-5 * np.abs(want) + 3e-6 * rms).all()
+
+
 def test_n53_m20_one_slice_vs_reference(dev):
     """BASELINE config 5 (the bench workload): one slice of the n53 m20 tree, 1024 amplitudes."""
     case, exp, sim = sim_from("n53_m20_sparse1024")

@@ -148,3 +148,18 @@ def test_open_qubit_shard_is_a_block_of_the_unsharded_slice():
         pos |= bit[b] << (len(case.output_bonds) - 1 - d)
     assert in_block.sum() > 500
     assert _rel(got[pos[in_block]], fexp["per_slice_c64"][0][in_block]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["n12_sparse5_f64leaves", "n12_sparse64_sc9_f64leaves"])
+def test_f64_built_leaves_reproduce_the_state_vector(name):
+    """Leaves built in float64 and cast once: the oracle in complex128 on those
+    leaves must reproduce the circuit's float64 state vector (recorded in the case) to the
+    precision of the complex64 leaves themselves, ~1e-7 of the rms amplitude."""
+    case, exp = load_golden(name)
+    sv = case.extra["statevector_f64"]
+    want = np.array([sv[b] for b in case.bitstrings_sorted])
+    got = O.contract_slices(case.leaves, case.scheme, case.pattern, case.slicing_bonds, case.slicing_indices(),
+                            range(case.n_slices), dtype=np.complex128).reshape(-1)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    assert np.abs(got - want).max() < 5e-7 * rms
+    assert np.abs(exp["per_slice_c128"].sum(axis=0) - got).max() < 1e-12 * rms       # and the reference executor agrees

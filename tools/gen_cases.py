@@ -145,6 +145,10 @@ CONFIGS = {
     # (SURVEY.md 8-f1); the expected outputs are still the REFERENCE executor's, run on that scheme
     "n12_full_own": (n12_qsim, lambda: [], dict(sc_target=30, trials=4, iters=10), None, True),
     "n12_sparse100_sc8_own": (n12_qsim, lambda: random_bitstrings(12, 100, 2), dict(sc_target=8, trials=4, iters=10), None, True),
+    # leaves built in float64 then cast (from_circuit_file(leaf_precision="double")); the case
+    # also records the float64 state-vector amplitudes of the bitstrings (TensorNetworkCircuit.state_vec)
+    "n12_sparse5_f64leaves": (n12_qsim, lambda: list(KAT_N12), dict(sc_target=30, trials=4, iters=10), None, True),
+    "n12_sparse64_sc9_f64leaves": (n12_qsim, lambda: random_bitstrings(12, 64, 1), dict(sc_target=9, trials=4, iters=10), None, True),
     "n30_sparse64_sc26": (n30_qsim, lambda: google_amplitudes(64)[0], dict(sc_target=26, trials=4, iters=5), None, False),
     "n30_full": (n30_qsim, lambda: [], dict(sc_target=30, trials=4, iters=5), [0], False),
     # BASELINE config 2 sharded over its first 3 output qubits: 8 shards x 4 regular
@@ -167,6 +171,20 @@ def google_extra(name, bitstrings):
     return {"google_amplitudes": [complex(table[b]) for b in bitstrings]}
 
 
+def statevector_extra(name, circ_fn, bitstrings):
+    """float64 state-vector amplitudes of the requested bitstrings (n12 "_f64leaves" cases): the truth
+    no complex64 pipeline can be better than."""
+    if not name.endswith("_f64leaves"):
+        return {}
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        sv = artensor.TensorNetworkCircuit(circ_fn(), dtype=torch.complex128).state_vec().reshape(-1)
+    finally:
+        torch.set_default_dtype(old)
+    return {"statevector_f64": {b: complex(sv[int(b, 2)]) for b in bitstrings}}
+
+
 def validate_scheme(scheme, pattern):
     """B2: every chunked step must cover exactly next_shape[0] rows, no empty chunk."""
     if pattern != "sparse":
@@ -186,9 +204,10 @@ def build(name):
     if not os.path.exists(case_path):
         t0 = time.time()
         shard_bits = int(name.rsplit("_shard", 1)[1]) if "_shard" in name else 0
-        if name.endswith("_own") or shard_bits:
+        f64 = name.endswith("_f64leaves")
+        if name.endswith("_own") or shard_bits or f64:
             from artensor_b200 import TensorNetworkSimulation as OwnSimulation
-            sim = OwnSimulation.from_circuit_file(circ_fn(), bitstrings)
+            sim = OwnSimulation.from_circuit_file(circ_fn(), bitstrings, leaf_precision="double" if f64 else "single")
             assert sim.scheme_compiler == "b200"
         else:
             sim = TensorNetworkSimulation.from_circuit_file(circ_fn(), bitstrings)
@@ -206,7 +225,7 @@ def build(name):
             bitstrings_sorted=getattr(sim, "bitstrings_sorted", None),
             n_qubits=len(sim.final_qubits),
             extra={"prepare": {k: v for k, v in prep.items()}, "bitstrings_in": bitstrings, "n_shard_bonds": shard_bits,
-                   **google_extra(name, bitstrings),
+                   **google_extra(name, bitstrings), **statevector_extra(name, circ_fn, bitstrings),
                    "ref_slicing_indices": {b: [(int(t), int(d)) for t, d in v] for b, v in sim.slicing_indices.items()}},
         )
     case = load_case(case_path)
