@@ -76,10 +76,6 @@ struct SkinnyParams {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return *(const uint32_t*)&h;
-}
 
 // KC = complex k per row and k-block, KB = k-blocks (K = KC * KB; KB == 2 only with KC == 32: the
 // two producer groups then convert the two k-blocks of the SAME tile, each with its own row scale,
@@ -310,12 +306,14 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                     for (int q = 0; q < 4; ++q) {
                         const int k = 4 * c + q;
                         if (k < KC) {
-                            const float xr = av[i][k].x * sc, xi = av[i][k].y * sc;
-                            const __half2 hh = __floats2half2_rn(xr, xi);
+                            // packed fp32x2 math (sm_100): scale, and residual x * sc - hi, one instruction each
+                            const float2 xs = __fmul2_rn(av[i][k], make_float2(sc, sc));
+                            const __half2 hh = __float22half2_rn(xs);
                             h[q] = *(const uint32_t*)&hh;
                             if constexpr (PANELS == 2) {
-                                const float2 hf = __half22float2(hh);
-                                l[q] = pack_half2(xr - hf.x, xi - hf.y);
+                                const float2 lo = __ffma2_rn(__half22float2(hh), make_float2(-1.f, -1.f), xs);
+                                const __half2 ll = __float22half2_rn(lo);
+                                l[q] = *(const uint32_t*)&ll;
                             }
                         } else {
                             h[q] = 0u;

@@ -52,6 +52,62 @@ __device__ __forceinline__ void cfma(float2& acc, const float2 a, const float2 b
     acc.y = fmaf(a.y, b.x, acc.y);
 }
 
+// Packed form (fma.rn.f32x2, sm_100): TWO outputs n, n+1 per instruction.  The right operand is kept
+// PLANAR in shared memory (real plane, imaginary plane), the accumulators planar in registers:
+//   accR(n, n+1) += a.x * bR(n, n+1) - a.y * bI(n, n+1)      accI(n, n+1) += a.x * bI(n, n+1) + a.y * bR(n, n+1)
+// -- the same four fused multiply-adds per output in the same order as cfma (bit-identical results), in
+// half the instructions: these kernels are bound by issue slots, not by the FMA count, once the SM
+// clock sits at the power-capped ~1.2 GHz of a long slice.
+struct RowAmp {
+    float2 x, y, ny;          // (a.x, a.x), (a.y, a.y), (-a.y, -a.y)
+};
+__device__ __forceinline__ RowAmp row_amp(const float2 a) {
+    RowAmp r;
+    r.x = make_float2(a.x, a.x);
+    r.y = make_float2(a.y, a.y);
+    r.ny = make_float2(-a.y, -a.y);
+    return r;
+}
+__device__ __forceinline__ void cfma2(float2& accR, float2& accI, const RowAmp& a, const float2 bR, const float2 bI) {
+#ifdef TNC_STEM_SCALAR      // A/B build: the same planar data flow with scalar FFMAs
+    accR.x = fmaf(a.x.x, bR.x, accR.x), accR.y = fmaf(a.x.x, bR.y, accR.y);
+    accR.x = fmaf(a.ny.x, bI.x, accR.x), accR.y = fmaf(a.ny.x, bI.y, accR.y);
+    accI.x = fmaf(a.x.x, bI.x, accI.x), accI.y = fmaf(a.x.x, bI.y, accI.y);
+    accI.x = fmaf(a.y.x, bR.x, accI.x), accI.y = fmaf(a.y.x, bR.y, accI.y);
+#else
+    accR = __ffma2_rn(a.x, bR, accR);
+    accR = __ffma2_rn(a.ny, bI, accR);
+    accI = __ffma2_rn(a.x, bI, accI);
+    accI = __ffma2_rn(a.y, bR, accI);
+#endif
+}
+// One row amplitude against NCH outputs: bR / bI point at the NCH reals / imaginaries of B[k][n0 ..]
+// (warp-uniform shared-memory addresses: broadcast loads).
+template <int NCH>
+__device__ __forceinline__ void row_fma(float2* accR, float2* accI, const float2 a, const float* bR, const float* bI) {
+    static_assert(NCH >= 2 && NCH % 2 == 0, "packed path: pairs of outputs");
+    const RowAmp ra = row_amp(a);
+    if constexpr (NCH == 2) {
+        cfma2(accR[0], accI[0], ra, *(const float2*)bR, *(const float2*)bI);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NCH; i += 4) {
+            const float4 r = *(const float4*)(bR + i), m = *(const float4*)(bI + i);
+            cfma2(accR[i / 2], accI[i / 2], ra, make_float2(r.x, r.y), make_float2(m.x, m.y));
+            cfma2(accR[i / 2 + 1], accI[i / 2 + 1], ra, make_float2(r.z, r.w), make_float2(m.z, m.w));
+        }
+    }
+}
+// planar accumulators -> interleaved (re, im) outputs
+template <int NCH>
+__device__ __forceinline__ void interleave(const float2* accR, const float2* accI, float2* out) {
+#pragma unroll
+    for (int i = 0; i < NCH / 2; ++i) {
+        out[2 * i] = make_float2(accR[i].x, accI[i].x);
+        out[2 * i + 1] = make_float2(accR[i].y, accI[i].y);
+    }
+}
+
 // NCH: outputs (complex) a thread produces per pass over its row; KCH: row amplitudes per chunk.
 // Light variants (few accumulators) are compiled for 4 resident CTAs per SM: their rows are short,
 // and the bytes in flight per SM are what bounds them.
@@ -59,8 +115,9 @@ template <int NCH, int KCH>
 __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4 : 2)) stem_kernel(const StemParams p) {
     extern __shared__ __align__(16) unsigned char stem_smem[];
     const int K = 1 << p.kb, N = 1 << p.nb;
-    float2* Bs = (float2*)stem_smem;                    // [fold][K][N]
-    uint32_t* koff = (uint32_t*)(Bs + (size_t)p.fold * K * N);   // A offset of contracted index k
+    float* BsR = (float*)stem_smem;                     // [fold][K][N] real plane, then the imaginary plane
+    float* BsI = BsR + (size_t)p.fold * K * N;
+    uint32_t* koff = (uint32_t*)(BsI + (size_t)p.fold * K * N);   // A offset of contracted index k
     const uint32_t stage = ((smem_u32(koff + K) + 15u) & ~15u) + (threadIdx.x >> 5) * 4096u;   // this warp's staging buffer
     const bool staged = NCH >= 2 && p.mb >= 5;           // whole warps only
     const int lane = threadIdx.x & 31;
@@ -92,7 +149,9 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
                     uint32_t o = 0;
                     for (int i = 0; i < p.kb; ++i) o |= ((uint32_t)(k >> i) & 1u) << p.k_b[i];
                     for (int i = 0; i < p.nb; ++i) o |= ((uint32_t)(n >> i) & 1u) << p.n_b[i];
-                    Bs[(size_t)f * K * N + e] = bsrc[o];
+                    const float2 x = bsrc[o];
+                    BsR[(size_t)f * K * N + e] = x.x;
+                    BsI[(size_t)f * K * N + e] = x.y;
                 }
             }
             __syncthreads();
@@ -109,13 +168,16 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
         // folded: the row of A is read from HBM once and meets every row of B (the repeats hit L1/L2)
 #pragma unroll 1
         for (int f = 0; f < p.fold; ++f) {
-        const float2* __restrict__ Bf = Bs + (size_t)f * K * N;
+        const float* __restrict__ BfR = BsR + (size_t)f * K * N;
+        const float* __restrict__ BfI = BsI + (size_t)f * K * N;
         float2* __restrict__ cp = p.c + ((((int64_t)b * p.fold + f) << p.mb) + r) * N;
 #pragma unroll 1
         for (int n0 = 0; n0 < N; n0 += NCH) {
-            float2 acc[NCH];
+            float2 acc[NCH];                             // NCH == 1: the output; else (accR, accI) pairs of outputs
 #pragma unroll
             for (int i = 0; i < NCH; ++i) acc[i] = make_float2(0.f, 0.f);
+            float2* accR = acc;
+            float2* accI = acc + (NCH >= 2 ? NCH / 2 : 0);
 #pragma unroll 1
             for (int k0 = 0; k0 < K; k0 += KCH) {
                 float2 av[KCH];
@@ -132,28 +194,22 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
                 }
 #pragma unroll
                 for (int j = 0; j < KCH; ++j) {
-                    const float2* brow = Bf + (size_t)(k0 + j) * N + n0;
-                    if constexpr (NCH == 1) {
-                        cfma(acc[0], av[j], brow[0]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NCH; i += 2) {
-                            const float4 bb = *(const float4*)(brow + i);      // warp-uniform: broadcast
-                            cfma(acc[i], av[j], make_float2(bb.x, bb.y));
-                            cfma(acc[i + 1], av[j], make_float2(bb.z, bb.w));
-                        }
-                    }
+                    const size_t bo = (size_t)(k0 + j) * N + n0;
+                    if constexpr (NCH == 1) cfma(acc[0], av[j], make_float2(BfR[bo], BfI[bo]));
+                    else row_fma<NCH>(accR, accI, av[j], BfR + bo, BfI + bo);
                 }
             }
             if constexpr (NCH == 1) {
                 cp[n0] = acc[0];
             } else {
+                float2 out[NCH];
+                interleave<NCH>(accR, accI, out);
                 if (staged) {
-                    store_rows_coalesced<NCH / 2>(stage, (const float*)acc, (float*)(cp - (int64_t)lane * N + n0), 2 * (int64_t)N, lane);
+                    store_rows_coalesced<NCH / 2>(stage, (const float*)out, (float*)(cp - (int64_t)lane * N + n0), 2 * (int64_t)N, lane);
                 } else {
 #pragma unroll
                     for (int i = 0; i < NCH; i += 2)
-                        *(float4*)(cp + n0 + i) = make_float4(acc[i].x, acc[i].y, acc[i + 1].x, acc[i + 1].y);
+                        *(float4*)(cp + n0 + i) = make_float4(out[i].x, out[i].y, out[i + 1].x, out[i + 1].y);
                 }
             }
         }
@@ -211,7 +267,8 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     const int N = NCH < 16 ? NCH : (1 << p.nb);        // the launcher picks NCH = min(N, 16)
     const uint32_t stage_bytes = (uint32_t)(K << 8) * 8u;
-    float2* Bs = (float2*)(bulk_smem + p.off_b);                 // [b_rows][K][N]
+    float* BsR = (float*)(bulk_smem + p.off_b);                  // [b_rows][K][N] real plane, then the imaginary plane
+    float* BsI = BsR + (size_t)p.b_rows * K * N;
     uint32_t* koff_s = (uint32_t*)(bulk_smem + p.off_koff);      // stage offset (amplitudes) of contracted index k
     const uint32_t bar_full = smem_u32(bulk_smem + p.off_bars), bar_empty = bar_full + 8u * (uint32_t)p.stages;
     const uint32_t stage0 = smem_u32(bulk_smem);
@@ -222,7 +279,9 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
         uint32_t o = 0;
         for (int i = 0; i < KB; ++i) o |= ((uint32_t)(k >> i) & 1u) << p.k_b[i];
         for (int i = 0; i < p.nb; ++i) o |= ((uint32_t)(n >> i) & 1u) << p.n_b[i];
-        Bs[e] = p.b[((int64_t)row << p.rank_b) + o];
+        const float2 x = p.b[((int64_t)row << p.rank_b) + o];
+        BsR[e] = x.x;
+        BsI[e] = x.y;
     }
     if (tid < K) {
         uint32_t lo = 0, c = 0;
@@ -334,31 +393,28 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
             int32_t rb = 0;
             if (p.rows_mode_b == TNC_ROWS_IDENTITY) rb = b;
             else if (p.rows_mode_b >= 0) rb = p.rows_b[b];
-            const float2* __restrict__ Bf = Bs + (size_t)rb * K * N;
+            const float* __restrict__ BfR = BsR + (size_t)rb * K * N;
+            const float* __restrict__ BfI = BsI + (size_t)rb * K * N;
             float2* __restrict__ cp = p.c + ((((int64_t)b) << p.mb) + r) * N;
 #pragma unroll 1
             for (int n0 = 0; n0 < N; n0 += NCH) {
-                float2 acc[NCH];
+                float2 acc[NCH];                         // NCH == 1: the output; else (accR, accI) pairs of outputs
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) acc[i] = make_float2(0.f, 0.f);
+                float2* accR = acc;
+                float2* accI = acc + (NCH >= 2 ? NCH / 2 : 0);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float2* brow = Bf + (size_t)k * N + n0;
-                    if constexpr (NCH == 1) {
-                        cfma(acc[0], av[k], brow[0]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NCH; i += 2) {
-                            const float4 bb = *(const float4*)(brow + i);      // warp-uniform: broadcast
-                            cfma(acc[i], av[k], make_float2(bb.x, bb.y));
-                            cfma(acc[i + 1], av[k], make_float2(bb.z, bb.w));
-                        }
-                    }
+                    const size_t bo = (size_t)k * N + n0;
+                    if constexpr (NCH == 1) cfma(acc[0], av[k], make_float2(BfR[bo], BfI[bo]));
+                    else row_fma<NCH>(accR, accI, av[k], BfR + bo, BfI + bo);
                 }
                 if constexpr (NCH == 1) {
                     cp[n0] = acc[0];
                 } else {
-                    store_rows_coalesced<NCH / 2>(stage_w, (const float*)acc, (float*)(cp - (int64_t)lane * N + n0), 2 * (int64_t)N, lane);
+                    float2 out[NCH];
+                    interleave<NCH>(accR, accI, out);
+                    store_rows_coalesced<NCH / 2>(stage_w, (const float*)out, (float*)(cp - (int64_t)lane * N + n0), 2 * (int64_t)N, lane);
                 }
             }
         }
