@@ -314,7 +314,7 @@ int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* e) {
     }
     if (e->algo == TNC_ALGO_SKINNY && !skinny_supported(*e, plan->dtype, plan->tc_precision)) {
         set_error("einsum: the streaming tensor-core kernel does not support this step (m=%d k=%d n=%d h=%d nb=%d, "
-                  "precision %d; needs 2 <= k <= 5, 1 <= n <= 7, m >= 7, one right operand, output [rows][m][n])",
+                  "precision %d; needs 2 <= k <= 6 (n <= 6 at k = 6), 1 <= n <= 7, m >= 7, one right operand, output [rows][m][n])",
                   e->n_m, e->n_k, e->n_n, e->n_h, e->nb, plan->tc_precision);
         return TNC_ERR_UNSUPPORTED;
     }
