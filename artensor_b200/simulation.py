@@ -83,6 +83,15 @@ def partition_slices(begin, end, rank, world):
 _Base = _reference_simulation_class()
 
 
+def _need_base():
+    """The inherited parts of the class exist only if `artensor` was importable when this module was
+    imported (the base class is fixed at class creation)."""
+    if _Base is object:
+        _reference()                       # raises the explanatory ImportError when it is absent
+        raise ImportError("`artensor` became importable only after `artensor_b200` was imported: put the "
+                          "reference on sys.path (or `import artensor`) before importing artensor_b200")
+
+
 class TensorNetworkSimulation(_Base):
     """The reference's simulation object with the hot path replaced.
 
@@ -111,8 +120,7 @@ class TensorNetworkSimulation(_Base):
         """The reference's order search and slicing, unchanged (simulation.py:47-77 through
         `super()`); afterwards the slicing indices are recounted on the real tensors
         (`slicing_dims`) and kept in slice-id order."""
-        if _Base is object:
-            _reference()                   # raises the explanatory ImportError
+        _need_base()
         self._sc_target = sc_target
         self.shard_bonds = []
         super().prepare_contraction(sc_target=sc_target, trials=trials, iters=iters, betas=betas,
@@ -270,8 +278,7 @@ class TensorNetworkSimulation(_Base):
         if leaf_precision not in ("single", "double"):
             raise ValueError(f"leaf_precision {leaf_precision!r}: expected 'single' or 'double'")
         if leaf_precision == "single":
-            if _Base is object:
-                _reference()
+            _need_base()
             return super().from_circuit_file(circuit_filename, bitstrings)
         ref = _reference()
         pattern, max_bitstrings = check_bitstrings(bitstrings)

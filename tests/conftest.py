@@ -10,6 +10,13 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The reference package (build container only; absent on the GPU box) must be importable BEFORE
+# artensor_b200 is imported: artensor_b200.TensorNetworkSimulation subclasses the reference's class
+# when it can.  Tests that need the reference skip themselves when it is missing.
+_REF = os.environ.get("ARTENSOR_REFERENCE", "/root/reference")
+if os.path.isdir(os.path.join(_REF, "artensor")) and _REF not in sys.path:
+    sys.path.append(_REF)
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
