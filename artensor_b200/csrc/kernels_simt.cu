@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(kThreads) simt_einsum_kernel(SimtEinsumParams 
 // threads take consecutive k: the contracted bits are ordered by their position in A, so the loads
 // of A are coalesced), every thread keeps all 2^RC partial sums, and the CTA reduces them.
 constexpr int kRowdotThreads = 128;
-// NM / NN: left-only / right-only output bits (NM + NN <= 4, no shared kept modes)
+// NM / NN: left-only / right-only output bits (NM + NN <= 4, or NM, NN <= 3: up to 64 outputs per row --
+// the batched tail of a deep sparse scheme, e.g. [512 rows][3 bits][19 bits] x [512][19 bits][3 bits] in the
+// sc_target-32 n53 tree: 34 GB streamed once; the generic kernel ran it at 0.2 TB/s); no shared kept modes
 template <int NM, int NN>
 __global__ void __launch_bounds__(kRowdotThreads) simt_rowdot_kernel(SimtEinsumParams p) {
     constexpr int M = 1 << NM, NQ = 1 << NN, RC = NM + NN;
@@ -140,22 +142,58 @@ __global__ void __launch_bounds__(kRowdotThreads) simt_rowdot_kernel(SimtEinsumP
         for (int i = 0; i < M; ++i)
 #pragma unroll
             for (int j = 0; j < NQ; ++j) acc[i][j] = make_float2(0.f, 0.f);
-        for (uint32_t k = threadIdx.x; k < nk; k += kRowdotThreads) {
-            const uint32_t ka = p.koff_a[k], kb = p.koff_b[k];
-            float2 x[M], y[NQ];
-#pragma unroll
-            for (int i = 0; i < M; ++i) x[i] = a[oa[i] + ka];
-#pragma unroll
-            for (int j = 0; j < NQ; ++j) y[j] = b[ob[j] + kb];
+        if constexpr (NQ >= 2) {
+            // packed fp32x2 (sm_100): two right-only outputs per instruction, planar (re, re) / (im, im)
+            // accumulators, the same four fused multiply-adds per output in the same order
+            float2 accR[M][NQ / 2], accI[M][NQ / 2];
 #pragma unroll
             for (int i = 0; i < M; ++i)
 #pragma unroll
-                for (int j = 0; j < NQ; ++j) {
-                    acc[i][j].x = fmaf(x[i].x, y[j].x, acc[i][j].x);
-                    acc[i][j].x = fmaf(-x[i].y, y[j].y, acc[i][j].x);
-                    acc[i][j].y = fmaf(x[i].x, y[j].y, acc[i][j].y);
-                    acc[i][j].y = fmaf(x[i].y, y[j].x, acc[i][j].y);
+                for (int j = 0; j < NQ / 2; ++j) accR[i][j] = accI[i][j] = make_float2(0.f, 0.f);
+            for (uint32_t k = threadIdx.x; k < nk; k += kRowdotThreads) {
+                const uint32_t ka = p.koff_a[k], kb = p.koff_b[k];
+                float2 x[M], y[NQ];
+#pragma unroll
+                for (int i = 0; i < M; ++i) x[i] = a[oa[i] + ka];
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) y[j] = b[ob[j] + kb];
+#pragma unroll
+                for (int j = 0; j < NQ / 2; ++j) {
+                    const float2 yr = make_float2(y[2 * j].x, y[2 * j + 1].x), yi = make_float2(y[2 * j].y, y[2 * j + 1].y);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        accR[i][j] = __ffma2_rn(make_float2(x[i].x, x[i].x), yr, accR[i][j]);
+                        accR[i][j] = __ffma2_rn(make_float2(-x[i].y, -x[i].y), yi, accR[i][j]);
+                        accI[i][j] = __ffma2_rn(make_float2(x[i].x, x[i].x), yi, accI[i][j]);
+                        accI[i][j] = __ffma2_rn(make_float2(x[i].y, x[i].y), yr, accI[i][j]);
+                    }
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int j = 0; j < NQ / 2; ++j) {
+                    acc[i][2 * j] = make_float2(accR[i][j].x, accI[i][j].x);
+                    acc[i][2 * j + 1] = make_float2(accR[i][j].y, accI[i][j].y);
+                }
+        } else {
+            for (uint32_t k = threadIdx.x; k < nk; k += kRowdotThreads) {
+                const uint32_t ka = p.koff_a[k], kb = p.koff_b[k];
+                float2 x[M], y[NQ];
+#pragma unroll
+                for (int i = 0; i < M; ++i) x[i] = a[oa[i] + ka];
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) y[j] = b[ob[j] + kb];
+#pragma unroll
+                for (int i = 0; i < M; ++i)
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) {
+                        acc[i][j].x = fmaf(x[i].x, y[j].x, acc[i][j].x);
+                        acc[i][j].x = fmaf(-x[i].y, y[j].y, acc[i][j].x);
+                        acc[i][j].y = fmaf(x[i].x, y[j].y, acc[i][j].y);
+                        acc[i][j].y = fmaf(x[i].y, y[j].x, acc[i][j].y);
+                    }
+            }
         }
 #pragma unroll
         for (int i = 0; i < M; ++i)
@@ -190,21 +228,24 @@ __global__ void __launch_bounds__(kRowdotThreads) simt_rowdot_kernel(SimtEinsumP
     }
 }
 
+// (nm, nn) combinations compiled: nm + nn <= 4, and every nm, nn <= 3
+constexpr bool rowdot_shape(int nm, int nn) { return nm >= 0 && nn >= 0 && (nm + nn <= 4 || (nm <= 3 && nn <= 3)); }
+
 template <int NM>
 void launch_rowdot_n(const SimtEinsumParams& p, int nn, int grid, cudaStream_t s) {
-    if constexpr (NM <= 4) {
+    if constexpr (rowdot_shape(NM, 0)) {
         if (nn == 0) simt_rowdot_kernel<NM, 0><<<grid, kRowdotThreads, 0, s>>>(p);
     }
-    if constexpr (NM <= 3) {
+    if constexpr (rowdot_shape(NM, 1)) {
         if (nn == 1) simt_rowdot_kernel<NM, 1><<<grid, kRowdotThreads, 0, s>>>(p);
     }
-    if constexpr (NM <= 2) {
+    if constexpr (rowdot_shape(NM, 2)) {
         if (nn == 2) simt_rowdot_kernel<NM, 2><<<grid, kRowdotThreads, 0, s>>>(p);
     }
-    if constexpr (NM <= 1) {
+    if constexpr (rowdot_shape(NM, 3)) {
         if (nn == 3) simt_rowdot_kernel<NM, 3><<<grid, kRowdotThreads, 0, s>>>(p);
     }
-    if constexpr (NM == 0) {
+    if constexpr (rowdot_shape(NM, 4)) {
         if (nn == 4) simt_rowdot_kernel<NM, 4><<<grid, kRowdotThreads, 0, s>>>(p);
     }
 }
@@ -340,7 +381,7 @@ int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
     if (p.total <= 0) return TNC_OK;
     // many rows, a long contraction, <= 16 outputs per row, no shared kept modes: one CTA per row
     static const bool no_rowdot = knob("TNC_NO_ROWDOT") != nullptr;      // measurement aid
-    if (!no_rowdot && dtype == TNC_C64 && p.rank_c <= 4 && p.kb >= 7 && (p.total >> p.rank_c) >= 32) {
+    if (!no_rowdot && dtype == TNC_C64 && p.rank_c <= 6 && p.kb >= 7 && (p.total >> p.rank_c) >= 32) {
         int nm = 0, nn = 0;
         bool plain = true;
         for (int q = 0; q < p.rank_c; ++q) {
@@ -348,7 +389,7 @@ int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
             else if (p.c2a[q] >= 0) ++nm;
             else ++nn;
         }
-        if (plain) {
+        if (plain && rowdot_shape(nm, nn)) {
             const int grid = (int)std::min<int64_t>(p.total >> p.rank_c, (int64_t)sm_count() * 16);
             switch (nm) {
                 case 0: launch_rowdot_n<0>(p, nn, grid, s); break;

@@ -1523,16 +1523,27 @@ gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 drain_3m<1, DB>(slot_wait(), re, im, slot_free);
                 drain_3m<2, DB>(slot_wait(), re, im, slot_free);
             }
-            float acc[CPT];                              // interleaved (re, im) per complex column
+            // whole tiles by construction (M % 256 == 0, N % 256 == 0, no folded right-operand rows): 32
+            // interleaved floats (16 complex columns) at a time through the warp's staging buffer, straight
+            // from the planar accumulators (an interleaved copy of all 128 made the chunk loop spill)
+            {
+                const float sab = f16_inv_scale(g.amax[0]) * f16_inv_scale(g.amax[1]) * g.out_scale;
+                const uint32_t stage = base + C::STAGES * C::STAGE + 256 + (uint32_t)(warp - 2) * 4096u;
+                const int row0 = (2 * t.m_tile + (int)rank) * BM + q * 32, col0 = t.n0 + half * CPT;
+                float* crow = g.c + c_row(g, t.batch, row0) * g.ldc + col0;
 #pragma unroll
-            for (int j = 0; j < CPT / 4; ++j) {
-                acc[4 * j] = re[j].x;
-                acc[4 * j + 1] = im[j].x;
-                acc[4 * j + 2] = re[j].y;
-                acc[4 * j + 3] = im[j].y;
+                for (int c = 0; c < CPT; c += 32) {
+                    float o[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        o[4 * j] = re[c / 4 + j].x * sab;
+                        o[4 * j + 1] = im[c / 4 + j].x * sab;
+                        o[4 * j + 2] = re[c / 4 + j].y * sab;
+                        o[4 * j + 3] = im[c / 4 + j].y * sab;
+                    }
+                    store_rows_coalesced<8>(stage, o, crow + c, g.ldc, lane);
+                }
             }
-            store_tile_rows<CPT, true>(g, base + C::STAGES * C::STAGE + 256 + (uint32_t)(warp - 2) * 4096u, t.batch,
-                                       (2 * t.m_tile + (int)rank) * BM + q * 32, t.n0 + half * CPT, acc, lane);
         }
     }
     tc_fence_before();
@@ -2016,8 +2027,8 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     if (op->two_cta) grid &= ~(int64_t)1;               // whole pairs; tiles is even here
     g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
     if (op->use_3m) {
-        static const int drain = knob("TNC_TC_DRAIN") ? atoi(knob("TNC_TC_DRAIN")) : 16;
-        rc = drain == 32 ? launch_gemm3m<TNC_TC_3XF16, 32>(maps.m, g, grid, s) : launch_gemm3m<TNC_TC_3XF16, 16>(maps.m, g, grid, s);
+        // 16 TMEM columns per tcgen05.ld batch: 32 spill inside the chunk loop at the kernel's 168 registers
+        rc = launch_gemm3m<TNC_TC_3XF16, 16>(maps.m, g, grid, s);
     } else if (op->two_cta) {
         switch (op->precision) {
             case TNC_TC_3XF16: rc = launch_gemm_2cta<TNC_TC_3XF16>(maps.m, g, grid, s); break;

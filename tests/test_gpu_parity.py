@@ -648,10 +648,12 @@ def test_plan_cache_follows_scheme_contents(dev):
         assert np.abs(got - want).max() / np.sqrt(np.mean(np.abs(want) ** 2)) < 1e-5
 
 
-@pytest.mark.parametrize("m,n,k", [(2, 2, 9), (0, 0, 8), (1, 0, 11), (2, 1, 7), (0, 3, 10)])
+@pytest.mark.parametrize("m,n,k", [(2, 2, 9), (0, 0, 8), (1, 0, 11), (2, 1, 7), (0, 3, 10),
+                                   (3, 3, 9), (3, 2, 8), (2, 3, 10), (3, 1, 7), (1, 3, 12)])
 def test_generic_kernel_long_contraction_per_row(dev, m, n, k):
-    """The tail of a sparse scheme: many gathered row pairs, a long contraction, <= 16 outputs per
-    row (n30 / 10000 bitstrings at sc_target 27: [9998][2 bits][11 bits] x [9998][11 bits][2 bits]).
+    """The tail of a sparse scheme: many gathered row pairs, a long contraction, <= 64 outputs per
+    row (n30 / 10000 bitstrings at sc_target 27: [9998][2 bits][11 bits] x [9998][11 bits][2 bits];
+    the sc_target-32 n53 tree: [512][3 bits][19 bits] x [512][19 bits][3 bits], 34 GB streamed once).
     The generic path runs these with one CTA per output row (simt_rowdot_kernel)."""
     from artensor_b200 import ContractionPlan
     rng = np.random.RandomState(40 + k)
