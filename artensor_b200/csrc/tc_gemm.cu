@@ -272,6 +272,7 @@ struct Pack2Params {
     const uint32_t* amax;
     int32_t rows_mode, rank, tbits, mode, n_outer;
     int32_t inner_bits, blocked, bn_log2, kb_log2;   // PACK_EXPAND_SPLIT_F16 (see PackDesc)
+    int32_t planes;                                  // PACK_PLANAR3_F16 (see PackDesc)
     int64_t n_tiles;
     int8_t tile_src_pos[kPack2TileBits];   // source position of tile bit j in SOURCE order
     int8_t u2v[kPack2TileBits];            // destination-order bit that source-order bit j is
@@ -455,9 +456,10 @@ __global__ void __launch_bounds__(kPack2Threads, 4) pack2_kernel(const Pack2Para
                 float v[3][4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    v[0][e] = x[e].x * sc;
-                    v[1][e] = x[e].y * sc;
-                    v[2][e] = v[0][e] + v[1][e];
+                    const float xr = x[e].x * sc, xi = x[e].y * sc;
+                    if (p.planes == 1) v[0][e] = xr + xi, v[1][e] = xr, v[2][e] = xi;
+                    else if (p.planes == 2) v[0][e] = xr, v[1][e] = xi - xr, v[2][e] = xr + xi;
+                    else v[0][e] = xr, v[1][e] = xi, v[2][e] = xr + xi;
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -543,6 +545,7 @@ int launch_pack2(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo,
     p.rank = d.rank;
     p.mode = d.mode;
     p.inner_bits = d.inner_bits;
+    p.planes = d.planes;
     p.blocked = d.blocked;
     p.bn_log2 = d.bn_log2;
     p.kb_log2 = d.kb_log2 ? d.kb_log2 : 4;
@@ -1336,7 +1339,9 @@ struct Cfg3 {
 // Folds 64 columns of product P (0: Ar Br, 1: Ai Bi, 2: (Ar + Ai)(Br + Bi)) into the planar accumulators
 // (re[j], im[j] = columns 2j, 2j + 1) with packed fp32x2 adds: 2.5 instructions per complex output and chunk.
 // `release` runs as soon as the slot's last columns sit in registers (before their adds).
-template <int P, int DB, typename Release>
+// GAUSS: the products are X = (Ar + Ai) Br, Y = Ar (Bi - Br), Z = Ai (Br + Bi) with Cr = X - Z, Ci = X + Y: four
+// packed adds per column pair and chunk instead of Karatsuba's five.
+template <int P, int DB, bool GAUSS, typename Release>
 __device__ __forceinline__ void drain_3m(uint32_t taddr, float2* re, float2* im, Release release) {
     const float2 neg = make_float2(-1.f, -1.f);
 #pragma unroll
@@ -1350,7 +1355,16 @@ __device__ __forceinline__ void drain_3m(uint32_t taddr, float2* re, float2* im,
         for (int j = 0; j < DB; j += 2) {
             const float2 x = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
             const int o = (c + j) >> 1;
-            if (P == 0) {
+            if constexpr (GAUSS) {
+                if (P == 0) {
+                    re[o] = __fadd2_rn(re[o], x);
+                    im[o] = __fadd2_rn(im[o], x);
+                } else if (P == 1) {
+                    im[o] = __fadd2_rn(im[o], x);
+                } else {
+                    re[o] = __ffma2_rn(x, neg, re[o]);
+                }
+            } else if (P == 0) {
                 re[o] = __fadd2_rn(re[o], x);
                 im[o] = __ffma2_rn(x, neg, im[o]);
             } else if (P == 1) {
@@ -1363,7 +1377,7 @@ __device__ __forceinline__ void drain_3m(uint32_t taddr, float2* re, float2* im,
     }
 }
 
-template <int PREC, int DB>
+template <int PREC, int DB, bool GAUSS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
     using C = Cfg3<PREC>;
@@ -1519,9 +1533,9 @@ gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             };
 #pragma unroll 1
             for (int chunk = 0; chunk < nchunks; ++chunk) {
-                drain_3m<0, DB>(slot_wait(), re, im, slot_free);
-                drain_3m<1, DB>(slot_wait(), re, im, slot_free);
-                drain_3m<2, DB>(slot_wait(), re, im, slot_free);
+                drain_3m<0, DB, GAUSS>(slot_wait(), re, im, slot_free);
+                drain_3m<1, DB, GAUSS>(slot_wait(), re, im, slot_free);
+                drain_3m<2, DB, GAUSS>(slot_wait(), re, im, slot_free);
             }
             // whole tiles by construction (M % 256 == 0, N % 256 == 0, no folded right-operand rows): 32
             // interleaved floats (16 complex columns) at a time through the warp's staging buffer, straight
@@ -1641,12 +1655,12 @@ int launch_gemm_2cta(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, c
     return TNC_OK;
 }
 
-template <int PREC, int DB>
+template <int PREC, int DB, bool GAUSS>
 int launch_gemm3m(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cudaStream_t s) {
     static bool configured_on[kMaxDevices] = {};       // the attribute is per device
     bool& configured = configured_on[current_device()];
     if (!configured) {
-        TNC_CUDA(cudaFuncSetAttribute(gemm3m_2cta_kernel<PREC, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<PREC>::SMEM));
+        TNC_CUDA(cudaFuncSetAttribute(gemm3m_2cta_kernel<PREC, DB, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<PREC>::SMEM));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -1661,7 +1675,7 @@ int launch_gemm3m(const CUtensorMap* maps, const GemmArgs& g, int64_t grid, cuda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm3m_2cta_kernel<PREC, DB>, maps[0], maps[2], g));
+    TNC_CUDA(cudaLaunchKernelEx(&cfg, gemm3m_2cta_kernel<PREC, DB, GAUSS>, maps[0], maps[2], g));
     return TNC_OK;
 }
 
@@ -1692,6 +1706,7 @@ struct TcGemmOp {
     int blocked = 0, blocked_b = 0;                   // tile-contiguous panels (A, B')
     int two_cta = 0;                                  // CTA pairs (cta_group::2) on 256 x 256 tiles
     int use_3m = 0;                                   // 3M complex product on planar panels (gemm3m_2cta_kernel)
+    int gauss = 0;                                    //   in Gauss's form (planes s, r, i / r, i - r, s) instead of Karatsuba's
     int grid = 1;
     int64_t words_off = 0;                            // 256 bytes at the end of the step's scratch region (in the WORKSPACE, so that
                                                       // executions with different workspaces never share them): [0], [1] amax bits
@@ -1829,6 +1844,12 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     if (op->use_3m) {
         // planar panels, both operands alike: [tile of 128 rows][block of 64 k][re, im, re + im][hi, lo][128 rows][64 k]
         op->pa.mode = op->pb.mode = PACK_PLANAR3_F16;
+        // Gauss's form saves one of five packed adds per column pair and chunk; measured on one box, three
+        // alternations: 123.4 vs 123.9 ms on the fat step -- no difference, so Karatsuba's stays the default
+        op->gauss = 0;
+        if (const char* env = knob("TNC_TC_GAUSS")) op->gauss = atoi(env) != 0;
+        op->pa.planes = op->gauss ? 1 : 0;
+        op->pb.planes = op->gauss ? 2 : 0;
         int8_t pm[TNC_MAX_BITS], pn[TNC_MAX_BITS];      // operand position of row bit j (output order)
         for (int i = 0; i < e.n_m; ++i) pm[e.m_c[i] - e.n_n] = e.m_a[i];
         for (int i = 0; i < e.n_n; ++i) pn[e.n_c[i]] = e.n_b[i];
@@ -2028,7 +2049,8 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     g.rounds = (int32_t)((op->tiles + grid - 1) / grid);
     if (op->use_3m) {
         // 16 TMEM columns per tcgen05.ld batch: 32 spill inside the chunk loop at the kernel's 168 registers
-        rc = launch_gemm3m<TNC_TC_3XF16, 16>(maps.m, g, grid, s);
+        rc = op->gauss ? launch_gemm3m<TNC_TC_3XF16, 16, true>(maps.m, g, grid, s)
+                       : launch_gemm3m<TNC_TC_3XF16, 16, false>(maps.m, g, grid, s);
     } else if (op->two_cta) {
         switch (op->precision) {
             case TNC_TC_3XF16: rc = launch_gemm_2cta<TNC_TC_3XF16>(maps.m, g, grid, s); break;

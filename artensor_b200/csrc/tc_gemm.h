@@ -46,6 +46,8 @@ struct PackDesc {
     int32_t kb_log2;              //   log2 of the complex k per k-block: 4 (tf32, default) or 5 (fp16)
     const uint32_t* amax;         // fp16 modes: device word with the bits of the operand's largest magnitude;
                                   //   dst_lo may be null (hi part only)
+    int32_t planes;               // PACK_PLANAR3_F16: which three planes -- 0: re, im, re + im (Karatsuba, both operands);
+                                  //   1: re + im, re, im (Gauss, left operand); 2: re, im - re, re + im (Gauss, right operand)
     int8_t src_pos[TNC_MAX_BITS]; // source position feeding destination position i
 };
 int launch_pack(const PackDesc& d, const void* src, void* dst_hi, void* dst_lo, cudaStream_t s);

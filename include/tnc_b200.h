@@ -218,6 +218,7 @@ const char* tnc_last_error(void);
  *   TNC_TC_2CTA=0        single-CTA tiles instead of cta_group::2 pairs (also disables 3M)
  *   TNC_TC_KC=<n>        k-blocks accumulated in tensor memory before the fp32 register add
  *                        (default 1; more = faster, larger round-toward-zero bias)
+ *   TNC_TC_GAUSS=1       3M product in Gauss's form (planes s, r, i / r, i - r, s) instead of Karatsuba's
  *   TNC_TC_SYNC=<n>      k-blocks between the grid-wide lockstep barriers of a GEMM (0 = none)
  *   TNC_TC_GROUP_M=<n>   row tiles per sweep group of the persistent tile order
  *   TNC_TC_BLOCKED=0     row-major instead of tile-contiguous packed panels
