@@ -67,7 +67,7 @@ struct SkinnyParams {
     int32_t groups;                // active producer groups (<= kGroups, <= slots)
     int32_t fold;                  // rows of B folded into N (1 = none): accumulator columns [f * n_real, (f+1) * n_real)
                                    // of a tile are the outputs against row f of B and go to row block (batch * fold + f) of C
-    uint32_t koff_c[32];           // A offset of contracted index k inside one k-block: kernel parameters live in the
+    uint64_t koff_c[32];           // A BYTE offset of contracted index k inside one k-block: kernel parameters live in the
                                    // constant bank, so with k unrolled the offset is an instruction operand (the shared-
                                    // memory table cost an LDS + a 64-bit IMAD per 8-byte load: 6 instructions per load)
     int64_t kblock_off;            // A offset of the second k-block (K = 64)
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
     // ---------------------------------------------------------------- set-up (all threads)
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.slots; ++s) {
-            mbar_init(full_bar(s), 128 * KB);
+            mbar_init(full_bar(s), 4 * KB);         // one arrival per producer warp (its lane 0, behind a __syncwarp)
             mbar_init(done_bar(s), 1);
             mbar_init(free_bar(s), 4);
         }
@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
             for (int t = 0; t < p.n_runs; ++t) toff |= ((r0 >> p.run_src[t]) & (int64_t)p.run_mask[t]) << p.run_dst[t];
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                const float2* __restrict__ ap = p.a + (toff | row_off[i]);
+                // byte pointer of the row + a 32-bit byte offset per contracted index: one 64-bit add per load
+                const char* __restrict__ ap = (const char*)(p.a + (toff | row_off[i]));
                 if (KC >= 2 && p.a_vec) {
 #pragma unroll
                     for (int k = 0; k < KC; k += 2) {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) av[i][k] = TNC_LDG(ap + p.koff_c[k]);
+                    for (int k = 0; k < KC; ++k) av[i][k] = TNC_LDG((const float2*)(ap + p.koff_c[k]));
                 }
             }
             // the slot (shared memory tile, scales, TMEM accumulators) is free once the epilogue of
@@ -326,8 +327,12 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                 }
                 row_scale[(slot * SUBS + kb_mine * R + i) * 128 + row] = f16_inv_scale(mbits);
             }
+            // every thread orders its own tile stores before the tensor core's (async-proxy) reads; ONE arrival per
+            // warp then: the waiting warps (MMA issuer, epilogue) are woken by every arrival on a barrier they sleep
+            // on, and 128 arrivals per tile were ~15 % of all issued instructions
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(full_bar(slot));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(slot));
             // KB == 1: one thread of the group issues the tile's MMAs once every producer of the tile
             // has arrived (KB == 2: the idle third group does, see below)
             if (KB == 1 && (warp & 3) == 0) issue_mma(slot, use);
@@ -353,8 +358,8 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                 slot = 0;
                 ++use;
             }
-            mbar_wait(full_bar(slot), use & 1u);                          // acquires the producers' row scales
-            mbar_wait(done_bar(slot), use & 1u);
+            mbar_wait(done_bar(slot), use & 1u);                          // the tile's MMAs are done (sleeps on ONE arrival)
+            mbar_wait(full_bar(slot), use & 1u);                          // complete by then: acquires the producers' row scales
             tc_fence_after();
             // one accumulator (n_real columns from TMEM column `tcol`) -> n_real floats per row at `cptr`;
             // `release`: this is the last read of the slot's accumulators
@@ -534,9 +539,9 @@ int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void*
     for (int i = 0; i < e.n_n; ++i) p.n_b[e.n_c[i]] = e.n_b[i];
     p.a_vec = e.k_a[0] == 0;
     for (int k = 0; k < 32; ++k) {
-        uint32_t o = 0;
-        for (int i = 0; i < e.n_k && i < 5; ++i) o |= ((uint32_t)(k >> i) & 1u) << e.k_a[i];
-        p.koff_c[k] = o;
+        uint64_t o = 0;
+        for (int i = 0; i < e.n_k && i < 5; ++i) o |= (uint64_t)((k >> i) & 1) << e.k_a[i];
+        p.koff_c[k] = o << 3;                                            // bytes
     }
     p.kblock_off = e.n_k == 6 ? ((int64_t)1 << e.k_a[5]) : 0;
     // row bit j (output position n_n + j) -> A position; merge consecutive bits into runs
