@@ -9,7 +9,8 @@ import os
 
 TNC_MAX_BITS = 40
 TNC_MAX_SLICED = 8
-TNC_ABI_VERSION = 6
+TNC_ABI_VERSION = 7
+TNC_WORKSPACE_TAIL_BYTES = 4352
 TNC_PROFILE_SLOTS = 4
 
 TNC_C64 = 0
@@ -19,7 +20,7 @@ TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
 TNC_EINSUM_OUTER_ROWS = 1
 TNC_EINSUM_OUTER_PAIRS = 2
 TNC_TC_3XTF32, TNC_TC_3XF16, TNC_TC_F16 = 0, 1, 2
-TNC_OPT_TC_PRECISION, TNC_OPT_CUDA_GRAPH = 0, 1
+TNC_OPT_TC_PRECISION, TNC_OPT_CUDA_GRAPH, TNC_OPT_FUSE_AMAX = 0, 1, 2
 TC_PRECISIONS = {"3xtf32": TNC_TC_3XTF32, "3xf16": TNC_TC_3XF16, "f16": TNC_TC_F16}
 
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "UNSUPPORTED", 5: "STATE"}
@@ -77,6 +78,7 @@ SYMBOLS = {
     "tnc_plan_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "tnc_plan_num_ops": (C.c_int64, [C.c_void_p, C.c_int32]),
     "tnc_plan_last_launches": (C.c_int64, [C.c_void_p]),
+    "tnc_plan_num_fused_amax": (C.c_int64, [C.c_void_p, C.c_int32]),
     "tnc_plan_destroy": (None, [C.c_void_p]),
     "tnc_plan_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p]),

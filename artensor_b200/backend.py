@@ -116,6 +116,10 @@ class PlanOptions:
     # launch gaps of its ~100 kernels to matter (n53 m12: 3.3 ms per slice over 140 launches)
     cuda_graph: Optional[bool] = None
     graph_max_flops: float = 5e12
+    # tensor-core operands written by a streaming / GEMM kernel get their largest magnitude (the fp16 operand scale)
+    # reduced by that kernel's epilogue instead of a separate pass over the tensor (TNC_OPT_FUSE_AMAX); results are
+    # bit-identical either way
+    fuse_amax: bool = True
 
     def __post_init__(self):
         if self.tc_precision not in N.TC_PRECISIONS:
@@ -359,12 +363,13 @@ class ContractionPlan:
             del bufs[orig.j]
         base[N.TNC_PHASE_ONCE] = 0
         base[N.TNC_PHASE_SLICE] = arenas[N.TNC_PHASE_ONCE].high
-        self.workspace_bytes = max(arenas[N.TNC_PHASE_ONCE].high + arenas[N.TNC_PHASE_SLICE].high, ALIGN)
+        self.arena_bytes = max(arenas[N.TNC_PHASE_ONCE].high + arenas[N.TNC_PHASE_SLICE].high, ALIGN)
+        # the library keeps its own words (amax words reduced by producing kernels, the slice-id word of graph
+        # replay) in a tail behind the arena: tnc_plan_workspace_bytes
+        self.workspace_bytes = (self.arena_bytes + ALIGN - 1) // ALIGN * ALIGN + N.TNC_WORKSPACE_TAIL_BYTES
         exec_flops = sum(st.flops for st, ph in zip(self.steps, self.step_phase) if ph == N.TNC_PHASE_SLICE)
         self.cuda_graph = (self.n_sliced >= 1 and exec_flops < self.options.graph_max_flops
                            if self.options.cuda_graph is None else bool(self.options.cuda_graph))
-        if self.cuda_graph:
-            self.workspace_bytes += ALIGN           # the library's slice-id word lives in the last 256 bytes
 
         ops = {N.TNC_PHASE_ONCE: [], N.TNC_PHASE_SLICE: []}
         for phase in ops:
@@ -488,6 +493,7 @@ class ContractionPlan:
         try:
             N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_TC_PRECISION, N.TC_PRECISIONS[self.options.tc_precision]))
             N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_CUDA_GRAPH, 1 if self.cuda_graph else 0))
+            N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_FUSE_AMAX, 1 if self.options.fuse_amax else 0))
             for t in self.tables:
                 tid = C.c_int32()
                 N.check(lib.tnc_plan_add_table(handle, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t), C.byref(tid)))
@@ -502,7 +508,8 @@ class ContractionPlan:
                         N.check(lib.tnc_plan_add_permute(handle, phase, C.byref(rec)))
                     elif kind == "accum":
                         N.check(lib.tnc_plan_add_accum(handle, phase, C.byref(rec)))
-            N.check(lib.tnc_plan_finalize(handle, self.workspace_bytes))
+            N.check(lib.tnc_plan_finalize(handle, self.arena_bytes))
+            assert lib.tnc_plan_workspace_bytes(handle) == self.workspace_bytes
         except Exception:
             lib.tnc_plan_destroy(handle)
             self._handle = None
@@ -577,6 +584,12 @@ class ContractionPlan:
                                            workspace.data_ptr(), workspace.numel() * workspace.element_size(),
                                            stream_ptr, a0, a1))
         return list(a0)[:n0 * SL], list(a1)[:n1 * SL]
+
+    def fused_amax_operands(self, phase=None):
+        """Tensor-core operands (of `phase`; default: of both phases) whose amax the producing kernel reduces
+        instead of a separate pass over the tensor."""
+        phases = (N.TNC_PHASE_ONCE, N.TNC_PHASE_SLICE) if phase is None else (phase,)
+        return sum(int(self._lib.tnc_plan_num_fused_amax(self._handle, ph)) for ph in phases)
 
     @property
     def last_launches(self):

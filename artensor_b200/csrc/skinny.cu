@@ -71,6 +71,7 @@ struct SkinnyParams {
                                    // constant bank, so with k unrolled the offset is an instruction operand (the shared-
                                    // memory table cost an LDS + a 64-bit IMAD per 8-byte load: 6 instructions per load)
     int64_t kblock_off;            // A offset of the second k-block (K = 64)
+    uint32_t* amax_out;            // not null: the largest |component| written goes here (atomicMax of float bits)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
         const int n_real = 2 << p.nb;                                     // floats per output row
         int slot = 0;
         uint32_t use = 0;
+        float am = 0.f;                                                   // largest |component| this thread wrote (amax_out)
         for (int64_t j = 0;; ++j, ++slot) {
             const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
             if (tile >= p.tiles) break;
@@ -386,6 +388,10 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                             if constexpr (KB == 2) y = fmaf(__uint_as_float(w[x]), s1, y);
                             o[x] = fmaf(y, p.debias, y);
                         }
+                        if (p.amax_out) {
+#pragma unroll
+                            for (int x = 0; x < 32; ++x) amax_fold(am, o[x]);
+                        }
                         store_rows_coalesced<8>(stage, o, cptr + c0, n_real, lane);
                     }
                 } else {
@@ -409,6 +415,10 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                         if constexpr (KB == 2) y = fmaf(__uint_as_float(w[x]), s1, y);
                         o[x] = fmaf(y, p.debias, y);
                     }
+                    if (p.amax_out) {
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) amax_fold(am, o[x]);
+                    }
                     if (n_real == 16) store_rows_coalesced<4>(stage, o, cptr, n_real, lane);
                     else if (n_real == 8) store_rows_coalesced<2>(stage, o, cptr, n_real, lane);
                     else store_rows_coalesced<1>(stage, o, cptr, n_real, lane);
@@ -431,6 +441,7 @@ __global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_kernel(const SkinnyP
                 }
             }
         }
+        if (p.amax_out) amax_commit(p.amax_out, am);
     }
     tc_fence_before();
     __syncthreads();
@@ -513,12 +524,13 @@ bool skinny_supported(const tnc_einsum& e, int dtype, int precision) {
 }
 
 int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
-                  const int32_t* dev_rows_b, cudaStream_t s) {
+                  const int32_t* dev_rows_b, cudaStream_t s, uint32_t* amax_out) {
     if (!skinny_supported(e, TNC_C64, precision)) {
         set_error("skinny einsum: unsupported shape, rows or output layout (m=%d k=%d n=%d h=%d)", e.n_m, e.n_k, e.n_n, e.n_h);
         return TNC_ERR_UNSUPPORTED;
     }
     SkinnyParams p{};
+    p.amax_out = amax_out;
     p.a = (const float2*)a;
     p.b = (const float2*)b;
     p.c = (float2*)c;

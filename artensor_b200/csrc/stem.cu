@@ -43,6 +43,7 @@ struct StemParams {
     uint32_t run_mask[TNC_MAX_BITS];
     int8_t run_src[TNC_MAX_BITS], run_dst[TNC_MAX_BITS];
     int8_t k_a[TNC_MAX_BITS], k_b[TNC_MAX_BITS], n_b[TNC_MAX_BITS];
+    uint32_t* amax_out;            // not null: the largest |component| written goes here (atomicMax of float bits)
 };
 
 __device__ __forceinline__ void cfma(float2& acc, const float2 a, const float2 b) {
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
     const int64_t tiles_per_batch = (rows + kStemThreads - 1) / kStemThreads;
     const int64_t tiles = tiles_per_batch * p.nbatch;
     int cur_batch = -1;
+    float am = 0.f;                                      // largest |component| this thread wrote (amax_out)
     // Each CTA walks a contiguous range of tiles: with many small batches (outer steps: thousands of
     // row pairs of a few hundred tiles each) a strided walk would change batch -- reload B, two
     // barriers -- on every tile.
@@ -199,6 +201,13 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
                     else row_fma<NCH>(accR, accI, av[j], BfR + bo, BfI + bo);
                 }
             }
+            if (p.amax_out) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    amax_fold(am, acc[i].x);
+                    amax_fold(am, acc[i].y);
+                }
+            }
             if constexpr (NCH == 1) {
                 cp[n0] = acc[0];
             } else {
@@ -215,6 +224,7 @@ __global__ void __launch_bounds__(kStemThreads, (NCH * KCH <= 32 && NCH <= 8 ? 4
         }
         }
     }
+    if (p.amax_out) amax_commit(p.amax_out, am);
 }
 
 // -------------------------------------------------------------------------------------
@@ -250,6 +260,7 @@ struct BulkParams {
     int8_t run_src[TNC_MAX_BITS], run_dst[TNC_MAX_BITS];
     int8_t row_lo[8];              // A position (< T) of the tile's row bit j
     int8_t k_a[TNC_MAX_BITS], k_b[TNC_MAX_BITS], n_b[TNC_MAX_BITS];
+    uint32_t* amax_out;            // as in StemParams
 };
 
 constexpr int kBulkConsumers = 256;
@@ -359,6 +370,7 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
     for (int j = 0; j < 8; ++j) roff |= (((uint32_t)tid >> j) & 1u) << p.row_lo[j];
     int64_t cur_seg = -1;
     int32_t b0 = 0, b1 = 0;
+    float am = 0.f;                                      // largest |component| this thread wrote (amax_out)
     for (int64_t it = i_begin; it < i_end; ++it) {
         const int64_t seg = it >> tile_bits, tile = it & tile_mask;
         if (seg != cur_seg) {
@@ -409,6 +421,13 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
                     if constexpr (NCH == 1) cfma(acc[0], av[k], make_float2(BfR[bo], BfI[bo]));
                     else row_fma<NCH>(accR, accI, av[k], BfR + bo, BfI + bo);
                 }
+                if (p.amax_out) {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) {
+                        amax_fold(am, acc[i].x);
+                        amax_fold(am, acc[i].y);
+                    }
+                }
                 if constexpr (NCH == 1) {
                     cp[n0] = acc[0];
                 } else {
@@ -419,6 +438,7 @@ __global__ void __launch_bounds__(kBulkThreads, PER_SM) stem_bulk_kernel(const B
             }
         }
     }
+    if (p.amax_out) amax_commit(p.amax_out, am);
 }
 
 int sm_count() {
@@ -496,8 +516,9 @@ bool bulk_applies(const tnc_einsum& e) {
 }
 
 int launch_stem_bulk(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
-                     const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s) {
+                     const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, uint32_t* amax_out, cudaStream_t s) {
     BulkParams p{};
+    p.amax_out = amax_out;
     p.a = (const float2*)a;
     p.b = (const float2*)b;
     p.c = (float2*)c;
@@ -593,17 +614,18 @@ bool stem_supported(const tnc_einsum& e, int dtype) {
 }
 
 int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
-                const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s) {
+                const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s, uint32_t* amax_out) {
     if (!stem_supported(e, TNC_C64)) {
         set_error("stem einsum: unsupported shape or output layout (k=%d n=%d h=%d)", e.n_k, e.n_n, e.n_h);
         return TNC_ERR_UNSUPPORTED;
     }
     static const bool no_bulk = knob("TNC_STEM_NO_BULK") != nullptr;      // measurement aid
     if (!no_bulk && bulk_applies(e)) {
-        const int rc = launch_stem_bulk(e, a, b, c, dev_rows_a, dev_rows_b, dev_seg_begin, n_seg, s);
+        const int rc = launch_stem_bulk(e, a, b, c, dev_rows_a, dev_rows_b, dev_seg_begin, n_seg, amax_out, s);
         if (rc != TNC_ERR_UNSUPPORTED) return rc;
     }
     StemParams p{};
+    p.amax_out = amax_out;
     p.a = (const float2*)a;
     p.b = (const float2*)b;
     p.c = (float2*)c;

@@ -216,5 +216,16 @@ __device__ __forceinline__ void store_rows_coalesced(uint32_t stage_smem, const 
     __syncwarp();
 }
 
+// Largest output magnitude as a by-product of a producing kernel (the consumer is a tensor-core step that scales
+// its fp16 operands by it: no separate pass over the tensor).  Non-negative floats order like unsigned integers.
+__device__ __forceinline__ void amax_fold(float& m, const float x) {
+    m = fmaxf(m, fabsf(x));
+}
+// whole warp, converged
+__device__ __forceinline__ void amax_commit(uint32_t* word, const float m) {
+    const uint32_t bits = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if (bits && (threadIdx.x & 31) == 0) atomicMax(word, bits);
+}
+
 }  // namespace
 }  // namespace tnc

@@ -778,7 +778,8 @@ struct GemmArgs {
     const int32_t* pair_rows;     // OUTER_PAIRS: C row block of the pair (ra * outer_rj + rb); nullptr: the pair index itself
     int32_t sync_every;       // k-blocks between grid-wide lockstep barriers (0 = none)
     uint32_t* sync_counter;   // zeroed before the launch
-    const uint32_t* amax;     // fp16 precisions: amax words of A and B (the epilogue undoes their scaling)
+    const uint32_t *amax_a, *amax_b;   // fp16 precisions: amax words of A and B (the epilogue undoes their scaling)
+    uint32_t* amax_out;       // not null: the largest |component| of C goes here (atomicMax of float bits), see tc_gemm_run
     float out_scale;          // extra factor of the fp16 epilogue: 4 for the 3M panels (scaled one bit lower), else 1
 };
 
@@ -891,8 +892,10 @@ __device__ __forceinline__ void drain_chunk(uint32_t taddr, float* acc) {
 template <int CPT, bool F16>
 __device__ __forceinline__ void store_tile_rows(const GemmArgs& g, uint32_t stage, int batch, int row0, int col0, float* acc,
                                                 int lane) {
+    float am = 0.f;            // g.amax_out: largest |component| of this warp's part of the tile, committed per tile (a
+                               // running maximum would stay live across the chunk loop of the next tile)
     float sab = 1.f;
-    if constexpr (F16) sab = f16_inv_scale(g.amax[0]) * f16_inv_scale(g.amax[1]) * g.out_scale;
+    if constexpr (F16) sab = f16_inv_scale(*g.amax_a) * f16_inv_scale(*g.amax_b) * g.out_scale;
     // Output address of GEMM element (row, col).  Folded outer-rows steps (n_inner != 0): the GEMM
     // columns are (row of B, n), and C wants the row pair outermost, so every n_inner columns
     // belong to another row block of C; n_inner >= 32, so a 32-column slab never straddles two.
@@ -910,6 +913,10 @@ __device__ __forceinline__ void store_tile_rows(const GemmArgs& g, uint32_t stag
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[c + j] *= sab;
                 }
+                if (g.amax_out) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) amax_fold(am, acc[c + j]);
+                }
                 store_rows_coalesced<8>(stage, acc + c, cptr(row0, col0 + c), g.ldc, lane);
             }
         } else {
@@ -917,19 +924,28 @@ __device__ __forceinline__ void store_tile_rows(const GemmArgs& g, uint32_t stag
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) acc[j] *= sab;
             }
+            if (g.amax_out) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) amax_fold(am, acc[j]);
+            }
             store_rows_coalesced<CPT / 4>(stage, acc, cptr(row0, col0), g.ldc, lane);
         }
+        if (g.amax_out) amax_commit(g.amax_out, am);
         return;
     }
     const int row = row0 + lane;
-    if (row >= g.M) return;
+    if (row < g.M) {
 #pragma unroll
-    for (int j = 0; j < CPT; j += 4)
-        if (col0 + j < g.N) {
-            float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            if constexpr (F16) o = make_float4(o.x * sab, o.y * sab, o.z * sab, o.w * sab);
-            *(float4*)cptr(row, col0 + j) = o;
-        }
+        for (int j = 0; j < CPT; j += 4)
+            if (col0 + j < g.N) {
+                float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                if constexpr (F16) o = make_float4(o.x * sab, o.y * sab, o.z * sab, o.w * sab);
+                if (g.amax_out) amax_fold(am, o.x), amax_fold(am, o.y), amax_fold(am, o.z), amax_fold(am, o.w);
+                *(float4*)cptr(row, col0 + j) = o;
+            }
+    }
+    __syncwarp();
+    if (g.amax_out) amax_commit(g.amax_out, am);
 }
 
 template <int BN, int PREC>
@@ -1541,10 +1557,11 @@ gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             // interleaved floats (16 complex columns) at a time through the warp's staging buffer, straight
             // from the planar accumulators (an interleaved copy of all 128 made the chunk loop spill)
             {
-                const float sab = f16_inv_scale(g.amax[0]) * f16_inv_scale(g.amax[1]) * g.out_scale;
+                const float sab = f16_inv_scale(*g.amax_a) * f16_inv_scale(*g.amax_b) * g.out_scale;
                 const uint32_t stage = base + C::STAGES * C::STAGE + 256 + (uint32_t)(warp - 2) * 4096u;
                 const int row0 = (2 * t.m_tile + (int)rank) * BM + q * 32, col0 = t.n0 + half * CPT;
                 float* crow = g.c + c_row(g, t.batch, row0) * g.ldc + col0;
+                float am = 0.f;                // g.amax_out, committed per tile as in store_tile_rows
 #pragma unroll
                 for (int c = 0; c < CPT; c += 32) {
                     float o[32];
@@ -1555,8 +1572,13 @@ gemm3m_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         o[4 * j + 2] = re[c / 4 + j].y * sab;
                         o[4 * j + 3] = im[c / 4 + j].y * sab;
                     }
+                    if (g.amax_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) amax_fold(am, o[j]);
+                    }
                     store_rows_coalesced<8>(stage, o, crow + c, g.ldc, lane);
                 }
+                if (g.amax_out) amax_commit(g.amax_out, am);
             }
         }
     }
@@ -1962,23 +1984,26 @@ int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t*
     return TNC_OK;
 }
 
-int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* ctx, int* launches) {
+int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* ctx, int* launches, const TcAmaxWords& ext) {
     const bool f16 = op->precision != TNC_TC_3XTF32;
     const bool lo = op->precision != TNC_TC_F16;
     const int elem = f16 ? 2 : 4;
     int n_launch = 3;
     uint32_t* words = (uint32_t*)(ws + op->words_off);
     PackDesc pa = op->pa, pb = op->pb;                  // the op itself stays read-only: a run only fills local copies
-    pa.amax = f16 ? words : nullptr;
-    pb.amax = f16 ? words + 1 : nullptr;
+    // amax words: the step's own (scratch) unless the operand's producer already reduced one elsewhere
+    const uint32_t* amax_a = ext.a >= 0 ? (const uint32_t*)(ws + ext.a) : words;
+    const uint32_t* amax_b = ext.b >= 0 ? (const uint32_t*)(ws + ext.b) : words + 1;
+    pa.amax = f16 ? amax_a : nullptr;
+    pb.amax = f16 ? amax_b : nullptr;
     if (f16 || op->args.sync_every) TNC_CUDA(cudaMemsetAsync(words, 0, 256, s));
-    if (f16) {
+    if (f16 && (ext.a < 0 || ext.b < 0)) {
         // one launch finds the largest magnitude of both operands (whole source tensors: an upper
-        // bound of the gathered rows is all the scaling needs)
+        // bound of the gathered rows is all the scaling needs); an operand whose word is external gets no blocks
         const int64_t n4_a = op->a_elems / 2, n4_b = op->b_elems / 2;       // float4 = two amplitudes; ranks >= 2
         const int64_t cap = (int64_t)sm_count() * 8;
-        const int ga = (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_a + 511) / 512));
-        const int gb = (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_b + 511) / 512));
+        const int ga = ext.a >= 0 ? 0 : (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_a + 511) / 512));
+        const int gb = ext.b >= 0 ? 0 : (int)std::max<int64_t>(1, std::min<int64_t>(cap, (n4_b + 511) / 512));
         amax_kernel<<<ga + gb, 256, 0, s>>>((const float4*)(ws + op->a_off), n4_a, (const float4*)(ws + op->b_off), n4_b, ga,
                                             words);
         TNC_CUDA(cudaGetLastError());
@@ -2040,7 +2065,9 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     }
     GemmArgs g = op->args;
     g.c = (float*)(ws + op->c_off);
-    g.amax = f16 ? words : nullptr;
+    g.amax_a = f16 ? amax_a : nullptr;
+    g.amax_b = f16 ? amax_b : nullptr;
+    g.amax_out = ext.out >= 0 ? (uint32_t*)(ws + ext.out) : nullptr;
     g.sync_counter = words + 32;
     // persistent grid: one CTA per SM (the shared-memory footprint allows no more), every CTA
     // walks tiles c, c + grid, ...
@@ -2068,6 +2095,10 @@ int tc_gemm_run(TcGemmOp* op, char* ws, cudaStream_t s, LaunchHook hook, void* c
     if (hook) hook(ctx);
     if (launches) *launches = n_launch;
     return TNC_OK;
+}
+
+bool tc_gemm_emits_amax(const TcGemmOp* op) {
+    return op != nullptr;      // every GEMM kernel's epilogue can
 }
 
 void tc_gemm_destroy(TcGemmOp* op) {

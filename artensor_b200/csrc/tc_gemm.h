@@ -1,7 +1,8 @@
 // Tensor-core (tcgen05) lowering of one einsum step: two pack launches (bit-permutation of
 // each operand into a K-major panel, split into hi/lo parts; the right operand is also
 // expanded to its real 2N x 2K form) followed by one TMA-fed tcgen05 GEMM.  The fp16
-// precisions add one amax launch in front (power-of-two operand scaling).
+// precisions add one amax launch in front (power-of-two operand scaling) unless the kernels that
+// produced the operands already reduced it (TcAmaxWords).
 #pragma once
 #include "tnc_internal.h"
 
@@ -22,7 +23,16 @@ int64_t tc_gemm_scratch_bytes(const tnc_einsum& e, int dtype);
 int tc_gemm_create(const tnc_einsum& e, int dtype, int precision, const int32_t* dev_rows_a, const int32_t* dev_rows_b,
                    const int32_t* dev_pair_rows,
                    TcGemmOp** out);
-int tc_gemm_run(TcGemmOp* op, char* workspace, cudaStream_t s, LaunchHook hook, void* ctx, int* launches);
+// Workspace byte offsets of amax words kept OUTSIDE the step's scratch (-1: none).  `a` / `b`: the operand's
+// largest magnitude was already reduced there by the kernel that produced the operand, the step skips its own
+// pass over it; `out`: the GEMM epilogue reduces the largest magnitude of C there for the step that consumes C.
+struct TcAmaxWords {
+    int64_t a = -1, b = -1, out = -1;
+};
+int tc_gemm_run(TcGemmOp* op, char* workspace, cudaStream_t s, LaunchHook hook, void* ctx, int* launches,
+                const TcAmaxWords& ext = TcAmaxWords());
+// whether the step's GEMM kernel can reduce the amax of its output (TcAmaxWords::out)
+bool tc_gemm_emits_amax(const TcGemmOp* op);
 void tc_gemm_destroy(TcGemmOp* op);
 
 // ---------------------------------------------------------------- pack (bit-permutation) kernel

@@ -47,11 +47,17 @@ struct Op {
     int chain_len = 0;                    // > 1: head of a run of tiny generic steps executed by one launch; -1: member
     int64_t chain_off = -1;               // the run's ChainStep records in the device blob
     std::shared_ptr<TcGemmOp> tc;         // tensor-core lowering, when algo == TNC_ALGO_TC
+    // amax words in the workspace tail (byte offsets, -1: none).  a / b (tensor-core steps): the operand's producer
+    // already reduced the operand's largest magnitude there; out (any einsum kernel that can): reduce the largest
+    // magnitude of this step's output there, for the tensor-core step that consumes it
+    TcAmaxWords amax;
 };
 
 }  // namespace tnc
 
 using namespace tnc;
+
+constexpr int kAmaxWordsPerPhase = 512;      // 2 phases x 512 x 4 bytes = the first 4096 bytes of the tail
 
 struct tnc_plan {
     int dtype = TNC_C64;
@@ -64,11 +70,14 @@ struct tnc_plan {
     std::vector<LeafDev> leaves;
     int64_t leaves_off = 0;
     char* dev_blob = nullptr;
-    int64_t workspace_bytes = 0;
+    int64_t workspace_bytes = 0;          // arena + the library's tail (TNC_WORKSPACE_TAIL_BYTES)
+    int n_amax_words[2] = {0, 0};         // producer-reduced amax words of each phase (kAmaxWordsPerPhase slots each)
+    int64_t amax_words_off(int phase) const { return workspace_bytes - TNC_WORKSPACE_TAIL_BYTES + (int64_t)phase * kAmaxWordsPerPhase * 4; }
     std::atomic<int64_t> last_launches{0};   // written once at the end of an execute / profile call
     // CUDA-graph replay of the slice phase (TNC_OPT_CUDA_GRAPH): one instantiated graph per
     // (workspace, leaf blob, accumulator) the plan has been executed with
     bool use_graph = false;
+    bool fuse_amax = true;                // TNC_OPT_FUSE_AMAX
     std::atomic<bool> graph_failed{false};
     std::mutex graph_mu;
     struct GraphKey {
@@ -148,6 +157,13 @@ int tnc_plan_set_option(tnc_plan* plan, int32_t option, int64_t value) {
                 return TNC_ERR_INVALID;
             }
             plan->use_graph = value != 0;
+            return TNC_OK;
+        case TNC_OPT_FUSE_AMAX:
+            if (value != 0 && value != 1) {
+                set_error("set_option: TNC_OPT_FUSE_AMAX takes 0 or 1, got %lld", (long long)value);
+                return TNC_ERR_INVALID;
+            }
+            plan->fuse_amax = value != 0;
             return TNC_OK;
     }
     set_error("set_option: unknown option %d", option);
@@ -363,13 +379,15 @@ int tnc_plan_add_accum(tnc_plan* plan, int32_t phase, const tnc_accum* a) {
     return TNC_OK;
 }
 
-int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
-    if (!plan || plan->finalized || workspace_bytes < 0) {
+int tnc_plan_finalize(tnc_plan* plan, int64_t arena_bytes) {
+    if (!plan || plan->finalized || arena_bytes < 0) {
         set_error("finalize: bad arguments or already finalized");
         return plan && plan->finalized ? TNC_ERR_STATE : TNC_ERR_INVALID;
     }
-    // every tensor must fit the declared arena (graph replay keeps its slice-id word in the last 256 bytes)
-    const int64_t usable = workspace_bytes - (plan->use_graph ? 256 : 0);
+    // every tensor must fit the declared arena; the library's own words (producer-reduced amax words, the
+    // slice-id word of graph replay) live in a tail behind it
+    const int64_t usable = arena_bytes;
+    const int64_t workspace_bytes = ((arena_bytes + 255) & ~(int64_t)255) + TNC_WORKSPACE_TAIL_BYTES;
     auto fits = [&](const tnc_tensor& t) { return t.offset + tensor_bytes(plan, t) <= usable; };
     for (int ph = 0; ph < 2; ++ph)
         for (auto& op : plan->ops[ph]) {
@@ -379,12 +397,12 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
             if (op.kind == OP_ACCUM) ok = fits(op.a.src);
             if (!ok) {
                 set_error("finalize: an operation addresses memory beyond the declared %lld-byte arena",
-                          (long long)workspace_bytes);
+                          (long long)arena_bytes);
                 return TNC_ERR_NOMEM;
             }
         }
     for (auto& L : plan->leaves)
-        if (L.dst_offset + (((int64_t)L.dst_rows << L.dst_rank) * plan->elem_bytes()) > workspace_bytes) {
+        if (L.dst_offset + (((int64_t)L.dst_rows << L.dst_rank) * plan->elem_bytes()) > usable) {
             set_error("finalize: a leaf does not fit the declared arena");
             return TNC_ERR_NOMEM;
         }
@@ -483,7 +501,7 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
             if (op.kind != OP_EINSUM || op.e.algo != TNC_ALGO_TC) continue;
             const int32_t* ra = op.e.rows_a >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[op.e.rows_a]) : nullptr;
             const int32_t* rb = op.e.rows_b >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[op.e.rows_b]) : nullptr;
-            if (op.e.scratch_offset < 0 || op.e.scratch_offset + op.e.scratch_bytes > workspace_bytes) {
+            if (op.e.scratch_offset < 0 || op.e.scratch_offset + op.e.scratch_bytes > usable) {
                 set_error("finalize: a tensor-core scratch region lies outside the declared arena");
                 return TNC_ERR_NOMEM;
             }
@@ -494,7 +512,45 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes) {
             op.tc.reset(tc, tc_gemm_destroy);
         }
     plan->workspace_bytes = workspace_bytes;
+    // Operand scales without a pass over the operand: when the tensor a tensor-core step (fp16 precisions) reads was
+    // written by a streaming or GEMM kernel of the same phase, that kernel reduces the tensor's largest magnitude
+    // into a word of the workspace tail as it stores it, and the step's amax launch skips the operand.
+    if (plan->tc_precision != TNC_TC_3XTF32 && plan->fuse_amax)
+        for (int ph = 0; ph < 2; ++ph) {
+            auto& ops = plan->ops[ph];
+            int n_words = 0;
+            for (size_t i = 0; i < ops.size(); ++i) {
+                if (!ops[i].tc) continue;
+                for (int which = 0; which < 2; ++which) {
+                    const tnc_tensor& x = which ? ops[i].e.b : ops[i].e.a;
+                    // the latest earlier operation of the phase that wrote at this offset is the producer (the
+                    // buffer is live from there to here); leaves and results of the other phase find none
+                    for (size_t j = i; j-- > 0;) {
+                        Op& p = ops[j];
+                        if (p.kind == OP_PERMUTE && p.p.dst.offset == x.offset) break;
+                        if (p.kind != OP_EINSUM || p.e.c.offset != x.offset) continue;
+                        const bool same = p.e.c.rank == x.rank && p.e.c.rows == x.rows;
+                        const bool emits = p.chain_len == 0 && (p.e.algo == TNC_ALGO_STEM || p.e.algo == TNC_ALGO_SKINNY ||
+                                                                (p.tc && tc_gemm_emits_amax(p.tc.get())));
+                        if (same && emits && p.amax.out < 0 && n_words < kAmaxWordsPerPhase) {
+                            const int64_t off = plan->amax_words_off(ph) + 4 * (int64_t)n_words++;
+                            p.amax.out = off;
+                            (which ? ops[i].amax.b : ops[i].amax.a) = off;
+                        }
+                        break;
+                    }
+                }
+            }
+            plan->n_amax_words[ph] = n_words;
+        }
     plan->finalized = true;
+    return TNC_OK;
+}
+
+// zeroes the producer-reduced amax words of a phase (before the phase's first operation, once per pass)
+static int clear_amax_words(const tnc_plan* plan, int phase, char* ws, cudaStream_t st) {
+    if (plan->n_amax_words[phase] == 0) return TNC_OK;
+    TNC_CUDA(cudaMemsetAsync(ws + plan->amax_words_off(phase), 0, (size_t)plan->n_amax_words[phase] * 4, st));
     return TNC_OK;
 }
 
@@ -506,6 +562,11 @@ int64_t tnc_plan_num_ops(const tnc_plan* plan, int32_t phase) {
 }
 
 int64_t tnc_plan_last_launches(const tnc_plan* plan) { return plan ? plan->last_launches.load() : -1; }
+
+int64_t tnc_plan_num_fused_amax(const tnc_plan* plan, int32_t phase) {
+    if (!plan || !plan->finalized || !phase_ok(phase)) return -1;
+    return plan->n_amax_words[phase];
+}
 
 // NVTX range per operation ("tc m15 n13 k15 rows1", "skinny ...", "chain x13", "leaves", "accum"), only
 // with TNC_NVTX=1: lets ncu / nsys filter and group the launches by step class
@@ -550,7 +611,7 @@ static int run_op(const tnc_plan* plan, const Op& op, const void* leaf_blob, uin
             }
             if (op.tc) {
                 int launches = 0;
-                int rc = tc_gemm_run(op.tc.get(), ws, st, hook, hook_ctx, &launches);
+                int rc = tc_gemm_run(op.tc.get(), ws, st, hook, hook_ctx, &launches, op.amax);
                 *n_launches += launches;
                 return rc;
             }
@@ -558,10 +619,12 @@ static int run_op(const tnc_plan* plan, const Op& op, const void* leaf_blob, uin
                 const int32_t* ra = e.rows_a >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_a]) : nullptr;
                 const int32_t* rb = e.rows_b >= 0 ? (const int32_t*)(plan->dev_blob + plan->table_off[e.rows_b]) : nullptr;
                 *n_launches += 1;
+                uint32_t* amax_out = op.amax.out >= 0 ? (uint32_t*)(ws + op.amax.out) : nullptr;
                 if (e.algo == TNC_ALGO_SKINNY)
-                    return launch_skinny(e, plan->tc_precision, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st);
+                    return launch_skinny(e, plan->tc_precision, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, st,
+                                         amax_out);
                 const int32_t* seg = op.seg_off >= 0 ? (const int32_t*)(plan->dev_blob + op.seg_off) : nullptr;
-                return launch_stem(e, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, seg, op.n_seg, st);
+                return launch_stem(e, ws + e.a.offset, ws + e.b.offset, ws + e.c.offset, ra, rb, seg, op.n_seg, st, amax_out);
             }
             SimtEinsumParams p{};
             p.a = ws + e.a.offset;
@@ -664,6 +727,7 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
         plan->last_launches = 0;
         return TNC_OK;
     }
+    if (int rc = clear_amax_words(plan, TNC_PHASE_ONCE, ws, st)) return rc;
     for (auto& op : plan->ops[TNC_PHASE_ONCE]) {
         int rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, st, &launches);
         if (rc != TNC_OK) return rc;
@@ -693,6 +757,8 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
             int rc = TNC_OK;
             if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
                 cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                rc = clear_amax_words(plan, TNC_PHASE_SLICE, ws, cap);
+                if (rc == TNC_OK)
                 for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
                     rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, cap, &per_replay, nullptr, nullptr, word);
                     if (rc != TNC_OK) break;
@@ -727,11 +793,13 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
             }
         }
     }
-    for (; s < slice_end; ++s)
+    for (; s < slice_end; ++s) {
+        if (int rc = clear_amax_words(plan, TNC_PHASE_SLICE, ws, st)) return rc;
         for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
             int rc = run_op(plan, op, leaf_blob, s, accum_out, ws, st, &launches);
             if (rc != TNC_OK) return rc;
         }
+    }
     plan->last_launches = launches;
     return TNC_OK;
 }
@@ -771,7 +839,7 @@ int tnc_plan_profile(tnc_plan* plan, const void* leaf_blob, uint64_t slice_id, v
         ProfileCtx ctx;
         ctx.st = st;
         std::vector<size_t> first(n + 1, 0);      // index of the event that opens operation i
-        int rc = TNC_OK;
+        int rc = clear_amax_words(plan, ph, ws, st);
         ctx.mark();
         for (size_t i = 0; i < n && rc == TNC_OK; ++i) {
             first[i] = ctx.events.size() - 1;

@@ -86,14 +86,17 @@ bool stem_supported(const tnc_einsum& e, int dtype);
 // `dev_seg_begin` (n_seg + 1 batch indices, device) splits the batches into runs that share their
 // row of A (built by tnc_plan_finalize from the A-row table); nullptr: one run per batch, or a
 // single run when A has no rows.
+// `amax_out` (device word, zeroed by the caller) != nullptr: the kernel also leaves the bits of the largest
+// |component| it wrote there -- the operand scale of a consuming tensor-core step, for free.
 int launch_stem(const tnc_einsum& e, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
-                const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s);
+                const int32_t* dev_rows_b, const int32_t* dev_seg_begin, int n_seg, cudaStream_t s,
+                uint32_t* amax_out = nullptr);
 
 // ---------------------------------------------------------------- streaming tensor-core ("skinny") einsum
 // Same operand shapes and output layout as the streaming kernel, multiplied on tcgen05 (skinny.cu).
 bool skinny_supported(const tnc_einsum& e, int dtype, int precision);
 int launch_skinny(const tnc_einsum& e, int precision, const void* a, const void* b, void* c, const int32_t* dev_rows_a,
-                  const int32_t* dev_rows_b, cudaStream_t s);
+                  const int32_t* dev_rows_b, cudaStream_t s, uint32_t* amax_out = nullptr);
 
 // ---------------------------------------------------------------- leaves
 struct LeafDev {

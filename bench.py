@@ -77,6 +77,7 @@ def parse_args():
     ap.add_argument("--tc-precision", default=None, choices=["3xtf32", "3xf16", "f16"],
                     help="operand precision of the tensor-core steps (default: the library default, 3xf16)")
     ap.add_argument("--no-half", action="store_true", help="skip the complex-half mode measurement")
+    ap.add_argument("--no-fuse-amax", action="store_true", help="A/B aid: keep the separate amax pass of every tensor-core step")
     return ap.parse_args()
 
 
@@ -388,6 +389,8 @@ def main():
         opt_kw["tc_min_flops"] = args.tc_min_flops
     if args.tc_precision is not None:
         opt_kw["tc_precision"] = args.tc_precision
+    if args.no_fuse_amax:
+        opt_kw["fuse_amax"] = False
     sim.plan_options = PlanOptions(**opt_kw)
     precision = sim.plan_options.tc_precision
     plan = sim.plan()
@@ -680,7 +683,7 @@ def main():
             "useful_tflops": work["ref_flops_per_slice"] * value / 1e12,
             "flops_per_slice": work["ref_flops_per_slice"], "bytes_per_slice": work["ref_bytes_per_slice"],
             "extrapolated_full_task_seconds": (2.0 ** plan.n_sliced) / value,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "e2e": e2e, "gpu_launches": launches, "fused_amax_operands": plan.fused_amax_operands(), "clocks": clocks, "roofline": roofline,
             "slice_roofline": slice_roofline, "breakdown": breakdown,
             "cpu_baseline": cpu, "half_mode": half,
         }

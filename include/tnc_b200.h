@@ -31,9 +31,12 @@
 extern "C" {
 #endif
 
-#define TNC_ABI_VERSION 6
+#define TNC_ABI_VERSION 7
 #define TNC_MAX_BITS 40          /* max bit modes per group / per tensor */
 #define TNC_MAX_SLICED 8         /* max sliced bonds on one leaf */
+#define TNC_WORKSPACE_TAIL_BYTES 4352   /* the library's own words behind the arena: tnc_plan_workspace_bytes() =
+                                           arena rounded up to 256 + this (amax words reduced by producing kernels,
+                                           the slice-id word of CUDA-graph replay) */
 
 typedef enum tnc_status {
     TNC_OK = 0,
@@ -69,11 +72,15 @@ typedef enum tnc_tc_precision {
 
 typedef enum tnc_option {
     TNC_OPT_TC_PRECISION = 0,    /* value: tnc_tc_precision */
-    TNC_OPT_CUDA_GRAPH = 1       /* value 1: tnc_plan_execute replays the slice phase as ONE CUDA graph per slice
+    TNC_OPT_CUDA_GRAPH = 1,      /* value 1: tnc_plan_execute replays the slice phase as ONE CUDA graph per slice
                                     (captured on first use per workspace / leaf blob / accumulator) instead of
                                     ~100 stream launches -- for slices of a few ms, where launch gaps are a
-                                    measurable share.  The last 256 bytes of the workspace then belong to the
-                                    library (the slice-id word): declare 256 bytes more at finalize. */
+                                    measurable share.  The slice-id word lives in the workspace tail. */
+    TNC_OPT_FUSE_AMAX = 2        /* value 1 (default): when the operand of a tensor-core step (fp16 precisions) was
+                                    written by a streaming or GEMM kernel of the same phase, that kernel reduces the
+                                    operand's largest magnitude (its power-of-two scale) into a word of the workspace
+                                    tail while it stores the tensor, and the step's own amax pass skips the operand.
+                                    Results are bit-identical either way; 0 keeps the separate pass (A/B aid). */
 } tnc_option;
 
 typedef enum tnc_algo {
@@ -170,12 +177,16 @@ int tnc_plan_add_leaves(tnc_plan* plan, int32_t phase, const tnc_leaf* leaves, i
 int tnc_plan_add_einsum(tnc_plan* plan, int32_t phase, const tnc_einsum* op);
 int tnc_plan_add_permute(tnc_plan* plan, int32_t phase, const tnc_permute* op);
 int tnc_plan_add_accum(tnc_plan* plan, int32_t phase, const tnc_accum* op);
-/* Declares the arena size the operations were laid out for and uploads tables. */
-int tnc_plan_finalize(tnc_plan* plan, int64_t workspace_bytes);
+/* Declares the arena size the operations were laid out for (every tensor and scratch region must fit) and
+ * uploads tables.  The workspace a caller passes to execute is larger: tnc_plan_workspace_bytes() = the arena
+ * rounded up to 256 bytes + TNC_WORKSPACE_TAIL_BYTES. */
+int tnc_plan_finalize(tnc_plan* plan, int64_t arena_bytes);
 int64_t tnc_plan_workspace_bytes(const tnc_plan* plan);
 int64_t tnc_plan_num_ops(const tnc_plan* plan, int32_t phase);
 /* kernels launched by the last tnc_plan_execute on this plan */
 int64_t tnc_plan_last_launches(const tnc_plan* plan);
+/* tensor-core operands of `phase` whose amax is reduced by the kernel that produces them (TNC_OPT_FUSE_AMAX) */
+int64_t tnc_plan_num_fused_amax(const tnc_plan* plan, int32_t phase);
 void tnc_plan_destroy(tnc_plan* plan);
 
 /* ---- execution ----

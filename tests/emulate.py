@@ -46,7 +46,7 @@ def run_plan(plan, leaf_blob, slice_ids):
                 # the scratch panels must not overlap any operand of the step, and the output
                 # must have the layout the tensor-core GEMM writes (n modes lowest)
                 lo, hi = E.scratch_offset, E.scratch_offset + E.scratch_bytes
-                assert hi <= plan.workspace_bytes and lo % 1024 == 0
+                assert hi <= plan.arena_bytes and lo % 1024 == 0
                 for t in (E.a, E.b, E.c):
                     assert t.offset + ((t.rows << t.rank) * 8) <= lo or t.offset >= hi, "scratch overlaps an operand"
                 assert sorted(E.n_c[i] for i in range(E.n_n)) == list(range(E.n_n))

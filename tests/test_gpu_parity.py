@@ -190,11 +190,13 @@ def test_plan_permute_operation_through_the_abi(dev, rank):
         acc = N.TncAccum()
         acc.src, acc.out_pos = N.TncTensor(size, rank, 1), N.bits(range(rank))
         N.check(lib.tnc_plan_add_accum(h, N.TNC_PHASE_SLICE, C.byref(acc)))
-        N.check(lib.tnc_plan_finalize(h, 2 * size))
+        N.check(lib.tnc_plan_finalize(h, 2 * size))                # the arena; the workspace adds the library's tail
+        ws_bytes = lib.tnc_plan_workspace_bytes(h)
+        assert ws_bytes == 2 * size + N.TNC_WORKSPACE_TAIL_BYTES
         src = torch.randn(1 << rank, dtype=torch.complex64, device=dev)
         out = torch.zeros(1 << rank, dtype=torch.complex64, device=dev)
-        ws = torch.empty(2 * size, dtype=torch.uint8, device=dev)
-        N.check(lib.tnc_plan_execute(h, src.data_ptr(), 0, 1, out.data_ptr(), ws.data_ptr(), 2 * size,
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        N.check(lib.tnc_plan_execute(h, src.data_ptr(), 0, 1, out.data_ptr(), ws.data_ptr(), ws_bytes,
                                      torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
     finally:
@@ -217,7 +219,7 @@ def test_cuda_graph_replay_of_the_slice_phase(dev, name):
     mk = lambda g: ContractionPlan(case.scheme, shapes, case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
                                    slicing_indices=case.slicing_indices(), options=PlanOptions(cuda_graph=g))
     plain, graph = mk(False), mk(True)
-    assert graph.cuda_graph and not plain.cuda_graph and graph.workspace_bytes == plain.workspace_bytes + 1024
+    assert graph.cuda_graph and not plain.cuda_graph and graph.workspace_bytes == plain.workspace_bytes
     blob = plain.pack_leaves({k: v.to(dev) for k, v in case.leaves.items()})
     st = torch.cuda.current_stream().cuda_stream
     n = plain.n_slices
@@ -692,6 +694,59 @@ def test_tc_long_contraction_keeps_fp32_accuracy(dev, precision):
     err = np.abs(got - want) / rms
     print(f"K=16384 {precision}: max err/rms {err.max():.3e}, rms err/rms {np.sqrt(np.mean(err ** 2)):.3e}")
     assert err.max() < 1e-5
+
+
+# (producer kind, (m, n, k) of the producing step, plan options): the second step contracts 7 bonds of the first
+# step's result with a fresh tensor (k = 7: beyond the streaming tcgen05 kernel, so it is a tensor-core GEMM step)
+_FUSED_PRODUCERS = [
+    ("stem", (13, 2, 1), dict(tc_min_flops=0, tc_min_intensity=0, stem_min_elems=0, skinny_min_elems=1 << 62)),
+    ("stem", (12, 3, 1), dict(tc_min_flops=0, tc_min_intensity=0, stem_min_elems=0, skinny_min_elems=1 << 62)),
+    ("stem", (12, 2, 5), dict(tc_min_flops=0, tc_min_intensity=10, stem_min_elems=0, skinny_min_elems=1 << 62)),   # k > 4: per-thread kernel
+    ("skinny", (13, 4, 3), dict(tc_min_flops=0, tc_min_intensity=0, skinny_min_elems=0, skinny_min_n=1)),
+    ("skinny", (12, 5, 6), dict(tc_min_flops=0, tc_min_intensity=0, skinny_min_elems=0, skinny_min_n=1)),
+    ("tc", (8, 5, 7), dict(tc_min_flops=0, tc_min_intensity=0, skinny_min_elems=1 << 62)),          # 4M kernel
+    ("tc", (9, 7, 6), dict(tc_min_flops=0, tc_min_intensity=0, skinny_min_elems=1 << 62)),          # 3M kernel
+]
+
+
+@pytest.mark.parametrize("precision", ["3xf16", "f16"])
+@pytest.mark.parametrize("kind,shape,opts", _FUSED_PRODUCERS)
+@pytest.mark.parametrize("scale", [1.0, 3e-6])
+def test_operand_amax_reduced_by_the_producing_kernel(dev, kind, shape, opts, precision, scale):
+    """TNC_OPT_FUSE_AMAX: the kernel that writes a tensor-core step's left operand (streaming fp32, streaming
+    tcgen05, 4M and 3M GEMM) also reduces its largest magnitude, and the step's own amax pass skips that operand.
+    The maximum is exact either way, so the result must be BIT-IDENTICAL to the plan that keeps the separate pass;
+    and both meet the oracle."""
+    from artensor_b200 import ContractionPlan, PlanOptions
+    from artensor_b200 import _native as N
+    m, n, k = shape
+    rng = np.random.RandomState(m * 100 + n * 10 + k)
+    scheme0, leaves, c0 = single_step_case(m, n, k, seed=m + n + k)
+    leaves[0] = leaves[0] * scale                                  # the scale has to follow the data
+    c0 = c0 * scale
+    out0 = scheme0[0][1].split("->")[1]
+    k1 = list(rng.permutation(list(out0))[:7])                      # 7 of its bonds are contracted next
+    fresh = list(LETTERS[m + n + k:m + n + k + 5])
+    lb = k1 + fresh
+    rng.shuffle(lb)
+    lo = [c for c in out0 if c not in k1] + fresh
+    rng.shuffle(lo)
+    eq1 = out0 + "," + "".join(lb) + "->" + "".join(lo)
+    b1 = (rng.randn(*[2] * 12) + 1j * rng.randn(*[2] * 12)).astype(np.complex64)
+    leaves[2] = torch.from_numpy(b1)
+    want = np.einsum(eq1, c0, b1.astype(np.complex128), optimize=True)
+    scheme = [scheme0[0], ((0, 2), eq1)]
+    shapes = {i: tuple(v.shape) for i, v in leaves.items()}
+    algo = {"stem": N.TNC_ALGO_STEM, "skinny": N.TNC_ALGO_SKINNY, "tc": N.TNC_ALGO_TC}[kind]
+    outs = []
+    for fuse in (True, False):
+        plan = ContractionPlan(scheme, shapes, False, options=PlanOptions(tc_precision=precision, fuse_amax=fuse, **opts))
+        assert plan.step_algo == [algo, N.TNC_ALGO_TC]
+        assert plan.fused_amax_operands() == (1 if fuse else 0)
+        outs.append(_execute(dev, plan, leaves))
+    assert np.array_equal(outs[0], outs[1])
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    assert np.abs(outs[0] - want).max() / rms < (1e-5 if precision == "3xf16" else 4e-3)
 
 
 def test_tc_two_cta_blocked_tiles(dev):

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--check", action="store_true", help="compare with the golden per-slice amplitudes")
     ap.add_argument("--precision", default=None, choices=["3xtf32", "3xf16", "f16"])
     ap.add_argument("--tag", default="")
+    ap.add_argument("--no-fuse-amax", action="store_true")
     a = ap.parse_args()
     case = load_case(os.path.join(ROOT, "tests", "golden", f"{a.case}.case.gz"))
     sim = TensorNetworkSimulation.from_case(case)
@@ -39,6 +40,8 @@ def main():
         kw["tc_min_flops"] = a.tc_min_flops
     if a.precision is not None:
         kw["tc_precision"] = a.precision
+    if a.no_fuse_amax:
+        kw["fuse_amax"] = False
     sim.plan_options = PlanOptions(**kw)
     print(f"options: {sim.plan_options}", flush=True)
     plan = sim.plan()
