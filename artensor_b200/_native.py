@@ -20,7 +20,7 @@ TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
 TNC_EINSUM_OUTER_ROWS = 1
 TNC_EINSUM_OUTER_PAIRS = 2
 TNC_TC_3XTF32, TNC_TC_3XF16, TNC_TC_F16 = 0, 1, 2
-TNC_OPT_TC_PRECISION, TNC_OPT_CUDA_GRAPH, TNC_OPT_FUSE_AMAX = 0, 1, 2
+TNC_OPT_TC_PRECISION, TNC_OPT_CUDA_GRAPH, TNC_OPT_FUSE_AMAX, TNC_OPT_SLICE_REUSE = 0, 1, 2, 3
 TC_PRECISIONS = {"3xtf32": TNC_TC_3XTF32, "3xf16": TNC_TC_3XF16, "f16": TNC_TC_F16}
 
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "UNSUPPORTED", 5: "STATE"}

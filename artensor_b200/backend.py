@@ -21,6 +21,7 @@ from . import _native as N
 from .plan import SchemeParser, Step, TensorInfo, SchemeError
 
 ALIGN = 1024
+REGION_KEEP = 2     # third arena region (after ONCE and SLICE): slice-phase intermediates that outlive a slice (slice_reuse)
 
 
 class Arena:
@@ -66,18 +67,22 @@ class Arena:
 class Buf:
     """A tensor resident in the arena: `pos[mode]` is the bit position of each mode.
     Buffers of slice-invariant data live in the ONCE region, everything else in the SLICE
-    region that starts where the ONCE region ends (bases are fixed after allocation)."""
-    region: int           # N.TNC_PHASE_ONCE or N.TNC_PHASE_SLICE
+    region that starts where the ONCE region ends (bases are fixed after allocation); with
+    PlanOptions.slice_reuse, slice-phase results that must survive until a LATER slice (their
+    consumer depends on more sliced bonds than they do) get a region of their own, KEEP, where
+    nothing is ever laid over them."""
+    region: int           # N.TNC_PHASE_ONCE, N.TNC_PHASE_SLICE or REGION_KEEP
     rel_offset: int
     size: int
     info: TensorInfo
     pos: Dict[int, int]
     is_leaf: bool
-    base: List[int] = None   # shared [once_base, slice_base], filled in at the end
+    base: List[int] = None   # shared [once_base, slice_base, keep_base], filled in at the end
+    deps: frozenset = frozenset()   # sliced bonds (indices into slicing_bonds) the contents depend on
 
     @property
     def dependent(self):
-        return self.region == N.TNC_PHASE_SLICE
+        return self.region != N.TNC_PHASE_ONCE
 
     def tensor(self):
         return N.TncTensor(self.base[self.region] + self.rel_offset, self.info.rank, self.info.rows or 1)
@@ -120,6 +125,12 @@ class PlanOptions:
     # reduced by that kernel's epilogue instead of a separate pass over the tensor (TNC_OPT_FUSE_AMAX); results are
     # bit-identical either way
     fuse_amax: bool = True
+    # Cross-slice reuse (TNC_OPT_SLICE_REUSE): inside one execute call over consecutive slice ids, a step is
+    # contracted again only when a sliced bond it depends on changed since the previous slice -- the reference's
+    # loop (simulation.py:107-114) recomputes the whole tree for every slice although most of a deep tree depends
+    # on a few of the sliced bonds only.  Results are bit-identical; intermediates whose consumer depends on more
+    # bonds than they do keep a region of their own for the whole call (a larger workspace).
+    slice_reuse: bool = False
 
     def __post_init__(self):
         if self.tc_precision not in N.TC_PRECISIONS:
@@ -304,8 +315,27 @@ class ContractionPlan:
 
     # ------------------------------------------------------------------ lowering
     def _lower(self):
-        arenas = {N.TNC_PHASE_ONCE: Arena(), N.TNC_PHASE_SLICE: Arena()}
-        base = [0, 0]
+        arenas = {N.TNC_PHASE_ONCE: Arena(), N.TNC_PHASE_SLICE: Arena(), REGION_KEEP: Arena()}
+        base = [0, 0, 0]
+        reuse = self.slice_reuse = bool(self.options.slice_reuse and self.n_sliced > 0)
+        # sliced bonds behind every step's result, and behind the step that consumes it (the accumulate runs for
+        # every slice: it "depends" on every bond)
+        every = frozenset(range(self.n_sliced))
+        slot_deps = {tid: frozenset(self.leaf_sliced.get(tid, {}).values()) for tid in self.leaf_info}
+        slot_producer: Dict[int, int] = {}
+        self.step_deps: List[frozenset] = []
+        consumer_deps: List[frozenset] = []
+        for idx, st in enumerate(self.steps):
+            d = slot_deps[st.i] | slot_deps[st.j]
+            for t in (st.i, st.j):
+                if t in slot_producer:
+                    consumer_deps[slot_producer[t]] = d
+            self.step_deps.append(d)
+            consumer_deps.append(every)
+            slot_deps[st.i] = d
+            slot_producer[st.i] = idx
+            del slot_deps[st.j]
+            slot_producer.pop(st.j, None)
         # leaf blob layout (elements), in ascending tensor id order over the leaves the scheme uses
         self.leaf_order = sorted(self.leaf_info)
         self.leaf_src_offset = {}
@@ -321,13 +351,14 @@ class ContractionPlan:
             info = self.leaf_info[tid]
             region = N.TNC_PHASE_SLICE if (tid in self.leaf_sliced or not self.options.hoist) else N.TNC_PHASE_ONCE
             o, sz = arenas[region].alloc(info.numel * self.elem_bytes)
-            buf = Buf(region, o, sz, info, logical_positions(info), True, base)
+            buf = Buf(region, o, sz, info, logical_positions(info), True, base,
+                      frozenset(self.leaf_sliced.get(tid, {}).values()))
             bufs[tid] = buf
             leaf_bufs[region].append((tid, buf))
 
         pending = []        # (phase, step, A, B, C, algo) in scheme order
         self.step_phase, self.step_algo = [], []
-        for orig in self.steps:
+        for idx, orig in enumerate(self.steps):
             A, B = bufs[orig.i], bufs[orig.j]
             st = orig
             if self.options.swap_operands and self.dtype == N.TNC_C64 and should_swap(orig):
@@ -343,8 +374,13 @@ class ContractionPlan:
                 elif st.c.numel >= o.stem_min_elems and stem_eligible(st):
                     algo = N.TNC_ALGO_STEM
             cpos = self._choose_layout(st, A, B, algo)
-            o, sz = arenas[phase].alloc(st.c.numel * self.elem_bytes)
-            Cb = Buf(phase, o, sz, st.c, cpos, False, base)
+            # slice_reuse: a result whose consumer depends on more sliced bonds is read again in later slices
+            # without being recomputed -- it gets memory nothing else is ever laid over (KEEP); a result whose
+            # consumer depends on the same bonds is recomputed whenever it is read and recycles as before
+            keep = reuse and phase == N.TNC_PHASE_SLICE and self.step_deps[idx] != consumer_deps[idx]
+            region = REGION_KEEP if keep else phase
+            o, sz = arenas[region].alloc(st.c.numel * self.elem_bytes)
+            Cb = Buf(region, o, sz, st.c, cpos, False, base, self.step_deps[idx])
             scratch = None
             if algo == N.TNC_ALGO_TC:
                 # packed operand panels live only while the step runs
@@ -363,12 +399,17 @@ class ContractionPlan:
             del bufs[orig.j]
         base[N.TNC_PHASE_ONCE] = 0
         base[N.TNC_PHASE_SLICE] = arenas[N.TNC_PHASE_ONCE].high
-        self.arena_bytes = max(arenas[N.TNC_PHASE_ONCE].high + arenas[N.TNC_PHASE_SLICE].high, ALIGN)
+        base[REGION_KEEP] = base[N.TNC_PHASE_SLICE] + arenas[N.TNC_PHASE_SLICE].high
+        self.keep_bytes = arenas[REGION_KEEP].high
+        # bytes [lo, hi) that are recycled within a slice (everything the SLICE arena holds except the leaves)
+        leaf_hi = max([b.rel_offset + b.size for _, b in leaf_bufs[N.TNC_PHASE_SLICE]], default=0)
+        self.recycled_range = (base[N.TNC_PHASE_SLICE] + leaf_hi, base[REGION_KEEP])
+        self.arena_bytes = max(base[REGION_KEEP] + arenas[REGION_KEEP].high, ALIGN)
         # the library keeps its own words (amax words reduced by producing kernels, the slice-id word of graph
         # replay) in a tail behind the arena: tnc_plan_workspace_bytes
         self.workspace_bytes = (self.arena_bytes + ALIGN - 1) // ALIGN * ALIGN + N.TNC_WORKSPACE_TAIL_BYTES
         exec_flops = sum(st.flops for st, ph in zip(self.steps, self.step_phase) if ph == N.TNC_PHASE_SLICE)
-        self.cuda_graph = (self.n_sliced >= 1 and exec_flops < self.options.graph_max_flops
+        self.cuda_graph = (self.n_sliced >= 1 and exec_flops < self.options.graph_max_flops and not reuse
                            if self.options.cuda_graph is None else bool(self.options.cuda_graph))
 
         ops = {N.TNC_PHASE_ONCE: [], N.TNC_PHASE_SLICE: []}
@@ -494,6 +535,7 @@ class ContractionPlan:
             N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_TC_PRECISION, N.TC_PRECISIONS[self.options.tc_precision]))
             N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_CUDA_GRAPH, 1 if self.cuda_graph else 0))
             N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_FUSE_AMAX, 1 if self.options.fuse_amax else 0))
+            N.check(lib.tnc_plan_set_option(handle, N.TNC_OPT_SLICE_REUSE, 1 if self.slice_reuse else 0))
             for t in self.tables:
                 tid = C.c_int32()
                 N.check(lib.tnc_plan_add_table(handle, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t), C.byref(tid)))
@@ -594,6 +636,49 @@ class ContractionPlan:
     @property
     def last_launches(self):
         return int(self._lib.tnc_plan_last_launches(self._handle))
+
+    # ------------------------------------------------------------------ cross-slice reuse
+    def step_seconds_model(self):
+        """Rough B200 time of every step (seconds): tensor-bound GEMM steps at the measured useful rate of the
+        split-precision product, everything else at the streaming kernels' in-slice HBM rate, plus a launch.
+        Only the RATIOS matter: it ranks sliced bonds for `reuse_bond_order` and prices `reuse_summary`."""
+        out = []
+        for st, algo in zip(self.steps, self.step_algo):
+            rate = 5.5e14 if self.options.tc_precision != "f16" else 1.3e15
+            t = max(st.flops / rate, st.bytes_c64 / 4.5e12) if algo == N.TNC_ALGO_TC else st.bytes_c64 / 4.0e12
+            if algo == N.TNC_ALGO_TC:
+                t += (st.a.numel + st.b.numel) * 20 / 5.0e12          # operand panels: 8 bytes read, 12 written
+            out.append(t + 3e-6)
+        return out
+
+    def reuse_bond_order(self, fixed_high=0):
+        """Order of the sliced bonds (most significant slice-id bit first, as `slicing_bonds` is read) that makes
+        consecutive slice ids share the most work under PlanOptions.slice_reuse: over a long range a step runs once
+        per 2^p slices, p = the lowest slice-id bit among the bonds it depends on, so the bonds that the expensive
+        steps do NOT depend on should be the fastest-changing bits.  Greedy from the least significant bit up: give
+        the next bit to the bond that the cheapest set of not-yet-charged steps depends on.  The first `fixed_high`
+        bonds keep their (most significant) places."""
+        cost = self.step_seconds_model()
+        live = [(c, d) for c, d in zip(cost, self.step_deps) if d]
+        remaining = set(range(fixed_high, self.n_sliced))
+        low_first = []
+        while remaining:
+            best = min(sorted(remaining), key=lambda b: sum(c for c, d in live if b in d))
+            low_first.append(best)
+            remaining.discard(best)
+            live = [(c, d) for c, d in live if best not in d]
+        return list(range(fixed_high)) + low_first[::-1]
+
+    def reuse_summary(self, bond_order=None):
+        """Modelled seconds per slice: every step for every slice, against the amortised cost over a long range of
+        consecutive slice ids with slice_reuse (a step runs once per 2^(lowest bit it depends on) slices).
+        `bond_order`: a permutation of range(n_sliced), most significant first (default: the plan's own)."""
+        cost = self.step_seconds_model()
+        order = list(range(self.n_sliced)) if bond_order is None else list(bond_order)
+        bit = {b: self.n_sliced - 1 - i for i, b in enumerate(order)}
+        full = sum(c for c, ph in zip(cost, self.step_phase) if ph == N.TNC_PHASE_SLICE)
+        amortised = sum(c * 2.0 ** -min(bit[b] for b in d) for c, d in zip(cost, self.step_deps) if d)
+        return {"full_s": full, "amortised_s": amortised}
 
     def work_summary(self):
         """Executed vs reference-equivalent work per slice."""

@@ -51,6 +51,9 @@ struct Op {
     // already reduced the operand's largest magnitude there; out (any einsum kernel that can): reduce the largest
     // magnitude of this step's output there, for the tensor-core step that consumes it
     TcAmaxWords amax;
+    // slice-id bits (LSB-based) the operation's result depends on; leaf loads and the accumulate: every bit.
+    // Only filled in, and only read, with TNC_OPT_SLICE_REUSE
+    uint64_t deps = ~0ull;
 };
 
 }  // namespace tnc
@@ -78,6 +81,7 @@ struct tnc_plan {
     // (workspace, leaf blob, accumulator) the plan has been executed with
     bool use_graph = false;
     bool fuse_amax = true;                // TNC_OPT_FUSE_AMAX
+    bool slice_reuse = false;             // TNC_OPT_SLICE_REUSE
     std::atomic<bool> graph_failed{false};
     std::mutex graph_mu;
     struct GraphKey {
@@ -164,6 +168,13 @@ int tnc_plan_set_option(tnc_plan* plan, int32_t option, int64_t value) {
                 return TNC_ERR_INVALID;
             }
             plan->fuse_amax = value != 0;
+            return TNC_OK;
+        case TNC_OPT_SLICE_REUSE:
+            if (value != 0 && value != 1) {
+                set_error("set_option: TNC_OPT_SLICE_REUSE takes 0 or 1, got %lld", (long long)value);
+                return TNC_ERR_INVALID;
+            }
+            plan->slice_reuse = value != 0;
             return TNC_OK;
     }
     set_error("set_option: unknown option %d", option);
@@ -379,6 +390,87 @@ int tnc_plan_add_accum(tnc_plan* plan, int32_t phase, const tnc_accum* a) {
     return TNC_OK;
 }
 
+// TNC_OPT_SLICE_REUSE: the slice-id bits behind every slice-phase operation, and the check of what the option asks
+// of the caller's layout -- a result that is read by an operation depending on MORE bits is read again in later
+// slices without being recomputed, so no other operation of the phase may ever write over it.
+static int plan_slice_deps(tnc_plan* plan) {
+    auto& ops = plan->ops[TNC_PHASE_SLICE];
+    struct Range {
+        int64_t lo, hi;
+    };
+    auto range_of = [&](const tnc_tensor& t) { return Range{t.offset, t.offset + tensor_bytes(plan, t)}; };
+    std::map<int64_t, uint64_t> at;        // arena offset -> bits behind the tensor last written there
+    auto bits_at = [&](int64_t off) {      // ONCE-phase tensors are never written in this phase: no bits
+        auto it = at.find(off);
+        return it == at.end() ? 0ull : it->second;
+    };
+    const uint64_t every = plan->n_sliced >= 64 ? ~0ull : ((1ull << plan->n_sliced) - 1);
+    for (auto& op : ops) {
+        op.deps = every;                   // leaf loads and the accumulate run for every slice
+        if (op.kind == OP_LEAVES) {
+            for (int i = 0; i < op.leaf_count; ++i) {
+                const LeafDev& L = plan->leaves[op.leaf_begin + i];
+                uint64_t m = 0;
+                for (int q = 0; q < L.n_sliced; ++q) m |= 1ull << L.sliced_shift[q];
+                at[L.dst_offset] = m;
+            }
+        } else if (op.kind == OP_EINSUM) {
+            op.deps = bits_at(op.e.a.offset) | bits_at(op.e.b.offset);
+            at[op.e.c.offset] = op.deps;
+        } else if (op.kind == OP_PERMUTE) {
+            op.deps = bits_at(op.p.src.offset);
+            at[op.p.dst.offset] = op.deps;
+        }
+    }
+    // everything an operation writes
+    auto writes_of = [&](const Op& op, std::vector<Range>& out) {
+        out.clear();
+        if (op.kind == OP_LEAVES)
+            for (int i = 0; i < op.leaf_count; ++i) {
+                const LeafDev& L = plan->leaves[op.leaf_begin + i];
+                out.push_back(Range{L.dst_offset, L.dst_offset + (((int64_t)L.dst_rows << L.dst_rank) * plan->elem_bytes())});
+            }
+        if (op.kind == OP_EINSUM) {
+            out.push_back(range_of(op.e.c));
+            if (op.e.algo == TNC_ALGO_TC && op.e.scratch_bytes > 0)
+                out.push_back(Range{op.e.scratch_offset, op.e.scratch_offset + op.e.scratch_bytes});
+        }
+        if (op.kind == OP_PERMUTE) out.push_back(range_of(op.p.dst));
+    };
+    std::vector<Range> w;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const Op& x = ops[i];
+        if (x.kind != OP_EINSUM && x.kind != OP_PERMUTE) continue;
+        const tnc_tensor& out = x.kind == OP_EINSUM ? x.e.c : x.p.dst;
+        // the reader: the first later operation that takes a tensor at this offset
+        uint64_t reader = x.deps;
+        for (size_t j = i + 1; j < ops.size(); ++j) {
+            const Op& y = ops[j];
+            const bool reads = (y.kind == OP_EINSUM && (y.e.a.offset == out.offset || y.e.b.offset == out.offset)) ||
+                               (y.kind == OP_PERMUTE && y.p.src.offset == out.offset) ||
+                               (y.kind == OP_ACCUM && y.a.src.offset == out.offset);
+            if (reads) {
+                reader = y.deps;
+                break;
+            }
+        }
+        if (reader == x.deps) continue;                     // recomputed whenever it is read
+        const Range r = range_of(out);
+        for (size_t j = 0; j < ops.size(); ++j) {
+            if (j == i) continue;
+            writes_of(ops[j], w);
+            for (const Range& o : w)
+                if (o.lo < r.hi && r.lo < o.hi) {
+                    set_error("finalize: TNC_OPT_SLICE_REUSE needs the result of slice operation %d (bytes [%lld, %lld)) kept "
+                              "intact across slices, but operation %d writes [%lld, %lld)", (int)i, (long long)r.lo,
+                              (long long)r.hi, (int)j, (long long)o.lo, (long long)o.hi);
+                    return TNC_ERR_INVALID;
+                }
+        }
+    }
+    return TNC_OK;
+}
+
 int tnc_plan_finalize(tnc_plan* plan, int64_t arena_bytes) {
     if (!plan || plan->finalized || arena_bytes < 0) {
         set_error("finalize: bad arguments or already finalized");
@@ -444,7 +536,11 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t arena_bytes) {
                 op.seg_off = append(seg.data(), seg.size() * sizeof(int32_t));
             }
         }
-    // runs of consecutive tiny generic steps -> one chain launch each
+    if (plan->slice_reuse) {
+        if (int rc = plan_slice_deps(plan)) return rc;
+    }
+    // runs of consecutive tiny generic steps -> one chain launch each (with slice reuse: of steps that depend on the
+    // same slice-id bits, so that a chain runs exactly when each of its members must)
     static const bool no_chain = knob("TNC_NO_CHAIN") != nullptr;       // measurement aid
     auto chainable = [&](const Op& op) {
         if (no_chain || plan->dtype != TNC_C64 || op.kind != OP_EINSUM || op.e.algo != TNC_ALGO_SIMT) return false;
@@ -455,7 +551,7 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t arena_bytes) {
         auto& ops = plan->ops[ph];
         for (size_t i = 0; i < ops.size();) {
             size_t j = i;
-            while (j < ops.size() && chainable(ops[j])) ++j;
+            while (j < ops.size() && chainable(ops[j]) && (!plan->slice_reuse || ops[j].deps == ops[i].deps)) ++j;
             if (j - i >= 2) {
                 std::vector<ChainStep> recs;
                 for (size_t t = i; t < j; ++t) {
@@ -733,7 +829,7 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
         if (rc != TNC_OK) return rc;
     }
     uint64_t s = slice_begin;
-    if (plan->use_graph && !plan->graph_failed && slice_end - slice_begin >= 2) {
+    if (plan->use_graph && !plan->slice_reuse && !plan->graph_failed && slice_end - slice_begin >= 2) {
         // Replay the slice phase as one CUDA graph per slice: the slice id lives in a workspace word that
         // the leaf gather reads and the graph's last node increments.  Captured once per (workspace,
         // leaf blob, accumulator); a capture that fails falls back to plain launches for good.
@@ -794,8 +890,15 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
         }
     }
     for (; s < slice_end; ++s) {
-        if (int rc = clear_amax_words(plan, TNC_PHASE_SLICE, ws, st)) return rc;
+        if (!plan->slice_reuse) {
+            if (int rc = clear_amax_words(plan, TNC_PHASE_SLICE, ws, st)) return rc;
+        }
+        // slice reuse: after the first slice of the call, only what depends on a slice-id bit that changed
+        const bool all = s == slice_begin || !plan->slice_reuse;
+        const uint64_t changed = s ^ (s - 1);
         for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
+            if (!all && (op.kind == OP_EINSUM || op.kind == OP_PERMUTE) && !(op.deps & changed)) continue;
+            if (plan->slice_reuse && op.amax.out >= 0) TNC_CUDA(cudaMemsetAsync(ws + op.amax.out, 0, 4, st));
             int rc = run_op(plan, op, leaf_blob, s, accum_out, ws, st, &launches);
             if (rc != TNC_OK) return rc;
         }

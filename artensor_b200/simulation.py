@@ -180,6 +180,25 @@ class TensorNetworkSimulation(_Base):
         order = [rest.index(b) for b in self.output_bonds]       # qubit rank of every remaining output dim
         self.permute_dims = [int(d) for d in np.argsort(order)]
 
+    def optimize_slice_order(self):
+        """Reorders the sliced bonds -- i.e. which bond each bit of the slice id fixes -- so that consecutive slice
+        ids share as much of the tree as possible, for `plan_options.slice_reuse` (artensor_b200/backend.py
+        `reuse_bond_order`).  The set of slices and their sum are unchanged; slice id `s` no longer names the slice
+        the reference's loop calls `s` (simulation.py:107-113 fix bond i from bit i of `binary_repr(s)`), so
+        per-slice comparisons with the reference must be made before calling this.  Shard bonds
+        (`prepare_open_qubit_shards`) keep the most significant bits.  Returns the modelled seconds per slice
+        {"full_s", "amortised_before_s", "amortised_s"}."""
+        probe = _c.ContractionPlan(self.scheme, {i: tuple(self.tensors[i].shape) for i in self._ids()},
+                                   self.pattern == 'sparse', slicing_bonds=self.slicing_bonds,
+                                   slicing_indices=self.slicing_indices, dtype="c64", options=self.plan_options,
+                                   build_native=False)
+        order = probe.reuse_bond_order(fixed_high=len(self.shard_bonds))
+        before, after = probe.reuse_summary(), probe.reuse_summary(order)
+        self.slicing_bonds = [self.slicing_bonds[i] for i in order]
+        self.slicing_indices = slicing_dims(self.tensors, self.tensor_bonds, self.slicing_bonds)
+        self._plan_cache.clear()
+        return {"full_s": before["full_s"], "amortised_before_s": before["amortised_s"], "amortised_s": after["amortised_s"]}
+
     # ---- the hot path ----
     def plan(self, mode="c64"):
         """Compiled plan for a compute mode: "c64" (fp32-accurate) or "chalf" (reduced-precision

@@ -78,6 +78,8 @@ def parse_args():
                     help="operand precision of the tensor-core steps (default: the library default, 3xf16)")
     ap.add_argument("--no-half", action="store_true", help="skip the complex-half mode measurement")
     ap.add_argument("--no-fuse-amax", action="store_true", help="A/B aid: keep the separate amax pass of every tensor-core step")
+    ap.add_argument("--no-reuse", action="store_true", help="skip the cross-slice reuse measurement (`slice_reuse` key)")
+    ap.add_argument("--reuse-slices", type=int, default=256, help="consecutive slice ids per execute call of that measurement")
     return ap.parse_args()
 
 
@@ -645,6 +647,57 @@ def main():
             half["roofline_error"] = str(exc)
         del hplan
 
+    # ---- cross-slice reuse (PlanOptions.slice_reuse) on the same tree: every rank contracts ONE range of R consecutive
+    # slice ids in one execute call, the sliced bonds re-ordered for reuse.  Not the headline: `value` / `e2e` above
+    # contract every step for every slice, as the reference's loop does; here a step is contracted again only when a
+    # sliced bond behind it changed, with bit-identical amplitudes (tests/test_gpu_parity.py).
+    reuse = None
+    if not args.no_reuse and plan.n_sliced >= 2:
+        try:
+            rsim = TensorNetworkSimulation.from_case(case)
+            rsim.plan_options = PlanOptions(**dict(opt_kw, slice_reuse=True, cuda_graph=False))
+            model = rsim.optimize_slice_order()
+            rplan = rsim.plan()
+            ws = None
+            C.release_workspaces()
+            torch.cuda.empty_cache()
+            free_b, _ = torch.cuda.mem_get_info(dev)
+            if rplan.workspace_bytes > free_b - (2 << 30):
+                raise RuntimeError(f"workspace with reuse {rplan.workspace_bytes >> 30} GiB > free HBM {free_b >> 30} GiB")
+            R = min(args.reuse_slices, rplan.n_slices // world)
+            rws = C.get_workspace(dev, rplan.workspace_bytes)
+            rblob = rplan.pack_leaves(case.leaves, device=dev)
+            rlo = rank * R
+            rout = torch.zeros(rplan.out_shape, dtype=torch.complex64, device=dev)
+            rplan.execute(rblob, rout, rlo, rlo + min(R, 2), rws, stream.cuda_stream)       # warm-up (tensor maps)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rout.zero_()
+            r0.record(stream)
+            rplan.execute(rblob, rout, rlo, rlo + R, rws, stream.cuda_stream)
+            if world > 1:
+                dist.all_reduce(torch.view_as_real(rout), op=dist.ReduceOp.SUM)
+            r1.record(stream)
+            barrier()
+            rt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+            rms = float(rt.item())
+            reuse = {"value": world * R / (rms * 1e-3), "unit": UNIT, "slices_per_call_per_gpu": R,
+                     "ms_per_slice_per_gpu": rms / R, "launches_per_slice": rplan.last_launches / R,
+                     "bit_order": "sliced bonds re-ordered by TensorNetworkSimulation.optimize_slice_order",
+                     "workspace_gib": rplan.workspace_bytes / 2 ** 30,
+                     "modelled_ms_per_slice": {"every_step": model["full_s"] * 1e3,
+                                               "reuse_reference_bit_order": model["amortised_before_s"] * 1e3,
+                                               "reuse": model["amortised_s"] * 1e3},
+                     "extrapolated_full_task_seconds": (2.0 ** rplan.n_sliced) * (rms * 1e-3 / R) / world,
+                     "note": "same tree, same slices, bit-identical amplitudes: inside one call a step is contracted again "
+                             "only when a sliced bond behind it changed from the previous slice id; value / e2e above do "
+                             "NOT use it (every step contracted for every slice, like the reference's slice loop)"}
+            del rplan, rws, rblob
+        except Exception as exc:      # an extra measurement must never take the line down
+            reuse = {"value": None, "error": str(exc)}
+
     # ---- CPU baseline on the host cores (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -685,7 +738,7 @@ def main():
             "extrapolated_full_task_seconds": (2.0 ** plan.n_sliced) / value,
             "e2e": e2e, "gpu_launches": launches, "fused_amax_operands": plan.fused_amax_operands(), "clocks": clocks, "roofline": roofline,
             "slice_roofline": slice_roofline, "breakdown": breakdown,
-            "cpu_baseline": cpu, "half_mode": half,
+            "cpu_baseline": cpu, "half_mode": half, "slice_reuse": reuse,
         }
         emit(line)
     if world > 1:

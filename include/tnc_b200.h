@@ -76,11 +76,20 @@ typedef enum tnc_option {
                                     (captured on first use per workspace / leaf blob / accumulator) instead of
                                     ~100 stream launches -- for slices of a few ms, where launch gaps are a
                                     measurable share.  The slice-id word lives in the workspace tail. */
-    TNC_OPT_FUSE_AMAX = 2        /* value 1 (default): when the operand of a tensor-core step (fp16 precisions) was
+    TNC_OPT_FUSE_AMAX = 2,       /* value 1 (default): when the operand of a tensor-core step (fp16 precisions) was
                                     written by a streaming or GEMM kernel of the same phase, that kernel reduces the
                                     operand's largest magnitude (its power-of-two scale) into a word of the workspace
                                     tail while it stores the tensor, and the step's own amax pass skips the operand.
                                     Results are bit-identical either way; 0 keeps the separate pass (A/B aid). */
+    TNC_OPT_SLICE_REUSE = 3      /* value 1: inside one tnc_plan_execute call, after its first slice, a SLICE-phase
+                                    operation runs again only when a sliced bond its operands depend on changed from
+                                    the previous slice id (the library derives the dependencies from the leaf records).
+                                    The reference's loop (simulation.py:107-114) recomputes the whole tree per slice;
+                                    most of a deep tree depends on few of the sliced bonds.  Results are bit-identical.
+                                    Asks of the caller's layout, checked at finalize (TNC_ERR_INVALID): the result of
+                                    an operation whose reader depends on MORE sliced bonds is read again in later
+                                    slices, so no other operation of the phase may write over it (tensor or scratch).
+                                    Excludes TNC_OPT_CUDA_GRAPH replay (plain launches are used).  Default 0. */
 } tnc_option;
 
 typedef enum tnc_algo {

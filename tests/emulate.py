@@ -22,8 +22,31 @@ def _deposit(idx, positions):
     return out
 
 
-def run_plan(plan, leaf_blob, slice_ids):
-    """Execute plan.ops on a host arena; returns the accumulator (logical result order)."""
+def slice_deps(plan):
+    """Slice-id bits (LSB-based) behind every SLICE-phase operation, derived from the leaf records the way
+    tnc_plan_finalize does for TNC_OPT_SLICE_REUSE (leaf loads and the accumulate: every bit)."""
+    S = plan.n_sliced
+    at, deps = {}, []
+    for kind, rec in plan.ops[N.TNC_PHASE_SLICE]:
+        d = (1 << S) - 1
+        if kind == "leaves":
+            for L in rec:
+                at[L.dst.offset] = sum(1 << (S - 1 - L.sliced_bond[q]) for q in range(L.n_sliced))
+        elif kind == "einsum":
+            d = at.get(rec.a.offset, 0) | at.get(rec.b.offset, 0)
+            at[rec.c.offset] = d
+        elif kind == "permute":
+            d = at.get(rec.src.offset, 0)
+            at[rec.dst.offset] = d
+        deps.append(d)
+    return deps
+
+
+def run_plan(plan, leaf_blob, slice_ids, reuse=False, poison=False):
+    """Execute plan.ops on a host arena; returns the accumulator (logical result order).
+    reuse: TNC_OPT_SLICE_REUSE semantics over the (consecutive) slice_ids -- after the first slice an operation
+    runs only when a slice-id bit behind it changed.  poison: after every slice, everything outside the ONCE and
+    KEEP regions is overwritten with NaN (what recycled memory may hold by the time a later slice reads it)."""
     assert plan.dtype == N.TNC_C64
     arena = np.zeros(plan.workspace_bytes // 8, dtype=np.complex64)
     out = np.zeros(int(np.prod(plan.out_shape)) if plan.out_shape else 1, dtype=np.complex64)
@@ -117,7 +140,16 @@ def run_plan(plan, leaf_blob, slice_ids):
 
     for kind, rec in plan.ops[N.TNC_PHASE_ONCE]:
         run(kind, rec, 0)
+    deps = slice_deps(plan) if reuse else None
+    prev = None
     for sid in slice_ids:
-        for kind, rec in plan.ops[N.TNC_PHASE_SLICE]:
+        first = prev is None
+        for n, (kind, rec) in enumerate(plan.ops[N.TNC_PHASE_SLICE]):
+            if reuse and not first and kind in ("einsum", "permute") and not (deps[n] & (int(sid) ^ prev)):
+                continue
             run(kind, rec, int(sid))
+        prev = int(sid)
+        if poison:
+            lo, hi = plan.recycled_range
+            arena[lo // 8: hi // 8] = np.nan
     return out.reshape(plan.out_shape)

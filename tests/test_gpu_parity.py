@@ -238,6 +238,64 @@ def test_cuda_graph_replay_of_the_slice_phase(dev, name):
     assert graph.last_launches > 0
 
 
+@pytest.mark.parametrize("name,ranges", [
+    ("n12_sparse64_sc9", [(0, 256), (3, 41), (254, 256)]),
+    ("n12_sparse100_sc8_own", [(0, 256), (17, 18), (100, 133)]),
+    ("n12_sparse256c_sc10", None),
+    ("n30_sparse64_sc26", [(0, 4), (1, 3)]),
+    ("n53_m12_sparse1024", [(0, 64), (1000, 1037)]),
+])
+def test_slice_reuse_is_bit_identical(dev, name, ranges):
+    """TNC_OPT_SLICE_REUSE: within one execute call a step is contracted again only when a sliced bond behind it
+    changed from the previous slice id.  Every range must give bit for bit what contracting every step for every
+    slice gives (same kernels, same operands, same accumulation order) -- also with tensor-core steps whose operand
+    scale word was reduced by a producer that did NOT run again."""
+    from artensor_b200 import PlanOptions, ContractionPlan
+    case, exp, sim = sim_from(name)
+    shapes = {k: tuple(v.shape) for k, v in case.leaves.items()}
+    mk = lambda r: ContractionPlan(case.scheme, shapes, case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
+                                   slicing_indices=case.slicing_indices(), options=PlanOptions(slice_reuse=r, cuda_graph=False))
+    full, reuse = mk(False), mk(True)
+    assert reuse.slice_reuse and not full.slice_reuse
+    blob = full.pack_leaves({k: v.to(dev) for k, v in case.leaves.items()})
+    st = torch.cuda.current_stream().cuda_stream
+    n = full.n_slices
+    wf = torch.empty(full.workspace_bytes, dtype=torch.uint8, device=dev)
+    wr = torch.empty(reuse.workspace_bytes, dtype=torch.uint8, device=dev)
+    for lo, hi in (ranges or [(0, n)]):
+        outs = []
+        for plan, ws in ((full, wf), (reuse, wr)):
+            ws.fill_(0xff)                                  # whatever the workspace held must not matter (NaN patterns)
+            out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
+            plan.execute(blob, out, lo, hi, ws, st)
+            torch.cuda.synchronize()
+            outs.append((out, plan.last_launches))
+        assert torch.equal(outs[0][0], outs[1][0]), f"slices [{lo}, {hi})"
+        if name.startswith("n53") and hi - lo >= 8:
+            # (tiny n12 steps run as chains of steps with IDENTICAL dependencies under reuse: more, smaller launches)
+            assert outs[1][1] < 0.7 * outs[0][1], "reuse skipped nothing"
+
+
+def test_slice_reuse_with_optimised_slice_order(dev):
+    """`optimize_slice_order` renames the slices (another bond per slice-id bit) but not their set: the sum over all
+    of them stays the reference's, and slice_reuse on the new order still equals full recomputation bit for bit
+    while launching far fewer kernels."""
+    from artensor_b200 import PlanOptions
+    case, exp, sim = sim_from("n12_sparse64_sc9")
+    want = exp["per_slice_c128"].sum(axis=0).reshape(exp["shape"])
+    sim.plan_options = PlanOptions(slice_reuse=True, cuda_graph=False)
+    before = list(sim.slicing_bonds)
+    model = sim.optimize_slice_order()
+    assert sorted(sim.slicing_bonds) == sorted(before) and model["amortised_s"] <= model["amortised_before_s"]
+    got = sim.contraction(device=dev)
+    launches = sim.plan().last_launches
+    assert_amplitudes_close(got.cpu().numpy(), want)
+    sim.plan_options = PlanOptions(slice_reuse=False, cuda_graph=False)
+    sim._plan_cache.clear()
+    again = sim.contraction(device=dev)
+    assert torch.equal(got, again)
+
+
 def test_native_errors_are_raised_not_fatal(dev):
     from artensor_b200 import _native as N
     case, _, sim = sim_from("n12_sparse64_sc9")

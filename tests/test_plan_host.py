@@ -54,6 +54,51 @@ def test_slice_sum_and_hoisting(name):
         assert np.abs(got - want).max() / np.abs(want).max() < 5e-6
 
 
+@pytest.mark.parametrize("hoist", [True, False])
+@pytest.mark.parametrize("name", ["n12_sparse64_sc9", "n12_sparse256c_sc10", "n12_sparse100_sc8_own"])
+def test_slice_reuse_is_bit_identical_to_recomputing_every_slice(name, hoist):
+    """PlanOptions.slice_reuse: over a range of consecutive slice ids a step runs again only when a sliced bond
+    behind it changed.  The emulator follows the library's rule (dependencies derived from the leaf records), and
+    overwrites all recycled memory with NaN after every slice: the sum must still be bit-identical to running every
+    operation for every slice -- i.e. every result that is read in a later slice sits in the KEEP region."""
+    case, _ = load_golden(name)
+    n = 1 << len(case.slicing_bonds)
+    full = make_plan(case, options=PlanOptions(hoist=hoist))
+    plan = make_plan(case, options=PlanOptions(hoist=hoist, slice_reuse=True))
+    assert plan.slice_reuse and plan.keep_bytes > 0 and plan.workspace_bytes >= full.workspace_bytes
+    deps = emulate.slice_deps(plan)
+    steps = [st for st in plan.op_steps[1] if st is not None]
+    assert sum(1 for d in deps if d != (1 << plan.n_sliced) - 1) > len(steps) // 4     # there IS something to reuse
+    blob = plan.pack_leaves(case.leaves).numpy()
+    for lo, hi in [(0, min(n, 24)), (5, 14), (n - 3, n)]:
+        want = emulate.run_plan(full, blob, range(lo, hi))
+        got = emulate.run_plan(plan, blob, range(lo, hi), reuse=True, poison=True)
+        assert np.array_equal(got, want), f"slices [{lo}, {hi})"
+
+
+def test_slice_reuse_layout_check_of_the_library():
+    """tnc_plan_finalize checks what TNC_OPT_SLICE_REUSE asks of the layout on the host, before its first CUDA
+    call: the planner's layout passes it (on a machine without a GPU finalize then fails in cudaMalloc: status
+    CUDA), the layout of a plan made WITHOUT the option, executed with it, is refused (status INVALID)."""
+    import ctypes as C
+    import torch
+    from artensor_b200 import _native as N
+    case, _ = load_golden("n12_sparse64_sc9")
+    shapes = {k: tuple(v.shape) for k, v in case.leaves.items()}
+
+    def finalize_status(layout_reuse):
+        plan = make_plan(case, options=PlanOptions(slice_reuse=layout_reuse))
+        plan.slice_reuse = True                  # the option the library sees
+        try:
+            plan._build_native(plan.ops)
+        except N.NativeError as e:
+            return e.status
+        return 0
+    ok = finalize_status(True)
+    assert ok == (0 if torch.cuda.is_available() else 2)
+    assert finalize_status(False) == 1
+
+
 def test_work_summary_counts():
     case, _ = load_golden("n12_sparse64_sc9")
     w = make_plan(case).work_summary()

@@ -1,0 +1,81 @@
+"""Cross-slice reuse (PlanOptions.slice_reuse, TNC_OPT_SLICE_REUSE) measured on one GPU: seconds per slice over ranges
+of R consecutive slice ids in ONE execute call, reference bit order and the reuse-optimised order
+(TensorNetworkSimulation.optimize_slice_order), against contracting every step for every slice.
+    python tools/reuse_bench.py n53_m20_sparse1024 [--ranges 2,8,64,512] [--check 4]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from artensor_b200 import TensorNetworkSimulation, PlanOptions, load_case   # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("case")
+    ap.add_argument("--ranges", default="2,8,64,512")
+    ap.add_argument("--check", type=int, default=4, help="slices compared bit for bit with full recomputation")
+    ap.add_argument("--begin", type=int, default=0)
+    a = ap.parse_args()
+    case = load_case(os.path.join(ROOT, "tests", "golden", f"{a.case}.case.gz"))
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+
+    def timed(plan, blob, ws, lo, hi):
+        out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        plan.execute(blob, out, lo, hi, ws, st)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out, plan.last_launches
+
+    for order in ("reference", "optimised"):
+        sim = TensorNetworkSimulation.from_case(case)
+        model = None
+        if order == "optimised":
+            sim.plan_options = PlanOptions(slice_reuse=True)
+            model = sim.optimize_slice_order()
+        plans = {}
+        for reuse in (False, True):
+            sim.plan_options = PlanOptions(slice_reuse=reuse, cuda_graph=False)
+            sim._plan_cache.clear()
+            plans[reuse] = sim.plan()
+        n = plans[True].n_slices
+        blob = plans[True].pack_leaves(case.leaves, device=dev)
+        ws = torch.empty(max(p.workspace_bytes for p in plans.values()), dtype=torch.uint8, device=dev)
+        print(f"{a.case} [{order} bit order]: {n.bit_length() - 1} sliced bonds, workspace {plans[False].workspace_bytes / 2**30:.2f} GiB "
+              f"-> {plans[True].workspace_bytes / 2**30:.2f} GiB with reuse" + (f"; model {model}" if model else ""), flush=True)
+        timed(plans[False], blob, ws, a.begin, a.begin + 1)                      # warm-up
+        ms_full, _, l_full = timed(plans[False], blob, ws, a.begin, a.begin + 2)
+        print(f"   every step for every slice: {ms_full / 2:9.3f} ms per slice, {l_full // 2} launches per slice", flush=True)
+        if a.check:
+            hi = min(n, a.begin + a.check)
+            _, want, _ = timed(plans[False], blob, ws, a.begin, hi)
+            _, got, _ = timed(plans[True], blob, ws, a.begin, hi)
+            same = bool(torch.equal(want, got))
+            print(f"   slices [{a.begin}, {hi}) with reuse: bit-identical = {same}", flush=True)
+            assert same
+        for R in [int(x) for x in a.ranges.split(",")]:
+            hi = min(n, a.begin + R)
+            timed(plans[True], blob, ws, a.begin, min(hi, a.begin + 2))
+            ms, _, launches = timed(plans[True], blob, ws, a.begin, hi)
+            per = ms / (hi - a.begin)
+            print(f"   reuse, {hi - a.begin:5d} consecutive slices in one call: {ms:10.2f} ms = {per:9.3f} ms per slice "
+                  f"({1e3 / per:8.1f} slices/s), {launches / (hi - a.begin):7.1f} launches per slice", flush=True)
+            rows.append({"order": order, "slices": hi - a.begin, "ms": ms, "ms_per_slice": per, "launches": launches,
+                         "ms_per_slice_full": ms_full / 2})
+        del ws, blob
+        torch.cuda.empty_cache()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump({"case": a.case, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", f"reuse_{a.case}.json"), "w"))
+
+
+if __name__ == "__main__":
+    main()
