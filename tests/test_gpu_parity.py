@@ -276,6 +276,28 @@ def test_slice_reuse_is_bit_identical(dev, name, ranges):
             assert outs[1][1] < 0.7 * outs[0][1], "reuse skipped nothing"
 
 
+def test_slice_reuse_n53_m20_bit_identical(dev):
+    """The bench tree (fat tensor-core GEMM whose operands and operand scales are kept across slices): three
+    consecutive slices with reuse == the same three with every step contracted, bit for bit; and slice 0 still
+    meets the reference's recorded amplitudes."""
+    from artensor_b200 import PlanOptions
+    case, exp, sim = sim_from("n53_m20_sparse1024")
+    sim.plan_options = PlanOptions(slice_reuse=True)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if sim.plan().workspace_bytes > free - (8 << 30):
+        pytest.skip(f"needs {sim.plan().workspace_bytes >> 30} GiB of free HBM")
+    got = sim.contraction(device=dev, slice_range=(0, 3))
+    first = sim.contraction(device=dev, slice_range=(0, 1))
+    from artensor_b200 import contraction as _c
+    _c.release_workspaces()
+    sim.plan_options = PlanOptions(slice_reuse=False)
+    want = sim.contraction(device=dev, slice_range=(0, 3))
+    assert torch.equal(got, want)
+    k = int(np.where(exp["slice_ids"] == 0)[0][0])
+    assert_amplitudes_close(first.cpu().numpy().reshape(-1), exp["per_slice_c64"][k])
+    _c.release_workspaces()
+
+
 def test_slice_reuse_with_optimised_slice_order(dev):
     """`optimize_slice_order` renames the slices (another bond per slice-id bit) but not their set: the sum over all
     of them stays the reference's, and slice_reuse on the new order still equals full recomputation bit for bit

@@ -98,6 +98,15 @@ def main():
                 plan = ContractionPlan(sim.scheme, {i: tuple(t.shape) for i, t in sim.tensors.items()}, sim.pattern == "sparse",
                                        slicing_bonds=sim.slicing_bonds, slicing_indices=sim.slicing_indices, build_native=False)
                 t_slice, t_once, split = price(plan)
+                # the same tree under cross-slice reuse: sliced bonds re-ordered, KEEP region
+                from artensor_b200 import PlanOptions
+                order = plan.reuse_bond_order()
+                reuse_model = plan.reuse_summary(order)
+                bonds = [sim.slicing_bonds[i] for i in order]
+                from artensor_b200.simulation import slicing_dims
+                rplan = ContractionPlan(sim.scheme, {i: tuple(t.shape) for i, t in sim.tensors.items()}, sim.pattern == "sparse",
+                                        slicing_bonds=bonds, slicing_indices=slicing_dims(sim.tensors, sim.tensor_bonds, bonds),
+                                        options=PlanOptions(slice_reuse=True), build_native=False)
                 work = plan.work_summary()
                 S = len(sim.slicing_bonds)
                 name = f"{a.circuit}_sc{sc}_a{int(alpha)}_s{seed}"
@@ -106,6 +115,8 @@ def main():
                      "bytes_per_slice": work["exec_bytes_per_slice"], "workspace_gib": plan.workspace_bytes / 2 ** 30,
                      "predicted_ms_per_slice": 1e3 * t_slice, "predicted_split_ms": {k: 1e3 * v for k, v in split.items()},
                      "predicted_full_task_seconds": (2.0 ** S) * t_slice, "log2_full_task_seconds": S + float(np.log2(t_slice)),
+                     "reuse_modelled_ms_per_slice": 1e3 * reuse_model["amortised_s"], "reuse_workspace_gib": rplan.workspace_bytes / 2 ** 30,
+                     "reuse_full_task_seconds": (2.0 ** S) * reuse_model["amortised_s"],
                      "search_seconds": time.time() - t0}
                 print(json.dumps(r), flush=True)
                 results.append(r)
@@ -119,6 +130,9 @@ def main():
                     json.dump(results, f, indent=1)
     best = min(results, key=lambda r: r["predicted_full_task_seconds"])
     print("best:", json.dumps(best))
+    fits = [r for r in results if r["reuse_workspace_gib"] <= 170]
+    if fits:
+        print("best with cross-slice reuse (workspace <= 170 GiB):", json.dumps(min(fits, key=lambda r: r["reuse_full_task_seconds"])))
 
 
 if __name__ == "__main__":
