@@ -377,19 +377,24 @@ __global__ void __launch_bounds__(kThreads) accum_kernel(AccumParams p) {
 
 }  // namespace
 
+// Whether the generic path runs a step with the row-dot kernel (many rows, a long contraction, <= 64 outputs per
+// row, no shared kept modes: one CTA per row whose threads split K).  Such a step is never made part of a chain
+// launch (tnc_plan_finalize): it is summed in the same order however the steps around it are grouped.
+bool simt_uses_rowdot(int rank_c, int kb, int64_t total, int n_m, int n_n, int n_h) {
+    static const bool no_rowdot = knob("TNC_NO_ROWDOT") != nullptr;      // measurement aid
+    return !no_rowdot && rank_c <= 6 && kb >= 7 && (total >> rank_c) >= 32 && n_h == 0 && rowdot_shape(n_m, n_n);
+}
+
 int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
     if (p.total <= 0) return TNC_OK;
-    // many rows, a long contraction, <= 16 outputs per row, no shared kept modes: one CTA per row
-    static const bool no_rowdot = knob("TNC_NO_ROWDOT") != nullptr;      // measurement aid
-    if (!no_rowdot && dtype == TNC_C64 && p.rank_c <= 6 && p.kb >= 7 && (p.total >> p.rank_c) >= 32) {
-        int nm = 0, nn = 0;
-        bool plain = true;
+    {
+        int nm = 0, nn = 0, nh = 0;
         for (int q = 0; q < p.rank_c; ++q) {
-            if (p.c2a[q] >= 0 && p.c2b[q] >= 0) plain = false;
+            if (p.c2a[q] >= 0 && p.c2b[q] >= 0) ++nh;
             else if (p.c2a[q] >= 0) ++nm;
             else ++nn;
         }
-        if (plain && rowdot_shape(nm, nn)) {
+        if (dtype == TNC_C64 && simt_uses_rowdot(p.rank_c, p.kb, p.total, nm, nn, nh)) {
             const int grid = (int)std::min<int64_t>(p.total >> p.rank_c, (int64_t)sm_count() * 16);
             switch (nm) {
                 case 0: launch_rowdot_n<0>(p, nn, grid, s); break;

@@ -545,6 +545,7 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t arena_bytes) {
     auto chainable = [&](const Op& op) {
         if (no_chain || plan->dtype != TNC_C64 || op.kind != OP_EINSUM || op.e.algo != TNC_ALGO_SIMT) return false;
         const int64_t total = (int64_t)op.e.nb << op.e.c.rank;
+        if (simt_uses_rowdot(op.e.c.rank, op.e.n_k, total, op.e.n_m, op.e.n_n, op.e.n_h)) return false;   // own kernel, own summation order
         return total <= kChainMaxOutputs && (total << op.e.n_k) <= kChainMaxMacs;
     };
     for (int ph = 0; ph < 2; ++ph) {

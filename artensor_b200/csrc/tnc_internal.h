@@ -62,6 +62,7 @@ struct SimtEinsumParams {
     int8_t c2b[TNC_MAX_BITS];
 };
 int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s);
+bool simt_uses_rowdot(int rank_c, int kb, int64_t total, int n_m, int n_n, int n_h);
 
 // A run of consecutive tiny generic steps executed by ONE launch (one CTA walks the run, a block
 // barrier between steps) instead of one ~6 us launch per step.  Records live in the plan's device

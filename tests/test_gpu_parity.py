@@ -1025,6 +1025,33 @@ def test_n53_m20_tuned_tree_sc31_vs_reference(dev):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("name,n_sliced", [("n53_m20_sparse1024_sc30_s2", 42), ("n53_m20_sparse1024_sc31_s2", 40)])
+def test_n53_m20_trees_picked_for_slice_reuse(dev, name, n_sliced):
+    """SURVEY.md 8-f4 x 8-f2: trees of the reference's annealer picked by their AMORTISED cost under cross-slice
+    reuse (tools/order_search_sweep.py prices every tree with artensor_b200's step-time model and the reuse bit
+    order).  One slice against the recorded output -- sc30_s2: the REFERENCE executor run in the
+    build container; sc31_s2 (2^31-amplitude intermediates, 110 GiB arena): the CPU oracle run on the GPU box's
+    host, where the same slice was also checked against the oracle in complex128 (profiles/r02_slice_reuse.txt) --
+    and three consecutive slices of the reuse-ordered plan, one call against one call per slice, bit for bit."""
+    from artensor_b200 import PlanOptions, contraction as _c
+    case, exp, sim = sim_from(name)
+    assert len(case.slicing_bonds) == n_sliced
+    free, _ = torch.cuda.mem_get_info(dev)
+    sim.plan_options = PlanOptions(slice_reuse=True)
+    if sim.plan().workspace_bytes > free - (6 << 30):
+        pytest.skip(f"needs {sim.plan().workspace_bytes >> 30} GiB of free HBM")
+    s = int(exp["slice_ids"][0])
+    got = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()
+    assert_amplitudes_close(got, exp["per_slice_c64"][0])
+    sim.optimize_slice_order()
+    one_call = sim.contraction(device=dev, slice_range=(5, 8))
+    per_slice = sum(sim.contraction(device=dev, slice_range=(k, k + 1)) for k in range(5, 8))
+    assert torch.equal(one_call, sim.contraction(device=dev, slice_range=(5, 8)))
+    assert_amplitudes_close(one_call.cpu().numpy(), per_slice.cpu().numpy(), rtol=2e-6)   # another summation order of 3 terms
+    _c.release_workspaces()
+    torch.cuda.empty_cache()
+
+
 def test_n53_m20_tuned_tree_sc32_two_kernel_paths_agree(dev):
     """The sc_target 32 tree of the same sweep (42 sliced bonds, 2^32-amplitude intermediates, a
     128 GiB arena: what 180 GB of HBM are for) -- an EXPERIMENT, not a parity claim: no host can
