@@ -30,6 +30,10 @@ Timed regions
           the GPU arm's `cpu_baseline` quotes that measurement when it finds it on the same host,
           else a bounded timing model (every step's einsum on synthetic operands, large steps on
           sub-blocks), which is also printed beside the true slice as a cross-check.
+  slice_reuse  (extra object, NOT the headline) the same tree with PlanOptions.slice_reuse and the sliced bonds
+          re-ordered for it: `--reuse-slices` consecutive slice ids per GPU in ONE call through the public API, a
+          step contracted again only when a sliced bond behind it changed (bit-identical amplitudes).  `value` and
+          `e2e` contract every step for every slice, as the reference's loop does.
 """
 import argparse
 import json
@@ -346,7 +350,8 @@ def bench_config(workload, plan, slices_per_step):
     return {"workload": workload, "slices_per_step_per_gpu": slices_per_step, "sliced_bonds": plan.n_sliced,
             "total_slices_of_task": f"2^{plan.n_sliced}",
             "amplitudes_per_slice": int(math.prod(plan.out_shape)),
-            "scheme_steps": work["steps"], "l2": "working set >> L2 (multi-GiB intermediates), no flush"}
+            "scheme_steps": work["steps"], "l2": "working set >> L2 (multi-GiB intermediates), no flush",
+            "every_step_for_every_slice": True}      # the reference's loop; cross-slice reuse only in `slice_reuse`
 
 
 def plan_of(case, tc_min_flops, build_native=True):
