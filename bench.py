@@ -659,16 +659,26 @@ def main():
     reuse = None
     if not args.no_reuse and plan.n_sliced >= 2:
         try:
-            rsim = TensorNetworkSimulation.from_case(case)
-            rsim.plan_options = PlanOptions(**dict(opt_kw, slice_reuse=True, cuda_graph=False))
-            model = rsim.optimize_slice_order()
-            rplan = rsim.plan()
-            ws = None
-            C.release_workspaces()
-            torch.cuda.empty_cache()
-            free_b, _ = torch.cuda.mem_get_info(dev)
-            if rplan.workspace_bytes > free_b - (2 << 30):
-                raise RuntimeError(f"workspace with reuse {rplan.workspace_bytes >> 30} GiB > free HBM {free_b >> 30} GiB")
+            # set-up (no collectives): every rank then votes, and the collective part below runs on all ranks or on none
+            problem = None
+            try:
+                rsim = TensorNetworkSimulation.from_case(case)
+                rsim.plan_options = PlanOptions(**dict(opt_kw, slice_reuse=True, cuda_graph=False))
+                model = rsim.optimize_slice_order()
+                rplan = rsim.plan()
+                ws = None
+                C.release_workspaces()
+                torch.cuda.empty_cache()
+                free_b, _ = torch.cuda.mem_get_info(dev)
+                if rplan.workspace_bytes > free_b - (2 << 30):
+                    problem = f"workspace with reuse {rplan.workspace_bytes >> 30} GiB > free HBM {free_b >> 30} GiB"
+            except Exception as exc:
+                problem = str(exc)
+            vote = torch.tensor([0.0 if problem is None else 1.0], device=dev)
+            if world > 1:
+                dist.all_reduce(vote, op=dist.ReduceOp.MAX)
+            if vote.item() > 0:
+                raise RuntimeError(problem or "another rank could not set up the reuse plan")
             R = min(args.reuse_slices, rplan.n_slices // world)
             rhost = {k: v.pin_memory() for k, v in case.leaves.items()}
             grp = True if world > 1 else None
