@@ -1025,12 +1025,13 @@ def test_n53_m20_tuned_tree_sc31_vs_reference(dev):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("name,n_sliced", [("n53_m20_sparse1024_sc30_s2", 42), ("n53_m20_sparse1024_sc31_s2", 40)])
+@pytest.mark.parametrize("name,n_sliced", [("n53_m20_sparse1024_sc30_s2", 42), ("n53_m20_sparse1024_sc31_s2", 40),
+                                           ("n53_m20_sparse1024_sc31_s20", 37)])
 def test_n53_m20_trees_picked_for_slice_reuse(dev, name, n_sliced):
     """SURVEY.md 8-f4 x 8-f2: trees of the reference's annealer picked by their AMORTISED cost under cross-slice
     reuse (tools/order_search_sweep.py prices every tree with artensor_b200's step-time model and the reuse bit
-    order).  One slice against the recorded output -- sc30_s2: the REFERENCE executor run in the
-    build container; sc31_s2 (2^31-amplitude intermediates, 110 GiB arena): the CPU oracle run on the GPU box's
+    order).  One slice against the recorded output -- sc30_s2, sc31_s20: the REFERENCE executor run
+    in the build container; sc31_s2 (2^31-amplitude intermediates, 110 GiB arena): the CPU oracle run on the GPU box's
     host, where the same slice was also checked against the oracle in complex128 (profiles/r02_slice_reuse.txt) --
     and three consecutive slices of the reuse-ordered plan, one call against one call per slice, bit for bit."""
     from artensor_b200 import PlanOptions, contraction as _c
