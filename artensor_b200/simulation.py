@@ -133,6 +133,67 @@ class TensorNetworkSimulation(_Base):
             self.permute_dims = None
         self._plan_cache.clear()
 
+    _PREPARED = ("ctree", "scheme", "output_bonds", "slicing_bonds", "slicing_indices", "permute_dims",
+                 "bitstrings_sorted", "tensor_contraction_func", "_sc_target", "shard_bonds")
+
+    def prepare_contraction_sweep(self, sc_targets=(30, 31), alphas=(32.0, 96.0), start_seeds=(0,), trials=8, iters=4,
+                                  slicing_repeat=1, reuse=None, max_workspace_bytes=170 << 30, verbose=False):
+        """the reference's order search (`prepare_contraction`, unchanged) run over a grid of
+        sc_target x alpha x start seed, every tree priced with this executor's own step-time model
+        (`ContractionPlan.step_seconds_model`: tensor-bound steps at the measured useful rate of the split product,
+        the rest at the streaming kernels' HBM rate), and the tree with the smallest modelled time for ALL its
+        2^S slices kept.  The annealer scores trees by `log10(alpha 10^mc + 10^tc)` of ONE slice
+        (order_finder.py:11-16) and its result depends strongly on the seeds (n53 m20: 35 ... 53 sliced bonds over ten
+        settings of one schedule), so choosing among its outcomes with the machine's own cost is worth orders of
+        magnitude.  reuse: price the amortised cost under cross-slice reuse (default: whether
+        `plan_options.slice_reuse` is set); trees whose workspace exceeds `max_workspace_bytes` are skipped.
+        Returns the priced candidates, best first; the simulation is left prepared with the best one."""
+        _need_base()
+        reuse = bool(self.plan_options.slice_reuse) if reuse is None else bool(reuse)
+        from dataclasses import replace
+        options = replace(self.plan_options, slice_reuse=reuse)
+        results, best, best_state = [], None, None
+        for sc in sc_targets:
+            for alpha in alphas:
+                for seed in start_seeds:
+                    self.prepare_contraction(sc_target=sc, trials=trials, iters=iters, slicing_repeat=slicing_repeat,
+                                             start_seed=seed, alpha=alpha)
+                    order = None
+                    probe = _c.ContractionPlan(self.scheme, {i: tuple(self.tensors[i].shape) for i in self._ids()},
+                                               self.pattern == 'sparse', slicing_bonds=self.slicing_bonds,
+                                               slicing_indices=self.slicing_indices, dtype="c64", options=options,
+                                               build_native=False)
+                    if reuse:
+                        order = probe.reuse_bond_order()
+                        bonds = [self.slicing_bonds[i] for i in order]
+                        per_slice = probe.reuse_summary(order)["amortised_s"]
+                        probe = _c.ContractionPlan(self.scheme, {i: tuple(self.tensors[i].shape) for i in self._ids()},
+                                                   self.pattern == 'sparse', slicing_bonds=bonds,
+                                                   slicing_indices=slicing_dims(self.tensors, self.tensor_bonds, bonds),
+                                                   dtype="c64", options=options, build_native=False)
+                    else:
+                        per_slice = probe.reuse_summary()["full_s"]
+                    r = {"sc_target": sc, "alpha": alpha, "start_seed": seed, "sliced_bonds": probe.n_sliced,
+                         "seconds_per_slice": per_slice, "task_seconds": per_slice * 2.0 ** probe.n_sliced,
+                         "workspace_bytes": probe.workspace_bytes, "fits": probe.workspace_bytes <= max_workspace_bytes}
+                    if verbose:
+                        print(r, flush=True)
+                    results.append(r)
+                    if r["fits"] and (best is None or r["task_seconds"] < best["task_seconds"]):
+                        best = r
+                        best_state = {k: getattr(self, k) for k in self._PREPARED if hasattr(self, k)}
+                        best_state["_bit_order"] = order
+        if best is None:
+            raise RuntimeError("no tree of the sweep fits max_workspace_bytes")
+        for k, v in best_state.items():
+            if k != "_bit_order":
+                setattr(self, k, v)
+        if best_state["_bit_order"] is not None:
+            self.slicing_bonds = [self.slicing_bonds[i] for i in best_state["_bit_order"]]
+            self.slicing_indices = slicing_dims(self.tensors, self.tensor_bonds, self.slicing_bonds)
+        self._plan_cache.clear()
+        return sorted(results, key=lambda r: (not r["fits"], r["task_seconds"]))
+
     def update_scheme(self, sc_target=30, bitstrings=[]):
         """simulation.py:79-88.  The tree is compiled by artensor_b200.scheme (layout-friendly mode
         orders, reproducible strings, chunking that covers every row: SURVEY.md 4.3-B2/B5) unless

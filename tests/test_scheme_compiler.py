@@ -202,6 +202,41 @@ def test_drop_in_simulation_uses_own_compiler_and_lowers():
         sim.update_scheme(9, bits)
 
 
+@pytest.mark.parametrize("reuse", [False, True])
+def test_prepare_contraction_sweep_keeps_the_cheapest_tree(reuse):
+    """SURVEY.md 8-f4 as an API: the reference's order search over a grid of settings, every tree priced with this
+    package's step-time model (for all 2^S slices; amortised under cross-slice reuse when asked), the cheapest kept.
+    The simulation must be left prepared with exactly that tree -- and contract to the reference's amplitudes."""
+    ref = reference()
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emulate
+    from artensor_b200 import TensorNetworkSimulation, PlanOptions
+    from artensor_b200.backend import ContractionPlan
+    bits = random_bitstrings(12, 64, 1)
+    sim = TensorNetworkSimulation.from_circuit_file(N12, bits)
+    sim.plan_options = PlanOptions(slice_reuse=reuse)
+    res = sim.prepare_contraction_sweep(sc_targets=(8, 9), alphas=(32.0,), start_seeds=(0, 3), trials=2, iters=3)
+    assert len(res) == 4 and all(r["fits"] for r in res)
+    assert [r["task_seconds"] for r in res] == sorted(r["task_seconds"] for r in res)
+    best = res[0]
+    assert len(sim.slicing_bonds) == best["sliced_bonds"] and sim._sc_target == best["sc_target"]
+    plan = ContractionPlan(sim.scheme, {i: tuple(sim.tensors[i].shape) for i in sim._ids()}, True,
+                           slicing_bonds=sim.slicing_bonds, slicing_indices=sim.slicing_indices,
+                           options=sim.plan_options, build_native=False)
+    model = plan.reuse_summary()
+    per_slice = model["amortised_s"] if reuse else model["full_s"]
+    assert abs(per_slice - best["seconds_per_slice"]) <= 1e-9 * per_slice       # the kept tree (and bit order) is the priced one
+    got = emulate.run_plan(plan, plan.pack_leaves(sim.tensors).numpy(), range(plan.n_slices), reuse=reuse, poison=reuse).reshape(-1)
+    mine = dict(zip(sim.bitstrings_sorted, got.tolist()))
+    rsim = prepared("rand64", bits, 9)
+    want = run_on_reference_executor(ref, rsim, rsim.scheme, True).reshape(-1).tolist()
+    ref_amp = dict(zip(rsim.bitstrings_sorted, want))
+    scale = max(abs(v) for v in ref_amp.values())
+    assert max(abs(mine[k] - ref_amp[k]) for k in ref_amp) < 5e-6 * scale
+    with pytest.raises(RuntimeError):
+        sim.prepare_contraction_sweep(sc_targets=(9,), alphas=(32.0,), start_seeds=(0,), trials=1, iters=1, max_workspace_bytes=16)
+
+
 # ------------------------------------------------------------------------------------------------
 # host logic that needs no reference
 # ------------------------------------------------------------------------------------------------
