@@ -19,6 +19,7 @@ TNC_ALGO_SIMT, TNC_ALGO_TC, TNC_ALGO_STEM, TNC_ALGO_SKINNY = 0, 1, 2, 3
 TNC_ROWS_NONE, TNC_ROWS_IDENTITY = -1, -2
 TNC_EINSUM_OUTER_ROWS = 1
 TNC_EINSUM_OUTER_PAIRS = 2
+TNC_EINSUM_RUN_WITH_READER = 4
 TNC_TC_3XTF32, TNC_TC_3XF16, TNC_TC_F16 = 0, 1, 2
 TNC_OPT_TC_PRECISION, TNC_OPT_CUDA_GRAPH, TNC_OPT_FUSE_AMAX, TNC_OPT_SLICE_REUSE = 0, 1, 2, 3
 TC_PRECISIONS = {"3xtf32": TNC_TC_3XTF32, "3xf16": TNC_TC_3XF16, "f16": TNC_TC_F16}

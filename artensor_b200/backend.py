@@ -131,6 +131,11 @@ class PlanOptions:
     # on a few of the sliced bonds only.  Results are bit-identical; intermediates whose consumer depends on more
     # bonds than they do keep a region of their own for the whole call (a larger workspace).
     slice_reuse: bool = False
+    # Upper bound (bytes) for the KEEP region of slice_reuse, None = unbounded.  When the results that would have to be
+    # kept exceed it, the planner TIES some of them to their reader instead (TNC_EINSUM_RUN_WITH_READER): such a step is
+    # contracted again whenever its reader is, its result recycles -- less memory, more recomputation; the ties that
+    # cost the least modelled time per byte freed are chosen first.
+    keep_budget_bytes: Optional[int] = None
 
     def __post_init__(self):
         if self.tc_precision not in N.TC_PRECISIONS:
@@ -336,6 +341,43 @@ class ContractionPlan:
             slot_producer[st.i] = idx
             del slot_deps[st.j]
             slot_producer.pop(st.j, None)
+        # per step, before anything is allocated: operand roles, phase, algorithm
+        pre = []
+        self.step_phase, self.step_algo = [], []
+        for idx, orig in enumerate(self.steps):
+            st = orig
+            is_swapped = bool(self.options.swap_operands and self.dtype == N.TNC_C64 and should_swap(orig))
+            if is_swapped:
+                st = swapped(orig)
+            phase = N.TNC_PHASE_SLICE if (self.step_deps[idx] or not self.options.hoist) else N.TNC_PHASE_ONCE
+            algo = N.TNC_ALGO_SIMT
+            if self.dtype == N.TNC_C64:
+                o = self.options
+                if st.a.numel >= o.skinny_min_elems and skinny_eligible(st, o.tc_precision, o.skinny_min_n):
+                    algo = N.TNC_ALGO_SKINNY
+                elif st.flops >= o.tc_min_flops and st.flops >= o.tc_min_intensity * st.bytes_c64 and tc_eligible(st, o.tc_precision):
+                    algo = N.TNC_ALGO_TC
+                elif st.c.numel >= o.stem_min_elems and stem_eligible(st):
+                    algo = N.TNC_ALGO_STEM
+            pre.append((st, is_swapped, phase, algo))
+            self.step_phase.append(phase)
+            self.step_algo.append(algo)
+        # slice_reuse: when each step runs (run_deps: the sliced bonds whose change makes it run -- its own, or its
+        # reader's when it is tied to it) and which results must outlive a slice (kept)
+        self.step_tied = [False] * len(self.steps)
+        self.run_deps = list(self.step_deps)
+        consumer_of = [None] * len(self.steps)
+        prod = {}
+        for idx, st in enumerate(self.steps):
+            for t in (st.i, st.j):
+                if t in prod:
+                    consumer_of[prod[t]] = idx
+            prod[st.i] = idx
+            prod.pop(st.j, None)
+        self._consumer_of = consumer_of
+        kept = [False] * len(self.steps)
+        if reuse:
+            kept = self._plan_keep(consumer_of, every)
         # leaf blob layout (elements), in ascending tensor id order over the leaves the scheme uses
         self.leaf_order = sorted(self.leaf_info)
         self.leaf_src_offset = {}
@@ -357,39 +399,26 @@ class ContractionPlan:
             leaf_bufs[region].append((tid, buf))
 
         pending = []        # (phase, step, A, B, C, algo) in scheme order
-        self.step_phase, self.step_algo = [], []
         for idx, orig in enumerate(self.steps):
             A, B = bufs[orig.i], bufs[orig.j]
-            st = orig
-            if self.options.swap_operands and self.dtype == N.TNC_C64 and should_swap(orig):
-                st, A, B = swapped(orig), B, A
-            phase = N.TNC_PHASE_SLICE if (A.dependent or B.dependent) else N.TNC_PHASE_ONCE
-            algo = N.TNC_ALGO_SIMT
-            if self.dtype == N.TNC_C64:
-                o = self.options
-                if st.a.numel >= o.skinny_min_elems and skinny_eligible(st, o.tc_precision, o.skinny_min_n):
-                    algo = N.TNC_ALGO_SKINNY
-                elif st.flops >= o.tc_min_flops and st.flops >= o.tc_min_intensity * st.bytes_c64 and tc_eligible(st, o.tc_precision):
-                    algo = N.TNC_ALGO_TC
-                elif st.c.numel >= o.stem_min_elems and stem_eligible(st):
-                    algo = N.TNC_ALGO_STEM
+            st, is_swapped, phase, algo = pre[idx]
+            if is_swapped:
+                A, B = B, A
+            assert phase == (N.TNC_PHASE_SLICE if (A.dependent or B.dependent) else N.TNC_PHASE_ONCE)
             cpos = self._choose_layout(st, A, B, algo)
-            # slice_reuse: a result whose consumer depends on more sliced bonds is read again in later slices
-            # without being recomputed -- it gets memory nothing else is ever laid over (KEEP); a result whose
-            # consumer depends on the same bonds is recomputed whenever it is read and recycles as before
-            keep = reuse and phase == N.TNC_PHASE_SLICE and self.step_deps[idx] != consumer_deps[idx]
-            region = REGION_KEEP if keep else phase
+            # slice_reuse: a result whose reader runs more often than it does is read again in later slices
+            # without being recomputed -- it gets memory nothing else is ever laid over (KEEP); a result that
+            # runs exactly when its reader does is recomputed whenever it is read and recycles as before
+            region = REGION_KEEP if kept[idx] else phase
             o, sz = arenas[region].alloc(st.c.numel * self.elem_bytes)
-            Cb = Buf(region, o, sz, st.c, cpos, False, base, self.step_deps[idx])
+            Cb = Buf(region, o, sz, st.c, cpos, False, base, self.run_deps[idx])
             scratch = None
             if algo == N.TNC_ALGO_TC:
                 # packed operand panels live only while the step runs
                 so, ssz = arenas[phase].alloc(tc_scratch_bytes(st))
                 arenas[phase].release(so, ssz)
                 scratch = (so, ssz)
-            pending.append((phase, st, A, B, Cb, algo, scratch))
-            self.step_phase.append(phase)
-            self.step_algo.append(algo)
+            pending.append((phase, st, A, B, Cb, algo, scratch, self.step_tied[idx]))
             for old in (A, B):
                 # a buffer dies with its consumer unless it is a leaf (reloaded / kept) or a
                 # slice-invariant result consumed inside the slice loop (needed by every slice)
@@ -418,8 +447,10 @@ class ContractionPlan:
                 ops[phase].append(("leaves", [self._leaf_record(tid, b) for tid, b in leaf_bufs[phase]]))
         self.tables: List[np.ndarray] = []
         op_steps = {ph: [None] * len(ops[ph]) for ph in ops}     # Step behind each op (None: not an einsum)
-        for phase, st, A, B, Cb, algo, scratch in pending:
+        for phase, st, A, B, Cb, algo, scratch, tied in pending:
             rec = self._einsum_record(st, A, B, Cb, algo)
+            if tied:
+                rec.flags |= N.TNC_EINSUM_RUN_WITH_READER
             if scratch is not None:
                 rec.scratch_offset = base[phase] + scratch[0]
                 rec.scratch_bytes = scratch[1]
@@ -440,6 +471,73 @@ class ContractionPlan:
         self.op_steps = op_steps
         if self._build:
             self._build_native(ops)
+
+    def _plan_keep(self, consumer_of, every):
+        """slice_reuse: which step results must outlive a slice.  A step runs when a bond of its run_deps changed:
+        its own dependencies, or -- when it is TIED to its reader -- its reader's.  A result is KEPT (a region of its
+        own) when its reader runs on other occasions than it does (over consecutive slice ids: when the lowest
+        slice-id bits behind the two differ).  Without a budget nothing is tied.  With
+        `keep_budget_bytes`, while the kept results exceed it, the kept result whose tie costs the least modelled
+        time per byte is tied to its reader, together with the producers that ran in step with it (they keep
+        running in step with it, so they stay un-kept)."""
+        n = len(self.steps)
+        slice_phase = [ph == N.TNC_PHASE_SLICE for ph in self.step_phase]
+        size = [max(ALIGN, (st.c.numel * self.elem_bytes + ALIGN - 1) // ALIGN * ALIGN) for st in self.steps]   # as Arena.alloc rounds
+        producers = [[] for _ in range(n)]          # step-produced inputs of every step
+        for p, c in enumerate(consumer_of):
+            if c is not None:
+                producers[c].append(p)
+        cost = self.step_seconds_model()
+        bit = {b: self.n_sliced - 1 - b for b in range(self.n_sliced)}      # bond index -> slice-id bit
+
+        def run_deps(tied):
+            R = [None] * n
+            for idx in range(n - 1, -1, -1):
+                c = consumer_of[idx]
+                R[idx] = (R[c] if c is not None else every) if tied[idx] else self.step_deps[idx]
+            return R
+
+        def low(deps):
+            # going from slice id s - 1 to s flips the bits 0 .. ctz(s): a step runs exactly when its LOWEST bit is
+            # among them, so two steps run on the same slices iff their lowest bits agree (None: only in the first slice)
+            return min((bit[b] for b in deps), default=None)
+
+        def kept_of(R):
+            return [slice_phase[i] and low(R[i]) != low(R[consumer_of[i]] if consumer_of[i] is not None else every)
+                    for i in range(n)]
+
+        def amortised(R):
+            return sum(cost[i] * 2.0 ** -min(bit[b] for b in R[i]) for i in range(n) if slice_phase[i] and R[i])
+
+        tied = [False] * n
+        R = run_deps(tied)
+        kept = kept_of(R)
+        budget = self.options.keep_budget_bytes
+        while budget is not None and sum(size[i] for i in range(n) if kept[i]) > budget:
+            base_cost = amortised(R)
+            best = None
+            for c in range(n):
+                if not kept[c]:
+                    continue
+                trial = list(tied)
+                stack = [c]
+                while stack:                          # c and the producers that ran in step with it
+                    x = stack.pop()
+                    trial[x] = True
+                    stack.extend(p for p in producers[x] if slice_phase[p] and not kept[p] and not trial[p])
+                R2 = run_deps(trial)
+                k2 = kept_of(R2)
+                freed = sum(size[i] for i in range(n) if kept[i]) - sum(size[i] for i in range(n) if k2[i])
+                if freed <= 0:
+                    continue
+                score = (amortised(R2) - base_cost) / freed
+                if best is None or score < best[0]:
+                    best = (score, trial, R2, k2)
+            if best is None:
+                break
+            _, tied, R, kept = best
+        self.step_tied, self.run_deps = tied, R
+        return kept
 
     def _leaf_record(self, tid, buf: Buf):
         shp = self.full_leaf_shapes[tid]
@@ -677,7 +775,9 @@ class ContractionPlan:
         order = list(range(self.n_sliced)) if bond_order is None else list(bond_order)
         bit = {b: self.n_sliced - 1 - i for i, b in enumerate(order)}
         full = sum(c for c, ph in zip(cost, self.step_phase) if ph == N.TNC_PHASE_SLICE)
-        amortised = sum(c * 2.0 ** -min(bit[b] for b in d) for c, d in zip(cost, self.step_deps) if d)
+        # the plan's own order: what really runs (ties of keep_budget_bytes included); another order: the dependencies
+        deps = self.run_deps if bond_order is None else self.step_deps
+        amortised = sum(c * 2.0 ** -min(bit[b] for b in d) for c, d in zip(cost, deps) if d)
         return {"full_s": full, "amortised_s": amortised}
 
     def work_summary(self):

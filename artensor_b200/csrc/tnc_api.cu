@@ -393,6 +393,8 @@ int tnc_plan_add_accum(tnc_plan* plan, int32_t phase, const tnc_accum* a) {
 // TNC_OPT_SLICE_REUSE: the slice-id bits behind every slice-phase operation, and the check of what the option asks
 // of the caller's layout -- a result that is read by an operation depending on MORE bits is read again in later
 // slices without being recomputed, so no other operation of the phase may ever write over it.
+static inline uint64_t lowest_bit(uint64_t deps) { return deps & (~deps + 1); }
+
 static int plan_slice_deps(tnc_plan* plan) {
     auto& ops = plan->ops[TNC_PHASE_SLICE];
     struct Range {
@@ -422,6 +424,23 @@ static int plan_slice_deps(tnc_plan* plan) {
             at[op.p.dst.offset] = op.deps;
         }
     }
+    // the reader of an operation's result: the first later operation that takes a tensor at its offset
+    auto reader_of = [&](size_t i, const tnc_tensor& out) -> const Op* {
+        for (size_t j = i + 1; j < ops.size(); ++j) {
+            const Op& y = ops[j];
+            if ((y.kind == OP_EINSUM && (y.e.a.offset == out.offset || y.e.b.offset == out.offset)) ||
+                (y.kind == OP_PERMUTE && y.p.src.offset == out.offset) || (y.kind == OP_ACCUM && y.a.src.offset == out.offset))
+                return &y;
+        }
+        return nullptr;
+    };
+    // TNC_EINSUM_RUN_WITH_READER: such an operation runs whenever its reader does (readers come later: backwards)
+    for (size_t i = ops.size(); i-- > 0;) {
+        Op& x = ops[i];
+        if (x.kind != OP_EINSUM || !(x.e.flags & TNC_EINSUM_RUN_WITH_READER)) continue;
+        const Op* y = reader_of(i, x.e.c);
+        x.deps = y ? y->deps : every;
+    }
     // everything an operation writes
     auto writes_of = [&](const Op& op, std::vector<Range>& out) {
         out.clear();
@@ -442,19 +461,11 @@ static int plan_slice_deps(tnc_plan* plan) {
         const Op& x = ops[i];
         if (x.kind != OP_EINSUM && x.kind != OP_PERMUTE) continue;
         const tnc_tensor& out = x.kind == OP_EINSUM ? x.e.c : x.p.dst;
-        // the reader: the first later operation that takes a tensor at this offset
-        uint64_t reader = x.deps;
-        for (size_t j = i + 1; j < ops.size(); ++j) {
-            const Op& y = ops[j];
-            const bool reads = (y.kind == OP_EINSUM && (y.e.a.offset == out.offset || y.e.b.offset == out.offset)) ||
-                               (y.kind == OP_PERMUTE && y.p.src.offset == out.offset) ||
-                               (y.kind == OP_ACCUM && y.a.src.offset == out.offset);
-            if (reads) {
-                reader = y.deps;
-                break;
-            }
-        }
-        if (reader == x.deps) continue;                     // recomputed whenever it is read
+        // Consecutive slice ids flip the bits 0 .. ctz(s): an operation runs exactly when its LOWEST bit is among them,
+        // so two operations run on the same slices iff their lowest bits agree.
+        const Op* y = reader_of(i, out);
+        const uint64_t reader = y ? y->deps : x.deps;
+        if (lowest_bit(reader) == lowest_bit(x.deps)) continue;     // recomputed whenever it is read
         const Range r = range_of(out);
         for (size_t j = 0; j < ops.size(); ++j) {
             if (j == i) continue;
@@ -552,7 +563,8 @@ int tnc_plan_finalize(tnc_plan* plan, int64_t arena_bytes) {
         auto& ops = plan->ops[ph];
         for (size_t i = 0; i < ops.size();) {
             size_t j = i;
-            while (j < ops.size() && chainable(ops[j]) && (!plan->slice_reuse || ops[j].deps == ops[i].deps)) ++j;
+            while (j < ops.size() && chainable(ops[j]) &&
+                   (!plan->slice_reuse || lowest_bit(ops[j].deps) == lowest_bit(ops[i].deps))) ++j;
             if (j - i >= 2) {
                 std::vector<ChainStep> recs;
                 for (size_t t = i; t < j; ++t) {

@@ -112,6 +112,10 @@ typedef enum tnc_algo {
  * into M and B's rows into N, and scatters the row blocks of C through the inverse of the tables;
  * without the flag the same step gathers a.rows * b.rows copies of the operand rows. */
 #define TNC_EINSUM_OUTER_PAIRS 2
+/* RUN_WITH_READER (only read with TNC_OPT_SLICE_REUSE): the operation's result is not preserved across slices --
+ * it runs whenever the operation that reads its result runs (instead of only when a sliced bond behind its own
+ * operands changed), so its result needs no memory of its own.  Trades recomputation for workspace. */
+#define TNC_EINSUM_RUN_WITH_READER 4
 
 /* Row table ids: a plan-owned int32 table (tnc_plan_add_table) or one of these. */
 #define TNC_ROWS_NONE (-1)       /* operand has no row mode: always block 0 */

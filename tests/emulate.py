@@ -39,6 +39,19 @@ def slice_deps(plan):
             d = at.get(rec.src.offset, 0)
             at[rec.dst.offset] = d
         deps.append(d)
+    # TNC_EINSUM_RUN_WITH_READER: such an operation runs whenever the (later) operation that reads its result does
+    ops = plan.ops[N.TNC_PHASE_SLICE]
+    for n in range(len(ops) - 1, -1, -1):
+        kind, rec = ops[n]
+        if kind != "einsum" or not (rec.flags & N.TNC_EINSUM_RUN_WITH_READER):
+            continue
+        deps[n] = (1 << S) - 1
+        for m in range(n + 1, len(ops)):
+            k2, r2 = ops[m]
+            if (k2 == "einsum" and rec.c.offset in (r2.a.offset, r2.b.offset)) or \
+               (k2 == "permute" and r2.src.offset == rec.c.offset) or (k2 == "accum" and r2.src.offset == rec.c.offset):
+                deps[n] = deps[m]
+                break
     return deps
 
 

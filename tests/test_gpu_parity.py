@@ -253,24 +253,29 @@ def test_slice_reuse_is_bit_identical(dev, name, ranges):
     from artensor_b200 import PlanOptions, ContractionPlan
     case, exp, sim = sim_from(name)
     shapes = {k: tuple(v.shape) for k, v in case.leaves.items()}
-    mk = lambda r: ContractionPlan(case.scheme, shapes, case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
-                                   slicing_indices=case.slicing_indices(), options=PlanOptions(slice_reuse=r, cuda_graph=False))
+    mk = lambda r, b=None: ContractionPlan(case.scheme, shapes, case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
+                                           slicing_indices=case.slicing_indices(),
+                                           options=PlanOptions(slice_reuse=r, cuda_graph=False, keep_budget_bytes=b))
     full, reuse = mk(False), mk(True)
     assert reuse.slice_reuse and not full.slice_reuse
+    # a KEEP budget ties steps to their readers (TNC_EINSUM_RUN_WITH_READER): less memory, more recomputation, same bits
+    tight = [mk(True, reuse.keep_bytes // 4), mk(True, 0)]
+    assert tight[0].keep_bytes <= reuse.keep_bytes // 4 and sum(tight[0].step_tied) > 0 and tight[1].keep_bytes == 0
     blob = full.pack_leaves({k: v.to(dev) for k, v in case.leaves.items()})
     st = torch.cuda.current_stream().cuda_stream
     n = full.n_slices
     wf = torch.empty(full.workspace_bytes, dtype=torch.uint8, device=dev)
-    wr = torch.empty(reuse.workspace_bytes, dtype=torch.uint8, device=dev)
+    wr = torch.empty(max(p.workspace_bytes for p in [reuse] + tight), dtype=torch.uint8, device=dev)
     for lo, hi in (ranges or [(0, n)]):
         outs = []
-        for plan, ws in ((full, wf), (reuse, wr)):
+        for plan, ws in ((full, wf), (reuse, wr), (tight[0], wr), (tight[1], wr)):
             ws.fill_(0xff)                                  # whatever the workspace held must not matter (NaN patterns)
             out = torch.zeros(plan.out_shape, dtype=torch.complex64, device=dev)
             plan.execute(blob, out, lo, hi, ws, st)
             torch.cuda.synchronize()
             outs.append((out, plan.last_launches))
-        assert torch.equal(outs[0][0], outs[1][0]), f"slices [{lo}, {hi})"
+        for k in range(1, len(outs)):
+            assert torch.equal(outs[0][0], outs[k][0]), f"slices [{lo}, {hi}), plan {k}"
         if name.startswith("n53") and hi - lo >= 8:
             # (tiny n12 steps run as chains of steps with IDENTICAL dependencies under reuse: more, smaller launches)
             assert outs[1][1] < 0.7 * outs[0][1], "reuse skipped nothing"
@@ -1025,26 +1030,31 @@ def test_n53_m20_tuned_tree_sc31_vs_reference(dev):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("name,n_sliced", [("n53_m20_sparse1024_sc30_s2", 42), ("n53_m20_sparse1024_sc31_s2", 40),
-                                           ("n53_m20_sparse1024_sc31_s20", 37)])
-def test_n53_m20_trees_picked_for_slice_reuse(dev, name, n_sliced):
-    """SURVEY.md 8-f4 x 8-f2: trees of the reference's annealer picked by their AMORTISED cost under cross-slice
-    reuse (tools/order_search_sweep.py prices every tree with artensor_b200's step-time model and the reuse bit
-    order).  One slice against the recorded output -- sc30_s2, sc31_s20: the REFERENCE executor run
-    in the build container; sc31_s2 (2^31-amplitude intermediates, 110 GiB arena): the CPU oracle run on the GPU box's
-    host, where the same slice was also checked against the oracle in complex128 (profiles/r02_slice_reuse.txt) --
-    and three consecutive slices of the reuse-ordered plan, one call against one call per slice, bit for bit."""
+@pytest.mark.parametrize("name,n_sliced,keep_gib", [("n53_m20_sparse1024_sc30_s2", 42, None), ("n53_m20_sparse1024_sc31_s2", 40, None),
+                                                    ("n53_m20_sparse1024_sc31_s20", 37, None), ("n53_m20_sparse1024_sc32_s20", 35, 50)])
+def test_n53_m20_trees_picked_for_slice_reuse(dev, name, n_sliced, keep_gib):
+    """SURVEY.md 8-f4 x 8-f2: trees of the reference's annealer picked by their modelled cost for the whole task, slice by
+    slice and amortised under cross-slice reuse (tools/order_search_sweep.py).  One slice against the
+    recorded output -- sc30_s2, sc31_s20: the REFERENCE executor run in the build container; sc31_s2 (2^31-amplitude
+    intermediates, 110 GiB arena) and sc32_s20 (2^32, 155 GiB; reuse only under a 50 GiB KEEP budget, i.e. with steps tied
+    to their readers): the CPU oracle run on the GPU box's host, sc31_s2 also against the oracle in complex128
+    (profiles/r02_slice_reuse.txt) -- and three consecutive slices of the reuse-ordered plan, one call against one call
+    per slice."""
     from artensor_b200 import PlanOptions, contraction as _c
     case, exp, sim = sim_from(name)
     assert len(case.slicing_bonds) == n_sliced
     free, _ = torch.cuda.mem_get_info(dev)
-    sim.plan_options = PlanOptions(slice_reuse=True)
+    sim.plan_options = PlanOptions(slice_reuse=True, keep_budget_bytes=None if keep_gib is None else keep_gib << 30)
     if sim.plan().workspace_bytes > free - (6 << 30):
         pytest.skip(f"needs {sim.plan().workspace_bytes >> 30} GiB of free HBM")
     s = int(exp["slice_ids"][0])
-    got = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()
+    got = sim.contraction(device=dev, slice_range=(s, s + 1)).cpu().numpy()      # the reference's slice ids
     assert_amplitudes_close(got, exp["per_slice_c64"][0])
+    _c.release_workspaces()
+    torch.cuda.empty_cache()
     sim.optimize_slice_order()
+    if sim.plan().workspace_bytes > free - (6 << 30):
+        pytest.skip(f"needs {sim.plan().workspace_bytes >> 30} GiB of free HBM")
     one_call = sim.contraction(device=dev, slice_range=(5, 8))
     per_slice = sum(sim.contraction(device=dev, slice_range=(k, k + 1)) for k in range(5, 8))
     assert torch.equal(one_call, sim.contraction(device=dev, slice_range=(5, 8)))

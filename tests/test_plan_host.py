@@ -76,6 +76,33 @@ def test_slice_reuse_is_bit_identical_to_recomputing_every_slice(name, hoist):
         assert np.array_equal(got, want), f"slices [{lo}, {hi})"
 
 
+@pytest.mark.parametrize("name", ["n12_sparse64_sc9", "n12_sparse256c_sc10"])
+def test_slice_reuse_with_a_keep_budget(name):
+    """PlanOptions.keep_budget_bytes: when the results that must outlive a slice exceed the budget, steps are TIED to
+    their reader (TNC_EINSUM_RUN_WITH_READER: they run whenever the reader does, their result recycles).  Every budget
+    down to zero must give the bit-identical sum (emulator with all recycled memory poisoned after every slice), the
+    KEEP region must respect the budget, and the modelled cost must grow monotonically towards contracting every step
+    for every slice."""
+    case, _ = load_golden(name)
+    n = 1 << len(case.slicing_bonds)
+    full = make_plan(case)
+    free = make_plan(case, options=PlanOptions(slice_reuse=True))
+    blob = free.pack_leaves(case.leaves).numpy()
+    lo, hi = 3, min(n, 40)
+    want = emulate.run_plan(full, blob, range(lo, hi))
+    last = free.reuse_summary()["amortised_s"]
+    for budget in (free.keep_bytes, free.keep_bytes // 2, free.keep_bytes // 8, 0):
+        plan = make_plan(case, options=PlanOptions(slice_reuse=True, keep_budget_bytes=budget))
+        assert plan.keep_bytes <= max(budget, 0) or budget >= free.keep_bytes
+        assert (sum(plan.step_tied) > 0) == (budget < free.keep_bytes)
+        cost = plan.reuse_summary()
+        assert cost["amortised_s"] >= last * (1 - 1e-12) and cost["amortised_s"] <= cost["full_s"] * (1 + 1e-12)
+        last = cost["amortised_s"]
+        got = emulate.run_plan(plan, blob, range(lo, hi), reuse=True, poison=True)
+        assert np.array_equal(got, want), f"budget {budget}"
+    assert plan.keep_bytes == 0 and abs(last - cost["full_s"]) <= 1e-9 * cost["full_s"]      # budget 0: nothing is reused
+
+
 def test_slice_reuse_layout_check_of_the_library():
     """tnc_plan_finalize checks what TNC_OPT_SLICE_REUSE asks of the layout on the host, before its first CUDA
     call: the planner's layout passes it (on a machine without a GPU finalize then fails in cudaMalloc: status
@@ -86,8 +113,8 @@ def test_slice_reuse_layout_check_of_the_library():
     case, _ = load_golden("n12_sparse64_sc9")
     shapes = {k: tuple(v.shape) for k, v in case.leaves.items()}
 
-    def finalize_status(layout_reuse):
-        plan = make_plan(case, options=PlanOptions(slice_reuse=layout_reuse))
+    def finalize_status(layout_reuse, budget=None):
+        plan = make_plan(case, options=PlanOptions(slice_reuse=layout_reuse, keep_budget_bytes=budget))
         plan.slice_reuse = True                  # the option the library sees
         try:
             plan._build_native(plan.ops)
@@ -97,6 +124,10 @@ def test_slice_reuse_layout_check_of_the_library():
     ok = finalize_status(True)
     assert ok == (0 if torch.cuda.is_available() else 2)
     assert finalize_status(False) == 1
+    # with a keep budget the planner ties steps to their readers (TNC_EINSUM_RUN_WITH_READER): the library derives the
+    # same run conditions from the flags and accepts the smaller KEEP region
+    for budget in (8192, 0):
+        assert finalize_status(True, budget) == ok
 
 
 def test_work_summary_counts():

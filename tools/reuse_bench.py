@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--check", type=int, default=4, help="slices compared bit for bit with full recomputation")
     ap.add_argument("--begin", type=int, default=0)
     ap.add_argument("--orders", default="reference,optimised")
+    ap.add_argument("--keep-budget-gib", type=float, default=None, help="PlanOptions.keep_budget_bytes of the reuse plan")
+    ap.add_argument("--no-plain", action="store_true", help="skip the plan without reuse (large arenas)")
     a = ap.parse_args()
     case = load_case(os.path.join(ROOT, "tests", "golden", f"{a.case}.case.gz"))
     dev = torch.device("cuda:0")
@@ -45,14 +47,17 @@ def main():
             model = sim.optimize_slice_order()
         plans = {}
         for reuse in (False, True):
-            sim.plan_options = PlanOptions(slice_reuse=reuse, cuda_graph=False)
+            budget = None if a.keep_budget_gib is None else int(a.keep_budget_gib * 2 ** 30)
+            sim.plan_options = PlanOptions(slice_reuse=reuse, cuda_graph=False, keep_budget_bytes=budget if reuse else None)
             sim._plan_cache.clear()
             plans[reuse] = sim.plan()
         n = plans[True].n_slices
         blob = plans[True].pack_leaves(case.leaves, device=dev)
         ws = torch.empty(max(p.workspace_bytes for p in plans.values()), dtype=torch.uint8, device=dev)
         print(f"{a.case} [{order} bit order]: {n.bit_length() - 1} sliced bonds, workspace {plans[False].workspace_bytes / 2**30:.2f} GiB "
-              f"-> {plans[True].workspace_bytes / 2**30:.2f} GiB with reuse" + (f"; model {model}" if model else ""), flush=True)
+              f"-> {plans[True].workspace_bytes / 2**30:.2f} GiB with reuse (KEEP {plans[True].keep_bytes / 2**30:.2f} GiB, "
+              f"{sum(plans[True].step_tied)} steps tied to their reader; modelled {plans[True].reuse_summary()['amortised_s'] * 1e3:.2f} ms per slice)"
+              + (f"; model {model}" if model else ""), flush=True)
         timed(plans[False], blob, ws, a.begin, a.begin + 1)                      # warm-up
         ms_full, _, l_full = timed(plans[False], blob, ws, a.begin, a.begin + 2)
         print(f"   every step for every slice: {ms_full / 2:9.3f} ms per slice, {l_full // 2} launches per slice", flush=True)
