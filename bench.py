@@ -670,6 +670,11 @@ def main():
                 C.release_workspaces()
                 torch.cuda.empty_cache()
                 free_b, _ = torch.cuda.mem_get_info(dev)
+                if rplan.workspace_bytes > free_b - (4 << 30):
+                    # bound the KEEP region: steps are tied to their readers until the workspace fits
+                    budget = max(0, free_b - (6 << 30) - (rplan.workspace_bytes - rplan.keep_bytes))
+                    rsim.plan_options = PlanOptions(**dict(opt_kw, slice_reuse=True, cuda_graph=False, keep_budget_bytes=budget))
+                    rplan = rsim.plan()
                 if rplan.workspace_bytes > free_b - (2 << 30):
                     problem = f"workspace with reuse {rplan.workspace_bytes >> 30} GiB > free HBM {free_b >> 30} GiB"
             except Exception as exc:
@@ -698,7 +703,8 @@ def main():
             reuse = {"value": world * R / (rms * 1e-3), "unit": UNIT, "slices_per_call_per_gpu": R,
                      "ms_per_slice_per_gpu": rms / R, "launches_per_slice": rplan.last_launches / R,
                      "bit_order": "sliced bonds re-ordered by TensorNetworkSimulation.optimize_slice_order",
-                     "workspace_gib": rplan.workspace_bytes / 2 ** 30,
+                     "workspace_gib": rplan.workspace_bytes / 2 ** 30, "keep_gib": rplan.keep_bytes / 2 ** 30,
+                     "steps_tied_to_their_reader": int(sum(rplan.step_tied)),
                      "modelled_ms_per_slice": {"every_step": model["full_s"] * 1e3,
                                                "reuse_reference_bit_order": model["amortised_before_s"] * 1e3,
                                                "reuse": model["amortised_s"] * 1e3},
