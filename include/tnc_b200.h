@@ -86,9 +86,13 @@ typedef enum tnc_option {
                                     the previous slice id (the library derives the dependencies from the leaf records).
                                     The reference's loop (simulation.py:107-114) recomputes the whole tree per slice;
                                     most of a deep tree depends on few of the sliced bonds.  Results are bit-identical.
+                                    Slice ids are walked in ascending order, so going from s - 1 to s changes the
+                                    slice-id bits 0 .. ctz(s): an operation runs when the LOWEST bit behind it is among
+                                    them (or, with TNC_EINSUM_RUN_WITH_READER, whenever its reader runs).
                                     Asks of the caller's layout, checked at finalize (TNC_ERR_INVALID): the result of
-                                    an operation whose reader depends on MORE sliced bonds is read again in later
-                                    slices, so no other operation of the phase may write over it (tensor or scratch).
+                                    an operation whose reader runs on other slices than it does (their lowest bits
+                                    differ) is read again in later slices, so no other operation of the phase may write
+                                    over it (tensor or scratch).
                                     Excludes TNC_OPT_CUDA_GRAPH replay (plain launches are used).  Default 0. */
 } tnc_option;
 
