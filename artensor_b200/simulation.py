@@ -166,11 +166,11 @@ class TensorNetworkSimulation(_Base):
                     if reuse:
                         order = probe.reuse_bond_order()
                         bonds = [self.slicing_bonds[i] for i in order]
-                        per_slice = probe.reuse_summary(order)["amortised_s"]
                         probe = _c.ContractionPlan(self.scheme, {i: tuple(self.tensors[i].shape) for i in self._ids()},
                                                    self.pattern == 'sparse', slicing_bonds=bonds,
                                                    slicing_indices=slicing_dims(self.tensors, self.tensor_bonds, bonds),
                                                    dtype="c64", options=options, build_native=False)
+                        per_slice = probe.reuse_summary()["amortised_s"]      # what really runs (ties of a KEEP budget included)
                     else:
                         per_slice = probe.reuse_summary()["full_s"]
                     r = {"sc_target": sc, "alpha": alpha, "start_seed": seed, "sliced_bonds": probe.n_sliced,
