@@ -103,6 +103,46 @@ def test_slice_reuse_with_a_keep_budget(name):
     assert plan.keep_bytes == 0 and abs(last - cost["full_s"]) <= 1e-9 * cost["full_s"]      # budget 0: nothing is reused
 
 
+@pytest.mark.parametrize("name", ["n53_m12_sparse1024", "n53_m20_sparse1024"])
+def test_keep_planning_invariants_on_the_n53_trees(name):
+    """The planner's KEEP decisions on the big trees (host only): every slice-phase result is either kept or runs
+    exactly when its reader does (equal lowest slice-id bits of their run dependencies); run dependencies contain the
+    step's own; a budget is respected, ties only ever ADD modelled time, and the library's own finalize check accepts
+    the layout (it fails later, in cudaMalloc, on a machine without a GPU)."""
+    import torch
+    from artensor_b200 import _native as N
+    case, _ = load_golden(name)
+    S = len(case.slicing_bonds)
+    free = make_plan(case, options=PlanOptions(slice_reuse=True))
+    low = lambda d: min((S - 1 - b for b in d), default=None)
+    for budget in (None, free.keep_bytes // 3, 0):
+        plan = make_plan(case, options=PlanOptions(slice_reuse=True, keep_budget_bytes=budget))
+        every = frozenset(range(S))
+        kept_bytes = 0
+        for i, st in enumerate(plan.steps):
+            c = plan._consumer_of[i]
+            reader = plan.run_deps[c] if c is not None else every
+            assert plan.step_deps[i] <= plan.run_deps[i]
+            if plan.step_phase[i] != N.TNC_PHASE_SLICE:
+                continue
+            if low(plan.run_deps[i]) != low(reader):
+                kept_bytes += max(1024, (st.c.numel * 8 + 1023) // 1024 * 1024)
+            if plan.step_tied[i]:
+                assert plan.run_deps[i] == reader
+        assert kept_bytes == plan.keep_bytes
+        if budget is not None:
+            assert plan.keep_bytes <= budget
+        cost = plan.reuse_summary()
+        assert free.reuse_summary()["amortised_s"] * (1 - 1e-12) <= cost["amortised_s"] <= cost["full_s"] * (1 + 1e-12)
+        plan.slice_reuse = True
+        try:
+            plan._build_native(plan.ops)
+            status = 0
+        except N.NativeError as e:
+            status = e.status
+        assert status == (0 if torch.cuda.is_available() else 2), budget
+
+
 def test_slice_reuse_layout_check_of_the_library():
     """tnc_plan_finalize checks what TNC_OPT_SLICE_REUSE asks of the layout on the host, before its first CUDA
     call: the planner's layout passes it (on a machine without a GPU finalize then fails in cudaMalloc: status
