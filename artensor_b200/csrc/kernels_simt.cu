@@ -88,13 +88,17 @@ __global__ void __launch_bounds__(kThreads) simt_einsum_kernel(SimtEinsumParams 
 // K alone with uncoalesced loads; here one CTA owns an output row, its threads split K (consecutive
 // threads take consecutive k: the contracted bits are ordered by their position in A, so the loads
 // of A are coalesced), every thread keeps all 2^RC partial sums, and the CTA reduces them.
-constexpr int kRowdotThreads = 128;
+// THREADS per CTA: 128 when there are many rows (many CTAs per SM stream together); 256 for a few hundred rows with a
+// very long contraction -- one 128-thread CTA per row would leave ~7 warps per SM, far too few loads in flight for
+// HBM (n53 m20 sc31_s20 tree: [256 rows][3 bits][19 bits] x [256][19 bits][2 bits], 12.9 GB: 2.0 -> 3.4-3.7 TB/s
+// inside a slice; 512 threads measured the same to -8 %, and 64 outputs per row do not fit their 128 registers).
 // NM / NN: left-only / right-only output bits (NM + NN <= 4, or NM, NN <= 3: up to 64 outputs per row --
 // the batched tail of a deep sparse scheme, e.g. [512 rows][3 bits][19 bits] x [512][19 bits][3 bits] in the
 // sc_target-32 n53 tree: 34 GB streamed once; the generic kernel ran it at 0.2 TB/s); no shared kept modes
-template <int NM, int NN>
-__global__ void __launch_bounds__(kRowdotThreads) simt_rowdot_kernel(SimtEinsumParams p) {
+template <int NM, int NN, int THREADS>
+__global__ void __launch_bounds__(THREADS) simt_rowdot_kernel(SimtEinsumParams p) {
     constexpr int M = 1 << NM, NQ = 1 << NN, RC = NM + NN;
+    constexpr int kRowdotThreads = THREADS;
     __shared__ float2 part[kRowdotThreads / 32][M * NQ];
     const float2* __restrict__ A = (const float2*)p.a;
     const float2* __restrict__ B = (const float2*)p.b;
@@ -231,22 +235,32 @@ __global__ void __launch_bounds__(kRowdotThreads) simt_rowdot_kernel(SimtEinsumP
 // (nm, nn) combinations compiled: nm + nn <= 4, and every nm, nn <= 3
 constexpr bool rowdot_shape(int nm, int nn) { return nm >= 0 && nn >= 0 && (nm + nn <= 4 || (nm <= 3 && nn <= 3)); }
 
-template <int NM>
+template <int NM, int THREADS>
 void launch_rowdot_n(const SimtEinsumParams& p, int nn, int grid, cudaStream_t s) {
-    if constexpr (rowdot_shape(NM, 0)) {
-        if (nn == 0) simt_rowdot_kernel<NM, 0><<<grid, kRowdotThreads, 0, s>>>(p);
+    if constexpr (rowdot_shape(NM, 0) && (THREADS < 512 || NM + 0 <= 5)) {
+        if (nn == 0) simt_rowdot_kernel<NM, 0, THREADS><<<grid, THREADS, 0, s>>>(p);
     }
-    if constexpr (rowdot_shape(NM, 1)) {
-        if (nn == 1) simt_rowdot_kernel<NM, 1><<<grid, kRowdotThreads, 0, s>>>(p);
+    if constexpr (rowdot_shape(NM, 1) && (THREADS < 512 || NM + 1 <= 5)) {
+        if (nn == 1) simt_rowdot_kernel<NM, 1, THREADS><<<grid, THREADS, 0, s>>>(p);
     }
-    if constexpr (rowdot_shape(NM, 2)) {
-        if (nn == 2) simt_rowdot_kernel<NM, 2><<<grid, kRowdotThreads, 0, s>>>(p);
+    if constexpr (rowdot_shape(NM, 2) && (THREADS < 512 || NM + 2 <= 5)) {
+        if (nn == 2) simt_rowdot_kernel<NM, 2, THREADS><<<grid, THREADS, 0, s>>>(p);
     }
-    if constexpr (rowdot_shape(NM, 3)) {
-        if (nn == 3) simt_rowdot_kernel<NM, 3><<<grid, kRowdotThreads, 0, s>>>(p);
+    if constexpr (rowdot_shape(NM, 3) && (THREADS < 512 || NM + 3 <= 5)) {
+        if (nn == 3) simt_rowdot_kernel<NM, 3, THREADS><<<grid, THREADS, 0, s>>>(p);
     }
-    if constexpr (rowdot_shape(NM, 4)) {
-        if (nn == 4) simt_rowdot_kernel<NM, 4><<<grid, kRowdotThreads, 0, s>>>(p);
+    if constexpr (rowdot_shape(NM, 4) && (THREADS < 512 || NM + 4 <= 5)) {
+        if (nn == 4) simt_rowdot_kernel<NM, 4, THREADS><<<grid, THREADS, 0, s>>>(p);
+    }
+}
+template <int THREADS>
+void launch_rowdot(const SimtEinsumParams& p, int nm, int nn, int grid, cudaStream_t s) {
+    switch (nm) {
+        case 0: launch_rowdot_n<0, THREADS>(p, nn, grid, s); break;
+        case 1: launch_rowdot_n<1, THREADS>(p, nn, grid, s); break;
+        case 2: launch_rowdot_n<2, THREADS>(p, nn, grid, s); break;
+        case 3: launch_rowdot_n<3, THREADS>(p, nn, grid, s); break;
+        default: launch_rowdot_n<4, THREADS>(p, nn, grid, s); break;
     }
 }
 
@@ -395,14 +409,13 @@ int launch_simt_einsum(const SimtEinsumParams& p, int dtype, cudaStream_t s) {
             else ++nn;
         }
         if (dtype == TNC_C64 && simt_uses_rowdot(p.rank_c, p.kb, p.total, nm, nn, nh)) {
-            const int grid = (int)std::min<int64_t>(p.total >> p.rank_c, (int64_t)sm_count() * 16);
-            switch (nm) {
-                case 0: launch_rowdot_n<0>(p, nn, grid, s); break;
-                case 1: launch_rowdot_n<1>(p, nn, grid, s); break;
-                case 2: launch_rowdot_n<2>(p, nn, grid, s); break;
-                case 3: launch_rowdot_n<3>(p, nn, grid, s); break;
-                default: launch_rowdot_n<4>(p, nn, grid, s); break;
-            }
+            const int64_t rows = p.total >> p.rank_c;
+            const int grid = (int)std::min<int64_t>(rows, (int64_t)sm_count() * 16);
+            // few rows x a very long contraction: wide CTAs (the number of CTAs is bounded by the rows)
+            // (64 outputs per row: 128 accumulator registers -- 256 threads, which may use up to 255 registers each)
+            static const int forced = knob("TNC_ROWDOT_THREADS") ? atoi(knob("TNC_ROWDOT_THREADS")) : 0;   // experiment knob
+            if (rows < (int64_t)sm_count() * 8 && p.kb >= 12 && forced != 128) launch_rowdot<256>(p, nm, nn, grid, s);
+            else launch_rowdot<128>(p, nm, nn, grid, s);
             TNC_CUDA(cudaGetLastError());
             return TNC_OK;
         }

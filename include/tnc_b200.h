@@ -256,6 +256,7 @@ const char* tnc_last_error(void);
  *   TNC_STEM_BULK_CTAS=<2|3>  resident CTAs per SM of the bulk-copy streaming kernel
  *   TNC_NO_CHAIN=1       one launch per tiny generic step instead of chained launches
  *   TNC_NO_ROWDOT=1      generic kernel instead of the row-dot kernel for long contractions
+ *   TNC_ROWDOT_THREADS=128  narrow CTAs of the row-dot kernel also for few rows x a very long contraction
  */
 
 #ifdef __cplusplus
