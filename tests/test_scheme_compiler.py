@@ -316,3 +316,11 @@ def test_open_qubit_shards_concatenate_to_the_full_state(n_regular, n_bits):
     assert (got - full).abs().max().item() < 1e-12 * full.abs().max().item()
     with pytest.raises(ValueError):
         sim.prepare_open_qubit_shards(1)                            # already sharded
+    # the reuse bit order leaves the shard bonds where they are (most significant: a shard stays a contiguous slice
+    # range) and permutes the regular sliced bonds only -- every shard's sum over its slices is unchanged
+    before = list(sim.slicing_bonds)
+    sim.optimize_slice_order()
+    assert sim.slicing_bonds[:n_bits] == before[:n_bits] and sorted(sim.slicing_bonds[n_bits:]) == sorted(before[n_bits:])
+    for v in (0, (1 << n_bits) - 1):
+        again = contract(range(v * per_shard, (v + 1) * per_shard))
+        assert (again - blocks[v]).abs().max().item() < 1e-12 * full.abs().max().item()
