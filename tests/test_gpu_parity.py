@@ -277,7 +277,7 @@ def test_slice_reuse_is_bit_identical(dev, name, ranges):
         for k in range(1, len(outs)):
             assert torch.equal(outs[0][0], outs[k][0]), f"slices [{lo}, {hi}), plan {k}"
         if name.startswith("n53") and hi - lo >= 8:
-            # (tiny n12 steps run as chains of steps with IDENTICAL dependencies under reuse: more, smaller launches)
+            # (tiny n12 steps are chained only with steps that run on the same slices under reuse: more, smaller launches)
             assert outs[1][1] < 0.7 * outs[0][1], "reuse skipped nothing"
 
 
