@@ -86,8 +86,10 @@ struct tnc_plan {
     std::mutex graph_mu;
     struct GraphKey {
         const void *ws, *blob, *out;
+        int cls;                          // -1: every operation; t >= 0 (slice reuse): the operations that run when the
+                                          // slice-id bits 0 .. t changed
         bool operator<(const GraphKey& o) const {
-            return ws != o.ws ? ws < o.ws : blob != o.blob ? blob < o.blob : out < o.out;
+            return ws != o.ws ? ws < o.ws : blob != o.blob ? blob < o.blob : out != o.out ? out < o.out : cls < o.cls;
         }
     };
     std::map<GraphKey, std::pair<cudaGraphExec_t, int64_t>> graphs;      // exec, launches per replay
@@ -842,58 +844,67 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
         if (rc != TNC_OK) return rc;
     }
     uint64_t s = slice_begin;
-    if (plan->use_graph && !plan->slice_reuse && !plan->graph_failed && slice_end - slice_begin >= 2) {
-        // Replay the slice phase as one CUDA graph per slice: the slice id lives in a workspace word that
-        // the leaf gather reads and the graph's last node increments.  Captured once per (workspace,
-        // leaf blob, accumulator); a capture that fails falls back to plain launches for good.
-        uint64_t* word = (uint64_t*)(ws + plan->workspace_bytes - 256);
-        tnc_plan::GraphKey key{workspace, leaf_blob, accum_out};
-        cudaGraphExec_t exec = nullptr;
-        int64_t per_replay = 0;
+    // Replay the slice phase as one CUDA graph per slice: the slice id lives in a workspace word that the leaf
+    // gather reads and the graph's last node increments.  Captured once per (workspace, leaf blob, accumulator[,
+    // class of changed bits]); a capture that fails falls back to plain launches for good.
+    uint64_t* const word = (uint64_t*)(ws + plan->workspace_bytes - 256);
+    // cls = -1: every operation of the phase; cls = t (slice reuse): what runs when the bits 0 .. t changed
+    auto graph_for = [&](int cls, int64_t* per_replay) -> cudaGraphExec_t {
+        tnc_plan::GraphKey key{workspace, leaf_blob, accum_out, cls};
         {
             std::lock_guard<std::mutex> lock(plan->graph_mu);
             auto it = plan->graphs.find(key);
             if (it != plan->graphs.end()) {
-                exec = it->second.first;
-                per_replay = it->second.second;
+                *per_replay = it->second.second;
+                return it->second.first;
             }
         }
-        if (!exec) {
-            // captured on a stream of its own (the caller's may be the legacy default stream, which cannot
-            // capture); nothing executes during capture, the graph is then launched on the caller's stream
-            cudaGraph_t graph = nullptr;
-            cudaStream_t cap = nullptr;
-            int rc = TNC_OK;
-            if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
-                cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-                rc = clear_amax_words(plan, TNC_PHASE_SLICE, ws, cap);
-                if (rc == TNC_OK)
+        // captured on a stream of its own (the caller's may be the legacy default stream, which cannot
+        // capture); nothing executes during capture, the graph is then launched on the caller's stream
+        const uint64_t mask = cls < 0 ? ~0ull : (cls >= 63 ? ~0ull : ((2ull << cls) - 1));
+        cudaGraphExec_t exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaStream_t cap = nullptr;
+        int64_t n = 0;
+        int rc = TNC_OK;
+        if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            if (cls < 0) rc = clear_amax_words(plan, TNC_PHASE_SLICE, ws, cap);
+            if (rc == TNC_OK)
                 for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
-                    rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, cap, &per_replay, nullptr, nullptr, word);
+                    if (cls >= 0 && (op.kind == OP_EINSUM || op.kind == OP_PERMUTE) && !(op.deps & mask)) continue;
+                    if (cls >= 0 && op.amax.out >= 0 && cudaMemsetAsync(ws + op.amax.out, 0, 4, cap) != cudaSuccess) rc = TNC_ERR_CUDA;
+                    if (rc == TNC_OK) rc = run_op(plan, op, leaf_blob, 0, accum_out, ws, cap, &n, nullptr, nullptr, word);
                     if (rc != TNC_OK) break;
                 }
-                if (rc == TNC_OK) rc = launch_slice_word(word, 1, true, cap);
-                ++per_replay;
-                const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
-                if (rc == TNC_OK && ce == cudaSuccess && graph &&
-                    cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)
-                    exec = nullptr;
-                if (graph) cudaGraphDestroy(graph);
-            }
-            if (cap) cudaStreamDestroy(cap);
-            if (!exec) {
-                cudaGetLastError();                      // clear the sticky capture error, if any
-                plan->graph_failed = true;
-            } else {
-                std::lock_guard<std::mutex> lock(plan->graph_mu);
-                auto ins = plan->graphs.emplace(key, std::make_pair(exec, per_replay));
-                if (!ins.second) {                       // another thread was faster
-                    cudaGraphExecDestroy(exec);
-                    exec = ins.first->second.first;
-                }
-            }
+            if (rc == TNC_OK) rc = launch_slice_word(word, 1, true, cap);
+            ++n;
+            const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+            if (rc == TNC_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)
+                exec = nullptr;
+            else if (rc != TNC_OK || ce != cudaSuccess)
+                exec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
         }
-        if (exec) {
+        if (cap) cudaStreamDestroy(cap);
+        if (!exec) {
+            cudaGetLastError();                      // clear the sticky capture error, if any
+            plan->graph_failed = true;
+            return nullptr;
+        }
+        std::lock_guard<std::mutex> lock(plan->graph_mu);
+        auto ins = plan->graphs.emplace(key, std::make_pair(exec, n));
+        if (!ins.second) {                           // another thread was faster
+            cudaGraphExecDestroy(exec);
+            exec = ins.first->second.first;
+            n = ins.first->second.second;
+        }
+        *per_replay = n;
+        return exec;
+    };
+    if (plan->use_graph && !plan->slice_reuse && !plan->graph_failed && slice_end - slice_begin >= 2) {
+        int64_t per_replay = 0;
+        if (cudaGraphExec_t exec = graph_for(-1, &per_replay)) {
             int rc = launch_slice_word(word, slice_begin, false, st);
             if (rc != TNC_OK) return rc;
             for (; s < slice_end; ++s) {
@@ -902,12 +913,32 @@ int tnc_plan_execute(tnc_plan* plan, const void* leaf_blob, uint64_t slice_begin
             }
         }
     }
+    if (plan->use_graph && plan->slice_reuse && !plan->graph_failed && slice_end - slice_begin >= 3) {
+        // slice reuse: the first slice of the call runs every operation (plain launches); slice s > begin flips the
+        // bits 0 .. ctz(s) and replays the graph of that class (at most n_sliced of them, captured on first use)
+        for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
+            if (op.amax.out >= 0) TNC_CUDA(cudaMemsetAsync(ws + op.amax.out, 0, 4, st));
+            int rc = run_op(plan, op, leaf_blob, s, accum_out, ws, st, &launches);
+            if (rc != TNC_OK) return rc;
+        }
+        ++s;
+        int rc = launch_slice_word(word, s, false, st);
+        if (rc != TNC_OK) return rc;
+        for (; s < slice_end; ++s) {
+            const int cls = __builtin_ctzll(s);
+            int64_t per_replay = 0;
+            cudaGraphExec_t exec = graph_for(cls, &per_replay);
+            if (!exec) break;                        // capture failed: the plain loop below takes over at slice s
+            TNC_CUDA(cudaGraphLaunch(exec, st));
+            launches += per_replay;
+        }
+    }
     for (; s < slice_end; ++s) {
         if (!plan->slice_reuse) {
             if (int rc = clear_amax_words(plan, TNC_PHASE_SLICE, ws, st)) return rc;
         }
         // slice reuse: after the first slice of the call, only what depends on a slice-id bit that changed
-        const bool all = s == slice_begin || !plan->slice_reuse;
+        const bool all = s == slice_begin || !plan->slice_reuse;      // (s > slice_begin after a failed graph capture: reuse rule)
         const uint64_t changed = s ^ (s - 1);
         for (auto& op : plan->ops[TNC_PHASE_SLICE]) {
             if (!all && (op.kind == OP_EINSUM || op.kind == OP_PERMUTE) && !(op.deps & changed)) continue;

@@ -93,7 +93,10 @@ typedef enum tnc_option {
                                     an operation whose reader runs on other slices than it does (their lowest bits
                                     differ) is read again in later slices, so no other operation of the phase may write
                                     over it (tensor or scratch).
-                                    Excludes TNC_OPT_CUDA_GRAPH replay (plain launches are used).  Default 0. */
+                                    With TNC_OPT_CUDA_GRAPH the first slice of a call runs as plain launches and every
+                                    later slice replays the graph of its class (the operations that run when the bits
+                                    0 .. ctz(s) changed; at most one graph per sliced bond, captured on first use).
+                                    Default 0. */
 } tnc_option;
 
 typedef enum tnc_algo {

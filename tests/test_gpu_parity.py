@@ -216,9 +216,11 @@ def test_cuda_graph_replay_of_the_slice_phase(dev, name):
     from artensor_b200 import PlanOptions, ContractionPlan
     case, exp, sim = sim_from(name)
     shapes = {k: tuple(v.shape) for k, v in case.leaves.items()}
-    mk = lambda g: ContractionPlan(case.scheme, shapes, case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
-                                   slicing_indices=case.slicing_indices(), options=PlanOptions(cuda_graph=g))
+    mk = lambda g, r=False: ContractionPlan(case.scheme, shapes, case.pattern == "sparse", slicing_bonds=case.slicing_bonds,
+                                            slicing_indices=case.slicing_indices(), options=PlanOptions(cuda_graph=g, slice_reuse=r))
     plain, graph = mk(False), mk(True)
+    both = mk(True, True)        # graph replay + cross-slice reuse: one graph per class of changed slice-id bits
+    assert both.cuda_graph and both.slice_reuse
     assert graph.cuda_graph and not plain.cuda_graph and graph.workspace_bytes == plain.workspace_bytes
     blob = plain.pack_leaves({k: v.to(dev) for k, v in case.leaves.items()})
     st = torch.cuda.current_stream().cuda_stream
@@ -231,10 +233,12 @@ def test_cuda_graph_replay_of_the_slice_phase(dev, name):
         return out
     wp = torch.empty(plain.workspace_bytes, dtype=torch.uint8, device=dev)
     wg = [torch.empty(graph.workspace_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    wb = torch.empty(both.workspace_bytes, dtype=torch.uint8, device=dev)
     for lo, hi in [(0, n), (1, n - 1), (n // 2, min(n, n // 2 + 3)), (0, n), (n - 2, n)]:
         want = run(plain, wp, lo, hi)
         for w in wg:
             assert torch.equal(run(graph, w, lo, hi), want), f"slices [{lo}, {hi})"
+        assert torch.equal(run(both, wb, lo, hi), want), f"graph + reuse, slices [{lo}, {hi})"
     assert graph.last_launches > 0
 
 

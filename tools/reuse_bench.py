@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--orders", default="reference,optimised")
     ap.add_argument("--keep-budget-gib", type=float, default=None, help="PlanOptions.keep_budget_bytes of the reuse plan")
     ap.add_argument("--no-plain", action="store_true", help="skip the plan without reuse (large arenas)")
+    ap.add_argument("--graph", action="store_true", help="TNC_OPT_CUDA_GRAPH as well: one graph per class of changed bits")
     a = ap.parse_args()
     case = load_case(os.path.join(ROOT, "tests", "golden", f"{a.case}.case.gz"))
     dev = torch.device("cuda:0")
@@ -48,7 +49,7 @@ def main():
         plans = {}
         for reuse in (False, True):
             budget = None if a.keep_budget_gib is None else int(a.keep_budget_gib * 2 ** 30)
-            sim.plan_options = PlanOptions(slice_reuse=reuse, cuda_graph=False, keep_budget_bytes=budget if reuse else None)
+            sim.plan_options = PlanOptions(slice_reuse=reuse, cuda_graph=bool(a.graph and reuse), keep_budget_bytes=budget if reuse else None)
             sim._plan_cache.clear()
             plans[reuse] = sim.plan()
         n = plans[True].n_slices
