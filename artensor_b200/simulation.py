@@ -260,6 +260,23 @@ class TensorNetworkSimulation(_Base):
         self._plan_cache.clear()
         return {"full_s": before["full_s"], "amortised_before_s": before["amortised_s"], "amortised_s": after["amortised_s"]}
 
+    def fit_reuse_to_memory(self, free_bytes, mode="c64", margin=6 << 30):
+        """With `plan_options.slice_reuse`: shrinks `plan_options.keep_budget_bytes` until the workspace of the plan
+        fits `free_bytes - margin` (tied results move into the recycled arena, so the budget may have to shrink more
+        than once).  Returns the plan; a budget of 0 (no reuse left) is the last resort."""
+        from dataclasses import replace
+        plan = self.plan(mode)
+        if not plan.slice_reuse:
+            return plan
+        budget = plan.keep_bytes if self.plan_options.keep_budget_bytes is None else self.plan_options.keep_budget_bytes
+        for _ in range(8):
+            if plan.workspace_bytes <= free_bytes - margin or budget == 0:
+                break
+            budget = max(0, budget - (plan.workspace_bytes - (free_bytes - margin)))
+            self.plan_options = replace(self.plan_options, keep_budget_bytes=budget)
+            plan = self.plan(mode)
+        return plan
+
     # ---- the hot path ----
     def plan(self, mode="c64"):
         """Compiled plan for a compute mode: "c64" (fp32-accurate) or "chalf" (reduced-precision

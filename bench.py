@@ -670,15 +670,8 @@ def main():
                 C.release_workspaces()
                 torch.cuda.empty_cache()
                 free_b, _ = torch.cuda.mem_get_info(dev)
-                budget = rplan.keep_bytes
-                for _ in range(6):
-                    if rplan.workspace_bytes <= free_b - (4 << 30) or budget == 0:
-                        break
-                    # bound the KEEP region: steps are tied to their readers until the workspace fits;
-                    # tied results move into the recycled arena, so the budget may have to shrink more than once
-                    budget = max(0, budget - (rplan.workspace_bytes - (free_b - (6 << 30))))
-                    rsim.plan_options = PlanOptions(**dict(opt_kw, slice_reuse=True, cuda_graph=False, keep_budget_bytes=budget))
-                    rplan = rsim.plan()
+                # bound the KEEP region if need be: steps are tied to their readers until the workspace fits
+                rplan = rsim.fit_reuse_to_memory(free_b)
                 if rplan.workspace_bytes > free_b - (2 << 30):
                     problem = f"workspace with reuse {rplan.workspace_bytes >> 30} GiB > free HBM {free_b >> 30} GiB"
             except Exception as exc:

@@ -143,6 +143,27 @@ def test_keep_planning_invariants_on_the_n53_trees(name):
         assert status == (0 if torch.cuda.is_available() else 2), budget
 
 
+def test_fit_reuse_to_memory_shrinks_the_keep_budget():
+    """TensorNetworkSimulation.fit_reuse_to_memory: the KEEP budget shrinks until the reuse plan's workspace fits the
+    free memory it is told about; with room to spare nothing is tied."""
+    from artensor_b200 import TensorNetworkSimulation
+    import artensor_b200.contraction as C
+    case, _ = load_golden("n53_m12_sparse1024")
+    sim = TensorNetworkSimulation.from_case(case)
+    sim.plan_options = PlanOptions(slice_reuse=True)
+    real = C.ContractionPlan
+    C.ContractionPlan = lambda *a, **k: real(*a, **dict(k, build_native=False))      # host-side planning only
+    try:
+        sim.optimize_slice_order()               # the reuse order keeps ~1.8 GiB of results across slices
+        roomy = sim.fit_reuse_to_memory(free_bytes=64 << 30)
+        assert sum(roomy.step_tied) == 0 and sim.plan_options.keep_budget_bytes is None
+        tight = sim.fit_reuse_to_memory(free_bytes=roomy.workspace_bytes - (1 << 29), margin=0)
+        assert tight.workspace_bytes <= roomy.workspace_bytes - (1 << 29) and sum(tight.step_tied) > 0
+        assert tight.keep_bytes < roomy.keep_bytes and sim.plan_options.keep_budget_bytes is not None
+    finally:
+        C.ContractionPlan = real
+
+
 def test_slice_reuse_layout_check_of_the_library():
     """tnc_plan_finalize checks what TNC_OPT_SLICE_REUSE asks of the layout on the host, before its first CUDA
     call: the planner's layout passes it (on a machine without a GPU finalize then fails in cudaMalloc: status
